@@ -14,7 +14,7 @@ HERE = Path(__file__).resolve().parent
 LIB_PATH = HERE / "libtb_oracle.so"
 
 ENV_SWING, ENV_HIT = 0, 1
-STATE_WORDS, INIT_WORDS, NUM_STATS = 32, 8, 8
+STATE_WORDS, INIT_WORDS, NUM_STATS = 32, 8, 10
 EV_RACKET_BALL, EV_COURT_BALL, EV_GOAL_BALL, EV_TIMEOUT, EV_BALL_PASSED, EV_NET_BALL, EV_RACKET_LOW = 1, 2, 4, 8, 16, 32, 64
 ENV_KINDS = {"SwingRacket-v0": ENV_SWING, "Tennisbot-v0": ENV_HIT, "swing": ENV_SWING, "hit": ENV_HIT}
 

@@ -755,6 +755,8 @@ static void env_step_one(tbo_ctx *c, int64_t i, const float *act, float *obs, fl
   pack_obs(c, s, ob);
   if (obs64) memcpy(obs64, ob, od * sizeof(double));
   *nphys += o.nphys;
+  stats[8] += o.nphys;
+  stats[9] += 1;
   stats[2] += o.hit_steps;
   if (o.done) {
     stats[0] += 1;
@@ -989,9 +991,9 @@ int tbo_set_state(tbo_ctx *c, const double *state) {
   memcpy(c->state, state, (size_t)c->n * TBO_STATE_WORDS * sizeof(double));
   return 0;
 }
-int tbo_read_stats(tbo_ctx *c, int64_t *stats8, int clear) {
-  if (!c || !stats8) return fail("tbo_read_stats: bad argument");
-  memcpy(stats8, c->stats, sizeof c->stats);
+int tbo_read_stats(tbo_ctx *c, int64_t *stats10, int clear) {
+  if (!c || !stats10) return fail("tbo_read_stats: bad argument");
+  memcpy(stats10, c->stats, sizeof c->stats);
   if (clear) memset(c->stats, 0, sizeof c->stats);
   return 0;
 }

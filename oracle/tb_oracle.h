@@ -29,7 +29,7 @@ extern "C" {
 
 #define TBO_STATE_WORDS 32 /* canonical per-env state record, see tbo_get_state */
 #define TBO_INIT_WORDS 8   /* explicit reset placement record, see tbo_reset_from */
-#define TBO_NUM_STATS 8
+#define TBO_NUM_STATS 10
 
 /* event bits written per env step */
 #define TBO_EV_RACKET_BALL 1   /* racket-ball manifold non-empty at some physics step of this env step */
@@ -74,8 +74,9 @@ int tbo_rollout(tbo_ctx *c, int action_mode, int k_steps, float *obs, float *rew
 int tbo_get_state(tbo_ctx *c, double *state /* [N, 32] */);
 int tbo_set_state(tbo_ctx *c, const double *state);
 /* episode statistics since create / last clear: episodes, sum length, racket-contact steps, goals, court
- * landings, time-outs, sum return * 2^20, sum return^2 * 2^10 (fixed point so sums are order independent). */
-int tbo_read_stats(tbo_ctx *c, int64_t *stats8, int clear);
+ * landings, time-outs, sum return * 2^20, sum return^2 * 2^10 (fixed point so sums are order independent),
+ * physics steps, env steps. */
+int tbo_read_stats(tbo_ctx *c, int64_t *stats10, int clear);
 int64_t tbo_physics_steps(tbo_ctx *c);
 
 /* building blocks exposed for unit tests */

@@ -1,0 +1,638 @@
+// tb_device.cuh - device-side dynamics of the tennisbot env step, templated on the arithmetic type.
+//
+// One thread owns one env and keeps its whole state in registers across every physics substep of an env step
+// (up to 776 inside SwingRacket's 26th step) and across the K env steps of a fused rollout.  The scene
+// (parameters + the two convex-prism edge tables) arrives as a __grid_constant__ kernel argument, so every
+// table lookup is a uniform constant-bank load and contexts with different parameters can share a device.
+//
+// What is restated here (paths relative to the reference checkout; Bullet semantics per SURVEY.md Appendix A):
+//   physics_step        <- pybullet.stepSimulation() as called at swingracket_env.py:82,107, tennisbot_env.py:121
+//   contact bits        <- pybullet.getContactPoints at swingracket_env.py:99,111,119, tennisbot_env.py:170
+//   swing/hit env logic <- swingracket_env.py:75-145, tennisbot_env.py:104-207
+//   episode placement   <- swingracket_env.py:151-186, tennisbot_env.py:217-261
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/tennisbot_b200.h"
+#include "tb_scene_data.h"
+
+namespace tb {
+
+// ------------------------------------------------------------------------------------------------ math shims
+template <typename T> struct M;
+template <> struct M<float> {
+  static __device__ __forceinline__ float sqrt(float x) { return sqrtf(x); }
+  static __device__ __forceinline__ float rsqrt(float x) { return 1.0f / sqrtf(x); }
+  static __device__ __forceinline__ float abs(float x) { return fabsf(x); }
+  static __device__ __forceinline__ void sincos(float x, float *s, float *c) { sincosf(x, s, c); }
+  static __device__ __forceinline__ float inf() { return __int_as_float(0x7f800000); }
+};
+template <> struct M<double> {
+  static __device__ __forceinline__ double sqrt(double x) { return ::sqrt(x); }
+  static __device__ __forceinline__ double rsqrt(double x) { return 1.0 / ::sqrt(x); }
+  static __device__ __forceinline__ double abs(double x) { return fabs(x); }
+  static __device__ __forceinline__ void sincos(double x, double *s, double *c) { ::sincos(x, s, c); }
+  static __device__ __forceinline__ double inf() { return __longlong_as_double(0x7ff0000000000000LL); }
+};
+
+template <typename T> __device__ __forceinline__ T clampv(T x, T lo, T hi) { return x < lo ? lo : (x > hi ? hi : x); }
+template <typename T> __device__ __forceinline__ T dot3(const T *a, const T *b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+template <typename T> __device__ __forceinline__ void cross3(const T *a, const T *b, T *o) {
+  o[0] = a[1] * b[2] - a[2] * b[1];
+  o[1] = a[2] * b[0] - a[0] * b[2];
+  o[2] = a[0] * b[1] - a[1] * b[0];
+}
+template <typename T> __device__ __forceinline__ T norm3(const T *a) { return M<T>::sqrt(dot3(a, a)); }
+
+// ------------------------------------------------------------------------------------------------ scene
+constexpr int kRacketEdges = TB_RACKET_OUTLINE_N;
+constexpr int kGoalEdges = TB_GOAL_SIDES;
+
+template <typename T> struct Edge {
+  T ax, ay, ex, ey, inv_len2, nx, ny;
+};
+template <typename T, int NE> struct Prism {
+  Edge<T> e[NE];
+  T half_thick, bound_radius;
+};
+
+template <typename T> struct Scene {
+  T dt, gravity_z, lin_damping, ang_damping, max_coord_vel;
+  T rest_racket, rest_court, rest_goal, mu_racket, mu_court, mu_goal;
+  T erp, slop, rest_vel_threshold, solver_residual, contact_threshold, hull_margin, box_margin, gyro;
+  int iters;
+  T ball_r, ball_inv_m, ball_inv_i, racket_inv_m;
+  T racket_i[3], racket_inv_i[3];
+  T com_z;
+  T swing_q[4], swing_off[3]; // spawn quaternion for rpy (0,0.5,0) and R*(0,0,com_z), built on the host in double
+  T floor_h[3], net_h[3], goal_r, goal_hz;
+  Prism<T, kRacketEdges> racket;
+  Prism<T, kGoalEdges> goal;
+};
+
+// ------------------------------------------------------------------------------------------------ state
+template <typename T> struct St {
+  T rp[3], rq[4], rv[3], rw[3], bp[3], bv[3], bw[3], aux[3], goal[2], d0, ret;
+  int step, flags;
+  uint32_t episode;
+};
+
+// ------------------------------------------------------------------------------------------------ RNG
+// Philox4x32-10, counter = (global env id lo, hi, episode, stream word), key = seed.
+__device__ __forceinline__ void philox4x32(uint64_t seed, uint64_t env_id, uint32_t episode, uint32_t w3, uint32_t out[4]) {
+  uint32_t c0 = (uint32_t)env_id, c1 = (uint32_t)(env_id >> 32), c2 = episode, c3 = w3;
+  uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    uint32_t h0 = __umulhi(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
+    uint32_t h1 = __umulhi(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;
+    c0 = h1 ^ c1 ^ k0;
+    c1 = l1;
+    c2 = h0 ^ c3 ^ k1;
+    c3 = l0;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+template <typename T> __device__ __forceinline__ T u01(uint32_t x) { return (T)(x >> 8) * (T)(1.0 / 16777216.0); }
+constexpr uint32_t kStreamReset = 0u, kStreamAction = 1u;
+__device__ __forceinline__ uint32_t stream_word(uint32_t stream, uint32_t step, uint32_t block) {
+  return (stream << 28) | ((step & 0xFFFFFu) << 4) | (block & 0xFu);
+}
+
+// ------------------------------------------------------------------------------------------------ geometry
+template <typename T> __device__ __forceinline__ void quat_to_mat(const T *q, T *R) {
+  T x = q[0], y = q[1], z = q[2], w = q[3];
+  R[0] = 1 - 2 * (y * y + z * z); R[1] = 2 * (x * y - z * w);     R[2] = 2 * (x * z + y * w);
+  R[3] = 2 * (x * y + z * w);     R[4] = 1 - 2 * (x * x + z * z); R[5] = 2 * (y * z - x * w);
+  R[6] = 2 * (x * z - y * w);     R[7] = 2 * (y * z + x * w);     R[8] = 1 - 2 * (x * x + y * y);
+}
+template <typename T> __device__ __forceinline__ void mat_vec(const T *R, const T *v, T *o) {
+  o[0] = R[0] * v[0] + R[1] * v[1] + R[2] * v[2];
+  o[1] = R[3] * v[0] + R[4] * v[1] + R[5] * v[2];
+  o[2] = R[6] * v[0] + R[7] * v[1] + R[8] * v[2];
+}
+template <typename T> __device__ __forceinline__ void matT_vec(const T *R, const T *v, T *o) {
+  o[0] = R[0] * v[0] + R[3] * v[1] + R[6] * v[2];
+  o[1] = R[1] * v[0] + R[4] * v[1] + R[7] * v[2];
+  o[2] = R[2] * v[0] + R[5] * v[1] + R[8] * v[2];
+}
+
+// Distance from (t; u,v) to a convex prism core: polygon in (u,v), extruded +-half_thick along t.
+// n = unit normal core -> point as (nt,nu,nv); q = closest core point.  Inside the core the minimum
+// translation axis (face vs outline) stands in for Bullet's EPA.
+template <typename T, int NE>
+__device__ __noinline__ T prism_distance(const Prism<T, NE> &pr, T t, T u, T v, T *n, T *q) {
+  T best_d2 = M<T>::inf(), bq0 = 0, bq1 = 0, max_side = -M<T>::inf();
+  int max_edge = 0;
+#pragma unroll 1
+  for (int i = 0; i < NE; ++i) {
+    const Edge<T> &e = pr.e[i];
+    T ru = u - e.ax, rv = v - e.ay;
+    T side = ru * e.nx + rv * e.ny;
+    if (side > max_side) { max_side = side; max_edge = i; }
+    T s = (ru * e.ex + rv * e.ey) * e.inv_len2;
+    s = s < 0 ? (T)0 : (s > 1 ? (T)1 : s);
+    T q0 = e.ax + s * e.ex, q1 = e.ay + s * e.ey;
+    T d0 = u - q0, d1 = v - q1;
+    T d2 = d0 * d0 + d1 * d1;
+    if (d2 < best_d2) { best_d2 = d2; bq0 = q0; bq1 = q1; }
+  }
+  T et = M<T>::abs(t) - pr.half_thick;
+  T st = t < 0 ? (T)-1 : (T)1;
+  if (max_side > 0) {
+    T du = u - bq0, dv = v - bq1;
+    if (et > 0) {
+      T dist = M<T>::sqrt(et * et + best_d2);
+      n[0] = st * et / dist; n[1] = du / dist; n[2] = dv / dist;
+      q[0] = st * pr.half_thick; q[1] = bq0; q[2] = bq1;
+      return dist;
+    }
+    T dist = M<T>::sqrt(best_d2);
+    n[0] = 0; n[1] = du / dist; n[2] = dv / dist;
+    q[0] = t; q[1] = bq0; q[2] = bq1;
+    return dist;
+  }
+  if (et > 0) {
+    n[0] = st; n[1] = 0; n[2] = 0;
+    q[0] = st * pr.half_thick; q[1] = u; q[2] = v;
+    return et;
+  }
+  T pen_face = -et, pen_poly = -max_side;
+  if (pen_face <= pen_poly) {
+    n[0] = st; n[1] = 0; n[2] = 0;
+    q[0] = st * pr.half_thick; q[1] = u; q[2] = v;
+    return -pen_face;
+  }
+  const Edge<T> &e = pr.e[max_edge];
+  n[0] = 0; n[1] = e.nx; n[2] = e.ny;
+  q[0] = t; q[1] = u + pen_poly * e.nx; q[2] = v + pen_poly * e.ny;
+  return -pen_poly;
+}
+
+// sphere centre vs box core (half extents shrunk by the embedded margin)
+template <typename T> __device__ __forceinline__ T box_distance(const T *h, T margin, const T *p, T *n) {
+  T d[3], q[3], d2 = 0;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    T c = h[i] - margin;
+    q[i] = p[i] < -c ? -c : (p[i] > c ? c : p[i]);
+    d[i] = p[i] - q[i];
+    d2 += d[i] * d[i];
+  }
+  if (d2 > 0) {
+    T dist = M<T>::sqrt(d2);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) n[i] = d[i] / dist;
+    return dist;
+  }
+  int ax = 0;
+  T pen = M<T>::inf();
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    T pi = (h[i] - margin) - M<T>::abs(p[i]);
+    if (pi < pen) { pen = pi; ax = i; }
+  }
+  n[0] = n[1] = n[2] = 0;
+  T sg = p[ax] < 0 ? (T)-1 : (T)1;
+  if (ax == 0) n[0] = sg; else if (ax == 1) n[1] = sg; else n[2] = sg;
+  return -pen;
+}
+
+// Bullet's btPlaneSpace1
+template <typename T> __device__ __forceinline__ void plane_space(const T *n, T *p, T *q) {
+  if (M<T>::abs(n[2]) > (T)0.70710678118654752440) {
+    T a = n[1] * n[1] + n[2] * n[2], k = M<T>::rsqrt(a);
+    p[0] = 0; p[1] = -n[2] * k; p[2] = n[1] * k;
+    q[0] = a * k; q[1] = -n[0] * p[2]; q[2] = n[0] * p[1];
+  } else {
+    T a = n[0] * n[0] + n[1] * n[1], k = M<T>::rsqrt(a);
+    p[0] = -n[1] * k; p[1] = n[0] * k; p[2] = 0;
+    q[0] = -n[2] * p[1]; q[1] = n[2] * p[0]; q[2] = a * k;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ contacts
+constexpr int kMaxContacts = 4;
+template <typename T> struct Contact {
+  int dyn;
+  T n[3], d, ra[3], rest, mu;
+};
+template <typename T> struct Row {
+  T u[3], rbxu[3], raxu[3], ia[3], jinv, rhs, lam;
+};
+
+// Projected Gauss-Seidel over the ball's contacts: per contact one normal row and a friction pair with an
+// implicit cone clamp, early exit on the squared-residual threshold (A.6).  Rare path (about one physics step
+// per episode), kept out of line so the substep loop stays small.  The rows are ALWAYS solved in double, also
+// by the float32 kernel: the residual early exit makes the impulse sensitive to the sweep count, and a float
+// solve that stops one sweep apart from the double oracle moves the ball's exit velocity by ~1e-2 m/s.
+template <typename T>
+__device__ __noinline__ void solve_contacts(const Scene<T> &sc, const Contact<T> *ct, int nc, const T *Rt,
+                                            const T *bvt, const T *bwt, const T *rvt, const T *rwt, T *dvb_o,
+                                            T *dwb_o, T *dva_o, T *dwa_o) {
+  typedef double S;
+  const S rb = sc.ball_r, inv_mb = sc.ball_inv_m, inv_ib = sc.ball_inv_i, inv_mr = sc.racket_inv_m, dt = sc.dt;
+  S R[9], bv[3], bw[3], rv[3], rw[3];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) R[i] = Rt[i];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) { bv[i] = bvt[i]; bw[i] = bwt[i]; rv[i] = rvt[i]; rw[i] = rwt[i]; }
+  S dvb[3] = {0, 0, 0}, dwb[3] = {0, 0, 0}, dva[3] = {0, 0, 0}, dwa[3] = {0, 0, 0};
+  Row<S> rows[kMaxContacts][3];
+#pragma unroll 1
+  for (int k = 0; k < nc; ++k) {
+    const Contact<T> &c = ct[k];
+    S dirs[3][3];
+    dirs[0][0] = c.n[0]; dirs[0][1] = c.n[1]; dirs[0][2] = c.n[2];
+    plane_space<S>(dirs[0], dirs[1], dirs[2]);
+    S rbv[3] = {-rb * dirs[0][0], -rb * dirs[0][1], -rb * dirs[0][2]};
+    S ra[3] = {(S)c.ra[0], (S)c.ra[1], (S)c.ra[2]};
+#pragma unroll 1
+    for (int r = 0; r < 3; ++r) {
+      Row<S> &w = rows[k][r];
+      w.u[0] = dirs[r][0]; w.u[1] = dirs[r][1]; w.u[2] = dirs[r][2];
+      cross3(rbv, w.u, w.rbxu);
+      S denom = inv_mb + dot3(w.rbxu, w.rbxu) * inv_ib;
+      S rel = dot3(w.u, bv) + dot3(w.rbxu, bw);
+      if (c.dyn) {
+        cross3(ra, w.u, w.raxu);
+        S l[3], li[3];
+        matT_vec(R, w.raxu, l);
+        li[0] = l[0] * (S)sc.racket_inv_i[0]; li[1] = l[1] * (S)sc.racket_inv_i[1]; li[2] = l[2] * (S)sc.racket_inv_i[2];
+        mat_vec(R, li, w.ia);
+        denom += inv_mr + dot3(w.raxu, w.ia);
+        rel -= dot3(w.u, rv) + dot3(w.raxu, rw);
+      } else {
+        w.raxu[0] = w.raxu[1] = w.raxu[2] = 0;
+        w.ia[0] = w.ia[1] = w.ia[2] = 0;
+      }
+      w.jinv = 1 / denom;
+      w.lam = 0;
+      if (r == 0) {
+        S e = fabs(rel) < (S)sc.rest_vel_threshold ? (S)0 : -(S)c.rest * rel;
+        if (e < 0) e = 0;
+        S pen = (S)c.d + (S)sc.slop, vel_err = e - rel, pos_err = 0;
+        if (pen > 0) vel_err -= pen / dt;
+        else pos_err = -pen * (S)sc.erp / dt;
+        w.rhs = (pos_err + vel_err) * w.jinv;
+      } else {
+        w.rhs = -rel * w.jinv;
+      }
+    }
+  }
+#pragma unroll 1
+  for (int it = 0; it < sc.iters; ++it) {
+    S resid = 0;
+#pragma unroll 1
+    for (int k = 0; k < nc; ++k) {
+      Row<S> &w = rows[k][0];
+      S jd = dot3(w.u, dvb) + dot3(w.rbxu, dwb) - dot3(w.u, dva) - dot3(w.raxu, dwa);
+      S dl = w.rhs - jd * w.jinv;
+      S sum = w.lam + dl;
+      if (sum < 0) { dl = -w.lam; sum = 0; }
+      w.lam = sum;
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        dvb[i] += w.u[i] * dl * inv_mb;
+        dwb[i] += w.rbxu[i] * dl * inv_ib;
+        if (ct[k].dyn) { dva[i] -= w.u[i] * dl * inv_mr; dwa[i] -= w.ia[i] * dl; }
+      }
+      S rr = dl / w.jinv;
+      if (rr * rr > resid) resid = rr * rr;
+    }
+#pragma unroll 1
+    for (int k = 0; k < nc; ++k) {
+      S lam_n = rows[k][0].lam;
+      if (!(lam_n > 0)) continue;
+      S lim = (S)ct[k].mu * lam_n;
+      S sum[2];
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        Row<S> &w = rows[k][1 + r];
+        S jd = dot3(w.u, dvb) + dot3(w.rbxu, dwb) - dot3(w.u, dva) - dot3(w.raxu, dwa);
+        sum[r] = w.lam + (w.rhs - jd * w.jinv);
+      }
+      S m2 = sum[0] * sum[0] + sum[1] * sum[1];
+      if (m2 > lim * lim) {
+        S sf = lim / ::sqrt(m2);
+        sum[0] *= sf; sum[1] *= sf;
+      }
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        Row<S> &w = rows[k][1 + r];
+        S d = sum[r] - w.lam;
+        w.lam = sum[r];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+          dvb[i] += w.u[i] * d * inv_mb;
+          dwb[i] += w.rbxu[i] * d * inv_ib;
+          if (ct[k].dyn) { dva[i] -= w.u[i] * d * inv_mr; dwa[i] -= w.ia[i] * d; }
+        }
+        S rr = d / w.jinv;
+        if (rr * rr > resid) resid = rr * rr;
+      }
+    }
+    if (resid <= (S)sc.solver_residual) break;
+  }
+#pragma unroll
+  for (int i = 0; i < 3; ++i) { dvb_o[i] = (T)dvb[i]; dwb_o[i] = (T)dwb[i]; dva_o[i] = (T)dva[i]; dwa_o[i] = (T)dwa[i]; }
+}
+
+// Narrow phase of the three rare pairs, out of line.  Each appends to ct[] and returns the event bit.
+template <typename T>
+__device__ __noinline__ int detect_racket(const Scene<T> &sc, const T *R, const T *rel, Contact<T> *ct, int *nc) {
+  T pl[3], nl[3], ql[3];
+  matT_vec(R, rel, pl);
+  T dc = prism_distance<T, kRacketEdges>(sc.racket, pl[0], pl[1], pl[2], nl, ql);
+  T d = dc - (sc.ball_r + sc.hull_margin);
+  if (!(d <= sc.contact_threshold)) return 0;
+  Contact<T> &k = ct[(*nc)++];
+  k.dyn = 1;
+  mat_vec(R, nl, k.n);
+  T qs[3] = {ql[0] + sc.hull_margin * nl[0], ql[1] + sc.hull_margin * nl[1], ql[2] + sc.hull_margin * nl[2]};
+  mat_vec(R, qs, k.ra);
+  k.d = d; k.rest = sc.rest_racket; k.mu = sc.mu_racket;
+  return TB_EV_RACKET_BALL;
+}
+template <typename T>
+__device__ __noinline__ int detect_box(const Scene<T> &sc, const T *h, const T *p, int bit, Contact<T> *ct, int *nc) {
+  T n[3];
+  T dc = box_distance(h, sc.box_margin, p, n);
+  T d = dc - (sc.ball_r + sc.box_margin);
+  if (!(d <= sc.contact_threshold)) return 0;
+  Contact<T> &k = ct[(*nc)++];
+  k.dyn = 0;
+  k.n[0] = n[0]; k.n[1] = n[1]; k.n[2] = n[2];
+  k.ra[0] = k.ra[1] = k.ra[2] = 0;
+  k.d = d; k.rest = sc.rest_court; k.mu = sc.mu_court;
+  return bit;
+}
+template <typename T>
+__device__ __noinline__ int detect_goal(const Scene<T> &sc, const T *p, Contact<T> *ct, int *nc) {
+  T nl[3], ql[3];
+  T dc = prism_distance<T, kGoalEdges>(sc.goal, p[2], p[0], p[1], nl, ql);
+  T d = dc - (sc.ball_r + sc.hull_margin);
+  if (!(d <= sc.contact_threshold)) return 0;
+  Contact<T> &k = ct[(*nc)++];
+  k.dyn = 0;
+  k.n[0] = nl[1]; k.n[1] = nl[2]; k.n[2] = nl[0];
+  k.ra[0] = k.ra[1] = k.ra[2] = 0;
+  k.d = d; k.rest = sc.rest_goal; k.mu = sc.mu_goal;
+  return TB_EV_GOAL_BALL;
+}
+template <typename T> __device__ __noinline__ int racket_low(const Scene<T> &sc, const T *R, T rpz) {
+  T low = M<T>::inf();
+#pragma unroll 1
+  for (int i = 0; i < kRacketEdges; ++i) {
+    T h = R[7] * sc.racket.e[i].ax + R[8] * sc.racket.e[i].ay;
+    if (h < low) low = h;
+  }
+  low += rpz - M<T>::abs(R[6]) * sc.racket.half_thick - sc.hull_margin;
+  return low <= sc.floor_h[2] + sc.contact_threshold ? TB_EV_RACKET_LOW : 0;
+}
+
+// One stepSimulation(): detect at the start-of-step poses, integrate velocities with Bullet's multibody
+// damping, solve contacts, integrate poses.  Returns the TB_EV_* contact bits getContactPoints would report.
+template <typename T, bool WITH_GOAL>
+__device__ __forceinline__ int physics_step(const Scene<T> &sc, St<T> &s, const T *f_racket, const T *t_racket,
+                                            const T *f_ball) {
+  const T dt = sc.dt, thr = sc.contact_threshold, rb = sc.ball_r;
+  T R[9];
+  quat_to_mat(s.rq, R);
+  Contact<T> ct[kMaxContacts];
+  int nc = 0, bits = 0;
+
+  // ---- (1) detection: cheap conservative rejects in line, narrow phase out of line
+  {
+    T rel[3] = {s.bp[0] - s.rp[0], s.bp[1] - s.rp[1], s.bp[2] - s.rp[2]};
+    T reach = sc.racket.bound_radius + rb + sc.hull_margin + thr;
+    if (dot3(rel, rel) <= reach * reach) bits |= detect_racket(sc, R, rel, ct, &nc);
+    const T reach_b = rb + sc.box_margin + thr;
+    if (!(M<T>::abs(s.bp[0]) - sc.floor_h[0] > reach_b || M<T>::abs(s.bp[1]) - sc.floor_h[1] > reach_b ||
+          M<T>::abs(s.bp[2]) - sc.floor_h[2] > reach_b))
+      bits |= detect_box(sc, sc.floor_h, s.bp, TB_EV_COURT_BALL, ct, &nc);
+    if (!(M<T>::abs(s.bp[0]) - sc.net_h[0] > reach_b || M<T>::abs(s.bp[1]) - sc.net_h[1] > reach_b ||
+          M<T>::abs(s.bp[2]) - sc.net_h[2] > reach_b))
+      bits |= detect_box(sc, sc.net_h, s.bp, TB_EV_COURT_BALL | TB_EV_NET_BALL, ct, &nc);
+    if (WITH_GOAL) {
+      T p[3] = {s.bp[0] - s.goal[0], s.bp[1] - s.goal[1], s.bp[2]};
+      T reach_g = rb + sc.hull_margin + thr, rxy = sc.goal_r + reach_g;
+      if (M<T>::abs(p[2]) - sc.goal_hz <= reach_g && p[0] * p[0] + p[1] * p[1] <= rxy * rxy)
+        bits |= detect_goal(sc, p, ct, &nc);
+    }
+    if (s.rp[2] - sc.racket.bound_radius - sc.hull_margin <= sc.floor_h[2] + thr &&
+        M<T>::abs(s.rp[0]) <= sc.floor_h[0] + 1 && M<T>::abs(s.rp[1]) <= sc.floor_h[1] + 1)
+      bits |= racket_low(sc, R, s.rp[2]);
+  }
+
+  // ---- (2) velocities: v += dt (F/m + g - v (k + k|v|)); omega likewise in the body frame with the gyro term
+  const T vmax = sc.max_coord_vel;
+  {
+    T kv = sc.lin_damping * (1 + norm3(s.bv)), kw = sc.ang_damping * (1 + norm3(s.bw));
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      T g = i == 2 ? sc.gravity_z : (T)0;
+      s.bv[i] = clampv(s.bv[i] + dt * (f_ball[i] * sc.ball_inv_m + g - s.bv[i] * kv), -vmax, vmax);
+      s.bw[i] = clampv(s.bw[i] + dt * (-s.bw[i] * kw), -vmax, vmax);
+    }
+  }
+  {
+    T kv = sc.lin_damping * (1 + norm3(s.rv));
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      T g = i == 2 ? sc.gravity_z : (T)0;
+      s.rv[i] = clampv(s.rv[i] + dt * (f_racket[i] * sc.racket_inv_m + g - s.rv[i] * kv), -vmax, vmax);
+    }
+    T wl[3], tl[3], iw[3], gy[3], al[3], aw[3];
+    matT_vec(R, s.rw, wl);
+    matT_vec(R, t_racket, tl);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) iw[i] = sc.racket_i[i] * wl[i];
+    cross3(wl, iw, gy);
+    T kw = sc.ang_damping * (1 + norm3(wl));
+#pragma unroll
+    for (int i = 0; i < 3; ++i) al[i] = (tl[i] - sc.gyro * gy[i]) * sc.racket_inv_i[i] - wl[i] * kw;
+    mat_vec(R, al, aw);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) s.rw[i] = clampv(s.rw[i] + dt * aw[i], -vmax, vmax);
+  }
+
+  // ---- (3) contact solve
+  if (nc > 0) {
+    T dvb[3], dwb[3], dva[3], dwa[3];
+    solve_contacts(sc, ct, nc, R, s.bv, s.bw, s.rv, s.rw, dvb, dwb, dva, dwa);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      s.bv[i] = clampv(s.bv[i] + dvb[i], -vmax, vmax);
+      s.bw[i] = clampv(s.bw[i] + dwb[i], -vmax, vmax);
+      s.rv[i] = clampv(s.rv[i] + dva[i], -vmax, vmax);
+      s.rw[i] = clampv(s.rw[i] + dwa[i], -vmax, vmax);
+    }
+  }
+
+  // ---- (4) poses: x += dt v ; q <- exp(omega dt) q
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    s.bp[i] += dt * s.bv[i];
+    s.rp[i] += dt * s.rv[i];
+  }
+  {
+    T ang = norm3(s.rw), k, cw;
+    if (ang < (T)0.001) {
+      k = (T)0.5 * dt - dt * dt * dt * (T)0.020833333333 * ang * ang;
+      T sn;
+      M<T>::sincos((T)0.5 * ang * dt, &sn, &cw);
+    } else {
+      T sn;
+      M<T>::sincos((T)0.5 * ang * dt, &sn, &cw);
+      k = sn / ang;
+    }
+    T ax = s.rw[0] * k, ay = s.rw[1] * k, az = s.rw[2] * k;
+    const T *q = s.rq;
+    T x = cw * q[0] + ax * q[3] + ay * q[2] - az * q[1];
+    T y = cw * q[1] - ax * q[2] + ay * q[3] + az * q[0];
+    T z = cw * q[2] + ax * q[1] - ay * q[0] + az * q[3];
+    T w = cw * q[3] - ax * q[0] - ay * q[1] - az * q[2];
+    T inv = M<T>::rsqrt(x * x + y * y + z * z + w * w);
+    s.rq[0] = x * inv; s.rq[1] = y * inv; s.rq[2] = z * inv; s.rq[3] = w * inv;
+  }
+  return bits;
+}
+
+// ------------------------------------------------------------------------------------------------ episodes
+template <typename T, int KIND> __device__ __forceinline__ void place(const Scene<T> &sc, St<T> &s, const T *in) {
+#pragma unroll
+  for (int i = 0; i < 3; ++i) { s.rv[i] = 0; s.rw[i] = 0; s.bv[i] = 0; s.bw[i] = 0; }
+  if (KIND == TB_ENV_SWING) {
+    // swingracket_env.py:161-175
+    s.rq[0] = sc.swing_q[0]; s.rq[1] = sc.swing_q[1]; s.rq[2] = sc.swing_q[2]; s.rq[3] = sc.swing_q[3];
+    s.rp[0] = in[0] + sc.swing_off[0]; s.rp[1] = in[1] + sc.swing_off[1]; s.rp[2] = in[2] + sc.swing_off[2];
+    s.bp[0] = in[0] - (T)0.1; s.bp[1] = in[1]; s.bp[2] = in[2] + (T)0.8;
+    s.aux[0] = in[0]; s.aux[1] = in[1]; s.aux[2] = in[2];
+    s.goal[0] = in[3]; s.goal[1] = in[4];
+    T dx = s.bp[0] - in[3], dy = s.bp[1] - in[4];
+    s.d0 = M<T>::sqrt(dx * dx + dy * dy);
+  } else {
+    // tennisbot_env.py:227-246
+    s.rq[0] = 0; s.rq[1] = 0; s.rq[2] = 0; s.rq[3] = 1;
+    s.rp[0] = in[0]; s.rp[1] = in[1]; s.rp[2] = in[2] + sc.com_z;
+    s.aux[0] = in[3]; s.aux[1] = in[4]; s.aux[2] = (T)(25.0 * 0.8);
+    s.bp[0] = in[5]; s.bp[1] = in[6]; s.bp[2] = in[7];
+    s.goal[0] = 0; s.goal[1] = 0; s.d0 = 0;
+  }
+}
+template <typename T, int KIND>
+__device__ __forceinline__ void draw_init(uint64_t seed, uint64_t gid, uint32_t episode, T *in) {
+  uint32_t r[4];
+  philox4x32(seed, gid, episode, stream_word(kStreamReset, 0, 0), r);
+  if (KIND == TB_ENV_SWING) {
+    in[0] = (T)5.5 + (T)5.5 * u01<T>(r[0]);
+    in[1] = (T)-4.0 + (T)8.0 * u01<T>(r[1]);
+    in[2] = (T)0.6;
+    in[3] = (T)-3.0 - (T)9.0 * u01<T>(r[2]);
+    in[4] = (T)-5.0 + (T)10.0 * u01<T>(r[3]);
+    in[5] = in[6] = in[7] = 0;
+  } else {
+    uint32_t r2[4];
+    philox4x32(seed, gid, episode, stream_word(kStreamReset, 0, 1), r2);
+    in[0] = (T)7.5 + (T)5.0 * u01<T>(r[0]);
+    in[1] = (T)-5.0 + (T)10.0 * u01<T>(r[1]);
+    in[2] = (T)0.2 + (T)0.01 * u01<T>(r[2]);
+    in[3] = (T)25.0 + (T)12.5 * u01<T>(r[3]);
+    in[4] = (T)-10.0 + (T)20.0 * u01<T>(r2[0]);
+    in[5] = (T)-12.0 + (T)6.0 * u01<T>(r2[1]);
+    in[6] = (T)-1.0 + (T)2.0 * u01<T>(r2[2]);
+    in[7] = (T)1.0 + (T)0.5 * u01<T>(r2[3]);
+  }
+}
+template <typename T, int KIND>
+__device__ __forceinline__ void start_episode(const Scene<T> &sc, St<T> &s, const T *in, uint32_t episode) {
+  place<T, KIND>(sc, s, in);
+  s.ret = 0; s.step = 0; s.flags = 0; s.episode = episode;
+}
+template <typename T, int KIND> __device__ __forceinline__ void pack_obs(const St<T> &s, float *o) {
+  if (KIND == TB_ENV_SWING) {
+    o[0] = (float)s.rp[0]; o[1] = (float)s.rp[1]; o[2] = (float)s.bp[0]; o[3] = (float)s.bp[1];
+    o[4] = (float)s.goal[0]; o[5] = (float)s.goal[1];
+  } else {
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      o[i] = (float)s.rp[i]; o[3 + i] = (float)s.rv[i]; o[6 + i] = (float)s.bp[i]; o[9 + i] = (float)s.bv[i];
+    }
+  }
+}
+
+struct StepOut {
+  float reward;
+  int done, events, hit_steps, nphys;
+};
+
+template <typename T> __device__ __forceinline__ T moved_dist_to_goal(const St<T> &s) {
+  T dx = s.bp[0] - s.goal[0], dy = s.bp[1] - s.goal[1];
+  return (s.d0 - M<T>::sqrt(dx * dx + dy * dy)) / s.d0 * (T)20;
+}
+template <typename T> __device__ __forceinline__ T dist_to_reward(T d) {
+  return d < (T)0.5 ? (T)20 : d < 1 ? (T)15 : d < 2 ? (T)10 : d < 3 ? (T)5 : d < 4 ? (T)1 : (T)0;
+}
+
+// One agent-visible step().  The physics call appears once; SwingRacket's fast-forward re-enters it.
+template <typename T, int KIND>
+__device__ __forceinline__ void env_step(const Scene<T> &sc, St<T> &s, const float *a, StepOut &o) {
+  T zero[3] = {0, 0, 0};
+  o.hit_steps = 0;
+  if (KIND == TB_ENV_SWING) {
+    T F[3] = {(T)a[0] * 400, (T)a[1] * 400, (T)a[2] * 400 + (T)(4 * 9.81)};
+    T Tq[3] = {(T)a[3] * 5, (T)a[4] * 5, (T)a[5] * 5};
+    int k = s.step, ev = 0, nphys = 0;
+    bool done = s.flags & 1, first = true;
+    T reward = 0;
+    while (true) {
+      int bits = physics_step<T, true>(sc, s, F, Tq, zero);
+      ++nphys; ++k;
+      ev |= bits;
+      if (first) {
+        if (k < 25 && (bits & TB_EV_RACKET_BALL)) { reward += 2; o.hit_steps = 1; }
+        first = false;
+        F[0] = F[1] = F[2] = 0;
+        Tq[0] = Tq[1] = Tq[2] = 0;
+        if (!(k > 25)) break;
+      } else {
+        if (bits & TB_EV_COURT_BALL) { done = true; reward += moved_dist_to_goal(s); }
+        if (bits & TB_EV_GOAL_BALL) { reward += moved_dist_to_goal(s); reward += 50; done = true; }
+        if (k > 800) { done = true; ev |= TB_EV_TIMEOUT; }
+        F[0] = -50 * (s.rp[0] - s.aux[0]);
+        F[1] = -2 * (s.rp[1] - s.aux[1]);
+        F[2] = -2 * (s.rp[2] - s.aux[2] - 4);
+      }
+      if (done) break;
+    }
+    s.step = k;
+    s.flags = done ? 1 : 0;
+    o.reward = (float)reward; o.done = done; o.events = ev; o.nphys = nphys;
+  } else {
+    T F[3] = {(T)a[0] * 10, (T)a[1] * 10, (T)(4 * 9.81)};
+    int k = s.step;
+    T Fb[3] = {0, 0, 0};
+    if (k < 5) { Fb[0] = s.aux[0]; Fb[1] = s.aux[1]; Fb[2] = s.aux[2]; }
+    int bits = physics_step<T, false>(sc, s, F, zero, Fb);
+    ++k;
+    s.step = k;
+    bool done = s.flags & 1;
+    o.events = bits; o.reward = 0; o.done = 0; o.nphys = 1;
+    if (k < 5) return;
+    T dz = s.bp[2] - s.rp[2], dy = s.bp[1] - s.rp[1];
+    T delta = M<T>::sqrt(dz * dz + dy * dy);
+    T reward = 0;
+    if (bits & TB_EV_RACKET_BALL) { reward += 25; reward += dist_to_reward(delta); o.hit_steps = 1; }
+    T xbr = s.bp[0] - s.rp[0];
+    if (!(xbr < (T)0.5)) { done = true; reward += dist_to_reward(delta); o.events |= TB_EV_BALL_PASSED; }
+    if (k > 1000) { done = true; o.events |= TB_EV_TIMEOUT; }
+    s.flags = done ? 1 : 0;
+    o.reward = (float)reward; o.done = done;
+  }
+}
+
+}  // namespace tb

@@ -1,0 +1,715 @@
+// tb_kernels.cu - kernels and the C ABI of libtennisbot_b200.so (include/tennisbot_b200.h).
+//
+// HBM layout: the state of N envs is 8 "packs" of 4 scalars, pack-major: element (pack p, env i) sits at
+// ((p * N + i) * 4) scalars.  A warp therefore reads/writes 32 consecutive 16-byte (f32) or 32-byte (f64)
+// records per pack: fully coalesced 128-bit accesses, 128 B (f32) / 256 B (f64) of state per env each way.
+//   pack0 racket pos xyz | ball pos x      pack4 ball vel xyz  | ball angvel x
+//   pack1 racket quat xyzw                 pack5 ball angvel yz | aux x, aux y
+//   pack2 racket vel xyz | ball pos y      pack6 aux z | goal x, goal y | d0
+//   pack3 racket angvel xyz | ball pos z   pack7 return | step | flags | episode   (integers bit-cast)
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+
+#include "tb_device.cuh"
+
+namespace tb {
+
+constexpr int kPacks = 8;
+constexpr int kBlock = 128;
+
+// ------------------------------------------------------------------------------------------------ pack I/O
+template <typename T> struct Pack { T x, y, z, w; };
+
+__device__ __forceinline__ Pack<float> ld_pack(const float *base, int64_t n, int p, int64_t i) {
+  float4 v = *reinterpret_cast<const float4 *>(base + ((int64_t)p * n + i) * 4);
+  return {v.x, v.y, v.z, v.w};
+}
+__device__ __forceinline__ void st_pack(float *base, int64_t n, int p, int64_t i, Pack<float> v) {
+  *reinterpret_cast<float4 *>(base + ((int64_t)p * n + i) * 4) = make_float4(v.x, v.y, v.z, v.w);
+}
+__device__ __forceinline__ Pack<double> ld_pack(const double *base, int64_t n, int p, int64_t i) {
+  const double2 *q = reinterpret_cast<const double2 *>(base + ((int64_t)p * n + i) * 4);
+  double2 a = q[0], b = q[1];
+  return {a.x, a.y, b.x, b.y};
+}
+__device__ __forceinline__ void st_pack(double *base, int64_t n, int p, int64_t i, Pack<double> v) {
+  double2 *q = reinterpret_cast<double2 *>(base + ((int64_t)p * n + i) * 4);
+  q[0] = make_double2(v.x, v.y);
+  q[1] = make_double2(v.z, v.w);
+}
+__device__ __forceinline__ float int_as(float, int64_t v) { return __int_as_float((int)v); }
+__device__ __forceinline__ double int_as(double, int64_t v) { return __longlong_as_double((long long)v); }
+__device__ __forceinline__ int64_t as_int(float v) { return (int64_t)__float_as_int(v); }
+__device__ __forceinline__ int64_t as_int(double v) { return (int64_t)__double_as_longlong(v); }
+
+template <typename T> __device__ __forceinline__ void load_state(const T *base, int64_t n, int64_t i, St<T> &s) {
+  Pack<T> p0 = ld_pack(base, n, 0, i), p1 = ld_pack(base, n, 1, i), p2 = ld_pack(base, n, 2, i),
+          p3 = ld_pack(base, n, 3, i), p4 = ld_pack(base, n, 4, i), p5 = ld_pack(base, n, 5, i),
+          p6 = ld_pack(base, n, 6, i), p7 = ld_pack(base, n, 7, i);
+  s.rp[0] = p0.x; s.rp[1] = p0.y; s.rp[2] = p0.z; s.bp[0] = p0.w;
+  s.rq[0] = p1.x; s.rq[1] = p1.y; s.rq[2] = p1.z; s.rq[3] = p1.w;
+  s.rv[0] = p2.x; s.rv[1] = p2.y; s.rv[2] = p2.z; s.bp[1] = p2.w;
+  s.rw[0] = p3.x; s.rw[1] = p3.y; s.rw[2] = p3.z; s.bp[2] = p3.w;
+  s.bv[0] = p4.x; s.bv[1] = p4.y; s.bv[2] = p4.z; s.bw[0] = p4.w;
+  s.bw[1] = p5.x; s.bw[2] = p5.y; s.aux[0] = p5.z; s.aux[1] = p5.w;
+  s.aux[2] = p6.x; s.goal[0] = p6.y; s.goal[1] = p6.z; s.d0 = p6.w;
+  s.ret = p7.x; s.step = (int)as_int(p7.y); s.flags = (int)as_int(p7.z); s.episode = (uint32_t)as_int(p7.w);
+}
+template <typename T> __device__ __forceinline__ void store_state(T *base, int64_t n, int64_t i, const St<T> &s) {
+  st_pack(base, n, 0, i, Pack<T>{s.rp[0], s.rp[1], s.rp[2], s.bp[0]});
+  st_pack(base, n, 1, i, Pack<T>{s.rq[0], s.rq[1], s.rq[2], s.rq[3]});
+  st_pack(base, n, 2, i, Pack<T>{s.rv[0], s.rv[1], s.rv[2], s.bp[1]});
+  st_pack(base, n, 3, i, Pack<T>{s.rw[0], s.rw[1], s.rw[2], s.bp[2]});
+  st_pack(base, n, 4, i, Pack<T>{s.bv[0], s.bv[1], s.bv[2], s.bw[0]});
+  st_pack(base, n, 5, i, Pack<T>{s.bw[1], s.bw[2], s.aux[0], s.aux[1]});
+  st_pack(base, n, 6, i, Pack<T>{s.aux[2], s.goal[0], s.goal[1], s.d0});
+  st_pack(base, n, 7, i, Pack<T>{s.ret, int_as(T(), s.step), int_as(T(), s.flags), int_as(T(), (int64_t)s.episode)});
+}
+
+// ------------------------------------------------------------------------------------------------ statistics
+struct Acc {
+  int episodes, sum_len, hits, goals, courts, timeouts, nphys, nsteps;
+  long long ret_q20, ret2_q10;
+};
+// warp-level reduction: one redux.sync per 32-bit counter, shuffles only for the two 64-bit sums and only when
+// some lane finished an episode; lane 0 issues one atomic per non-zero counter.
+__device__ __forceinline__ void flush_stats(const Acc &a, unsigned long long *stats) {
+  const unsigned full = 0xffffffffu;
+  int lane = threadIdx.x & 31;
+  int nphys = __reduce_add_sync(full, a.nphys), nsteps = __reduce_add_sync(full, a.nsteps);
+  int hits = __reduce_add_sync(full, a.hits), episodes = __reduce_add_sync(full, a.episodes);
+  if (lane == 0) {
+    atomicAdd(stats + TB_STAT_PHYSICS_STEPS, (unsigned long long)nphys);
+    atomicAdd(stats + TB_STAT_ENV_STEPS, (unsigned long long)nsteps);
+    if (hits) atomicAdd(stats + TB_STAT_RACKET_HITS, (unsigned long long)hits);
+  }
+  if (episodes == 0) return;
+  int sum_len = __reduce_add_sync(full, a.sum_len), goals = __reduce_add_sync(full, a.goals);
+  int courts = __reduce_add_sync(full, a.courts), timeouts = __reduce_add_sync(full, a.timeouts);
+  long long r1 = a.ret_q20, r2 = a.ret2_q10;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    r1 += __shfl_down_sync(full, r1, o);
+    r2 += __shfl_down_sync(full, r2, o);
+  }
+  if (lane == 0) {
+    atomicAdd(stats + TB_STAT_EPISODES, (unsigned long long)episodes);
+    atomicAdd(stats + TB_STAT_SUM_LENGTH, (unsigned long long)sum_len);
+    if (goals) atomicAdd(stats + TB_STAT_GOALS, (unsigned long long)goals);
+    if (courts) atomicAdd(stats + TB_STAT_COURT, (unsigned long long)courts);
+    if (timeouts) atomicAdd(stats + TB_STAT_TIMEOUTS, (unsigned long long)timeouts);
+    atomicAdd(stats + TB_STAT_SUM_RETURN_Q20, (unsigned long long)r1);
+    atomicAdd(stats + TB_STAT_SUM_RETURN2_Q10, (unsigned long long)r2);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ kernels
+struct StepIO {
+  void *state;
+  int64_t n, id_offset;
+  uint64_t seed;
+  int auto_reset, k_steps;
+  const float *actions;
+  float *obs, *reward, *term_obs, *reward_sum;
+  uint8_t *done, *events;
+  int32_t *done_count;
+  unsigned long long *stats;
+};
+
+template <int KIND> struct Dims {
+  static constexpr int obs = KIND == TB_ENV_SWING ? 6 : 12;
+  static constexpr int act = KIND == TB_ENV_SWING ? 6 : 2;
+};
+
+template <int KIND> __device__ __forceinline__ void load_action(const float *actions, int64_t i, float *a) {
+  if (KIND == TB_ENV_SWING) {
+    const float2 *p = reinterpret_cast<const float2 *>(actions + i * 6);
+    float2 a0 = p[0], a1 = p[1], a2 = p[2];
+    a[0] = a0.x; a[1] = a0.y; a[2] = a1.x; a[3] = a1.y; a[4] = a2.x; a[5] = a2.y;
+  } else {
+    float2 v = *reinterpret_cast<const float2 *>(actions + i * 2);
+    a[0] = v.x; a[1] = v.y;
+  }
+}
+template <int KIND> __device__ __forceinline__ void store_obs(float *obs, int64_t i, const float *o) {
+  if (KIND == TB_ENV_SWING) {
+    float2 *p = reinterpret_cast<float2 *>(obs + i * 6);
+    p[0] = make_float2(o[0], o[1]); p[1] = make_float2(o[2], o[3]); p[2] = make_float2(o[4], o[5]);
+  } else {
+    float4 *p = reinterpret_cast<float4 *>(obs + i * 12);
+    p[0] = make_float4(o[0], o[1], o[2], o[3]); p[1] = make_float4(o[4], o[5], o[6], o[7]);
+    p[2] = make_float4(o[8], o[9], o[10], o[11]);
+  }
+}
+
+// Episode bookkeeping shared by the API-mode and fused-rollout kernels.
+template <typename T, int KIND>
+__device__ __forceinline__ void finish_step(const Scene<T> &sc, const StepIO &io, int64_t i, St<T> &s, const StepOut &o,
+                                            Acc &acc, float *ob, bool write_terminal) {
+  s.ret += (T)o.reward;
+  acc.nphys += o.nphys;
+  acc.nsteps += 1;
+  acc.hits += o.hit_steps;
+  pack_obs<T, KIND>(s, ob);
+  if (o.done) {
+    acc.episodes += 1;
+    acc.sum_len += s.step;
+    acc.goals += (o.events & TB_EV_GOAL_BALL) ? 1 : 0;
+    acc.courts += (o.events & TB_EV_COURT_BALL) ? 1 : 0;
+    acc.timeouts += ((o.events & TB_EV_TIMEOUT) && !(o.events & (TB_EV_GOAL_BALL | TB_EV_COURT_BALL | TB_EV_BALL_PASSED))) ? 1 : 0;
+    double r = (double)s.ret;
+    acc.ret_q20 += __double2ll_rn(r * 1048576.0);
+    acc.ret2_q10 += __double2ll_rn(r * r * 1024.0);
+    if (write_terminal && io.term_obs) store_obs<KIND>(io.term_obs, i, ob);
+    if (io.auto_reset) {
+      uint32_t ep = s.episode + 1;
+      T in[TB_INIT_WORDS];
+      draw_init<T, KIND>(io.seed, (uint64_t)(io.id_offset + i), ep, in);
+      start_episode<T, KIND>(sc, s, in, ep);
+      pack_obs<T, KIND>(s, ob);
+    }
+  }
+}
+
+// API mode: one env step per launch, actions from HBM, obs/reward/done to HBM.
+template <typename T, int KIND>
+__global__ void __launch_bounds__(kBlock) step_kernel(const __grid_constant__ Scene<T> sc, const __grid_constant__ StepIO io) {
+  int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+  Acc acc = {};
+  if (i < io.n) {
+    T *base = static_cast<T *>(io.state);
+    St<T> s;
+    load_state(base, io.n, i, s);
+    float a[6];
+    load_action<KIND>(io.actions, i, a);
+    StepOut o;
+    env_step<T, KIND>(sc, s, a, o);
+    float ob[12];
+    finish_step<T, KIND>(sc, io, i, s, o, acc, ob, true);
+    store_obs<KIND>(io.obs, i, ob);
+    io.reward[i] = o.reward;
+    io.done[i] = (uint8_t)o.done;
+    if (io.events) io.events[i] = (uint8_t)o.events;
+    store_state(base, io.n, i, s);
+  }
+  flush_stats(acc, io.stats);
+}
+
+// Fused mode: K env steps per launch with in-kernel actions; state stays in registers for the whole rollout.
+template <typename T, int KIND>
+__global__ void __launch_bounds__(kBlock) rollout_kernel(const __grid_constant__ Scene<T> sc, const __grid_constant__ StepIO io) {
+  int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+  Acc acc = {};
+  if (i < io.n) {
+    T *base = static_cast<T *>(io.state);
+    St<T> s;
+    load_state(base, io.n, i, s);
+    float ob[12] = {0};
+    float rsum = 0;
+    int dcount = 0;
+#pragma unroll 1
+    for (int t = 0; t < io.k_steps; ++t) {
+      float a[8];
+      uint32_t r[4];
+#pragma unroll
+      for (int b = 0; b * 4 < Dims<KIND>::act; ++b) {
+        philox4x32(io.seed, (uint64_t)(io.id_offset + i), s.episode, stream_word(kStreamAction, (uint32_t)s.step, b), r);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) a[b * 4 + q] = 2.0f * u01<float>(r[q]) - 1.0f;
+      }
+      StepOut o;
+      env_step<T, KIND>(sc, s, a, o);
+      finish_step<T, KIND>(sc, io, i, s, o, acc, ob, false);
+      rsum += o.reward;
+      dcount += o.done;
+    }
+    if (io.obs) store_obs<KIND>(io.obs, i, ob);
+    if (io.reward_sum) io.reward_sum[i] = rsum;
+    if (io.done_count) io.done_count[i] = dcount;
+    store_state(base, io.n, i, s);
+  }
+  flush_stats(acc, io.stats);
+}
+
+template <typename T, int KIND>
+__global__ void __launch_bounds__(kBlock) reset_kernel(const __grid_constant__ Scene<T> sc, const __grid_constant__ StepIO io,
+                                                       const double *init, const uint8_t *mask) {
+  int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+  if (i >= io.n) return;
+  if (mask && !mask[i]) return;
+  T *base = static_cast<T *>(io.state);
+  St<T> s;
+  load_state(base, io.n, i, s);
+  uint32_t ep = s.episode + 1;  // a fresh context holds episode = 0xffffffff
+  T in[TB_INIT_WORDS];
+  if (init) {
+#pragma unroll
+    for (int j = 0; j < TB_INIT_WORDS; ++j) in[j] = (T)init[i * TB_INIT_WORDS + j];
+  } else {
+    draw_init<T, KIND>(io.seed, (uint64_t)(io.id_offset + i), ep, in);
+  }
+  start_episode<T, KIND>(sc, s, in, ep);
+  store_state(base, io.n, i, s);
+  if (io.obs) {
+    float ob[12];
+    pack_obs<T, KIND>(s, ob);
+    store_obs<KIND>(io.obs, i, ob);
+  }
+}
+
+// canonical double [N, 32] record <-> packed state
+template <typename T> __global__ void get_state_kernel(const T *base, int64_t n, double *out) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  St<T> s;
+  load_state(base, n, i, s);
+  double *o = out + i * TB_STATE_WORDS;
+  for (int j = 0; j < 3; ++j) {
+    o[TB_S_RACKET_POS + j] = s.rp[j]; o[TB_S_RACKET_VEL + j] = s.rv[j]; o[TB_S_RACKET_ANGVEL + j] = s.rw[j];
+    o[TB_S_BALL_POS + j] = s.bp[j]; o[TB_S_BALL_VEL + j] = s.bv[j]; o[TB_S_BALL_ANGVEL + j] = s.bw[j];
+    o[TB_S_AUX + j] = s.aux[j];
+  }
+  for (int j = 0; j < 4; ++j) o[TB_S_RACKET_QUAT + j] = s.rq[j];
+  o[TB_S_GOAL] = s.goal[0]; o[TB_S_GOAL + 1] = s.goal[1]; o[TB_S_D0] = s.d0; o[TB_S_RETURN] = s.ret;
+  o[TB_S_STEP] = s.step; o[TB_S_FLAGS] = s.flags; o[TB_S_EPISODE] = (double)(int32_t)s.episode;
+}
+template <typename T> __global__ void set_state_kernel(T *base, int64_t n, const double *in) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  St<T> s;
+  const double *o = in + i * TB_STATE_WORDS;
+  for (int j = 0; j < 3; ++j) {
+    s.rp[j] = (T)o[TB_S_RACKET_POS + j]; s.rv[j] = (T)o[TB_S_RACKET_VEL + j]; s.rw[j] = (T)o[TB_S_RACKET_ANGVEL + j];
+    s.bp[j] = (T)o[TB_S_BALL_POS + j]; s.bv[j] = (T)o[TB_S_BALL_VEL + j]; s.bw[j] = (T)o[TB_S_BALL_ANGVEL + j];
+    s.aux[j] = (T)o[TB_S_AUX + j];
+  }
+  for (int j = 0; j < 4; ++j) s.rq[j] = (T)o[TB_S_RACKET_QUAT + j];
+  s.goal[0] = (T)o[TB_S_GOAL]; s.goal[1] = (T)o[TB_S_GOAL + 1]; s.d0 = (T)o[TB_S_D0]; s.ret = (T)o[TB_S_RETURN];
+  s.step = (int)o[TB_S_STEP]; s.flags = (int)o[TB_S_FLAGS]; s.episode = (uint32_t)(int32_t)o[TB_S_EPISODE];
+  store_state(base, n, i, s);
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+struct Params {  // order matches k_param_names
+  double dt, gravity_z, lin_damping, ang_damping, max_coord_vel, rest_ball_racket, rest_ball_court, rest_ball_goal,
+      fric_ball_racket, fric_ball_court, fric_ball_goal, contact_erp, linear_slop, rest_vel_threshold,
+      solver_iterations, solver_residual, contact_threshold, hull_margin, box_margin, gyro_term, racket_scale;
+};
+static const char *k_param_names[] = {
+    "dt", "gravity_z", "lin_damping", "ang_damping", "max_coord_vel", "rest_ball_racket", "rest_ball_court",
+    "rest_ball_goal", "fric_ball_racket", "fric_ball_court", "fric_ball_goal", "contact_erp", "linear_slop",
+    "rest_vel_threshold", "solver_iterations", "solver_residual", "contact_threshold", "hull_margin",
+    "box_margin", "gyro_term", "racket_scale"};
+constexpr int kNumParams = sizeof(k_param_names) / sizeof(k_param_names[0]);
+static_assert(sizeof(Params) == kNumParams * sizeof(double), "Params / name table mismatch");
+
+static void params_default(Params &p) {
+  p.dt = 1.0 / 240.0;          // fixed PyBullet time step [R]
+  p.gravity_z = -9.81;         // swingracket_env.py:154
+  p.lin_damping = 0.04;        // btMultiBody default, a = -v (k + k|v|) [R]
+  p.ang_damping = 0.04;
+  p.max_coord_vel = 100.0;
+  p.rest_ball_racket = 0.9 * 0.9;  // racket.py:43 x objects.py:48
+  p.rest_ball_court = 0.9 * 0.9;   // objects.py:29 x objects.py:48
+  p.rest_ball_goal = 0.0;          // goal keeps Bullet's default restitution 0
+  p.fric_ball_racket = 0.2 * 0.2;
+  p.fric_ball_court = 0.2 * 0.2;
+  p.fric_ball_goal = 0.2 * 0.5;
+  p.contact_erp = 0.08;
+  p.linear_slop = 1e-5;
+  p.rest_vel_threshold = 0.2;
+  p.solver_iterations = 50;
+  p.solver_residual = 1e-7;
+  p.contact_threshold = 0.02 * std::sqrt(3.0) * TB_BALL_RADIUS;
+  p.hull_margin = TB_URDF_MARGIN;
+  p.box_margin = TB_URDF_MARGIN;
+  p.gyro_term = 1.0;
+  p.racket_scale = 1.0;
+}
+
+template <typename T, int NE> static void build_prism(Prism<T, NE> &pr, const double (*v)[2], double half_thick) {
+  double r2 = 0;
+  for (int i = 0; i < NE; ++i) {
+    const double *a = v[i], *b = v[(i + 1) % NE];
+    double ex = b[0] - a[0], ey = b[1] - a[1], l2 = ex * ex + ey * ey, il = 1.0 / std::sqrt(l2);
+    pr.e[i].ax = (T)a[0]; pr.e[i].ay = (T)a[1]; pr.e[i].ex = (T)ex; pr.e[i].ey = (T)ey;
+    pr.e[i].inv_len2 = (T)(1.0 / l2); pr.e[i].nx = (T)(ey * il); pr.e[i].ny = (T)(-ex * il);
+    double d2 = a[0] * a[0] + a[1] * a[1] + half_thick * half_thick;
+    if (d2 > r2) r2 = d2;
+  }
+  pr.half_thick = (T)half_thick;
+  pr.bound_radius = (T)std::sqrt(r2);
+}
+
+struct HostScene {  // double-precision master copy; Scene<T> is derived from it
+  double racket_v[kRacketEdges][2], goal_v[kGoalEdges][2], racket_half_x, racket_inertia[3], com_z, swing_q[4], swing_off[3];
+};
+static void build_host_scene(const Params &p, HostScene &h) {
+  double s = p.racket_scale, ymin = 1e30, ymax = -1e30, zmin = 1e30, zmax = -1e30;
+  for (int i = 0; i < kRacketEdges; ++i) {
+    double y = TB_RACKET_OUTLINE[i][0], z = TB_RACKET_OUTLINE[i][1];
+    ymin = std::fmin(ymin, y); ymax = std::fmax(ymax, y); zmin = std::fmin(zmin, z); zmax = std::fmax(zmax, z);
+    h.racket_v[i][0] = s * y;                      // COM frame = link frame shifted by the inertial origin
+    h.racket_v[i][1] = s * (z - TB_RACKET_COM_Z);  // racket.urdf:18-19
+  }
+  h.racket_half_x = s * TB_RACKET_HALF_X;
+  h.com_z = s * TB_RACKET_COM_Z;
+  // Bullet recomputes the inertia from the compound's AABB (margin included) as a solid box [R]
+  double m = p.hull_margin, ex = s * 2 * TB_RACKET_HALF_X + 2 * m, ey = s * (ymax - ymin) + 2 * m, ez = s * (zmax - zmin) + 2 * m;
+  h.racket_inertia[0] = TB_RACKET_MASS / 12.0 * (ey * ey + ez * ez);
+  h.racket_inertia[1] = TB_RACKET_MASS / 12.0 * (ex * ex + ez * ez);
+  h.racket_inertia[2] = TB_RACKET_MASS / 12.0 * (ex * ex + ey * ey);
+  // goal: PyBullet turns the URDF cylinder into a 32-gon prism, vertices (R sin, R cos) clockwise; store CCW
+  for (int i = 0; i < kGoalEdges; ++i) {
+    double th = 6.283185307179586476925286766559 * ((double)(kGoalEdges - 1 - i) / kGoalEdges);
+    h.goal_v[i][0] = TB_GOAL_RADIUS * std::sin(th);
+    h.goal_v[i][1] = TB_GOAL_RADIUS * std::cos(th);
+  }
+  // swing spawn: rpy (0, 0.5, 0) (swingracket_env.py:165) -> q = (0, sin .25, 0, cos .25); COM = base + R (0,0,com_z)
+  double q[4] = {0, std::sin(0.25), 0, std::cos(0.25)};
+  for (int i = 0; i < 4; ++i) h.swing_q[i] = q[i];
+  double x = q[0], y = q[1], z = q[2], w = q[3];
+  h.swing_off[0] = 2 * (x * z + y * w) * h.com_z;
+  h.swing_off[1] = 2 * (y * z - x * w) * h.com_z;
+  h.swing_off[2] = (1 - 2 * (x * x + y * y)) * h.com_z;
+}
+template <typename T> static void build_scene(const Params &p, Scene<T> &sc) {
+  HostScene h;
+  build_host_scene(p, h);
+  std::memset(&sc, 0, sizeof sc);
+  sc.dt = (T)p.dt; sc.gravity_z = (T)p.gravity_z; sc.lin_damping = (T)p.lin_damping; sc.ang_damping = (T)p.ang_damping;
+  sc.max_coord_vel = (T)p.max_coord_vel;
+  sc.rest_racket = (T)p.rest_ball_racket; sc.rest_court = (T)p.rest_ball_court; sc.rest_goal = (T)p.rest_ball_goal;
+  sc.mu_racket = (T)p.fric_ball_racket; sc.mu_court = (T)p.fric_ball_court; sc.mu_goal = (T)p.fric_ball_goal;
+  sc.erp = (T)p.contact_erp; sc.slop = (T)p.linear_slop; sc.rest_vel_threshold = (T)p.rest_vel_threshold;
+  sc.solver_residual = (T)p.solver_residual; sc.contact_threshold = (T)p.contact_threshold;
+  sc.hull_margin = (T)p.hull_margin; sc.box_margin = (T)p.box_margin; sc.gyro = (T)p.gyro_term;
+  sc.iters = (int)p.solver_iterations;
+  sc.ball_r = (T)TB_BALL_RADIUS;
+  sc.ball_inv_m = (T)(1.0 / TB_BALL_MASS);
+  sc.ball_inv_i = (T)(1.0 / (0.4 * TB_BALL_MASS * TB_BALL_RADIUS * TB_BALL_RADIUS));  // sphere inertia recomputed [R]
+  sc.racket_inv_m = (T)(1.0 / TB_RACKET_MASS);
+  for (int i = 0; i < 3; ++i) { sc.racket_i[i] = (T)h.racket_inertia[i]; sc.racket_inv_i[i] = (T)(1.0 / h.racket_inertia[i]); }
+  sc.com_z = (T)h.com_z;
+  for (int i = 0; i < 4; ++i) sc.swing_q[i] = (T)h.swing_q[i];
+  for (int i = 0; i < 3; ++i) sc.swing_off[i] = (T)h.swing_off[i];
+  sc.floor_h[0] = (T)TB_FLOOR_HX; sc.floor_h[1] = (T)TB_FLOOR_HY; sc.floor_h[2] = (T)TB_FLOOR_HZ;
+  sc.net_h[0] = (T)TB_NET_HX; sc.net_h[1] = (T)TB_NET_HY; sc.net_h[2] = (T)TB_NET_HZ;
+  sc.goal_r = (T)TB_GOAL_RADIUS; sc.goal_hz = (T)TB_GOAL_HALF_Z;
+  build_prism<T, kRacketEdges>(sc.racket, h.racket_v, h.racket_half_x);
+  build_prism<T, kGoalEdges>(sc.goal, h.goal_v, TB_GOAL_HALF_Z);
+}
+
+}  // namespace tb
+
+// ================================================================================================ C ABI
+using namespace tb;
+
+static thread_local char g_err[512];
+static int fail(const char *fmt, const char *detail = "") {
+  std::snprintf(g_err, sizeof g_err, fmt, detail);
+  return 1;
+}
+#define CU(call)                                                                     \
+  do {                                                                               \
+    cudaError_t e_ = (call);                                                         \
+    if (e_ != cudaSuccess) {                                                         \
+      std::snprintf(g_err, sizeof g_err, "%s failed: %s", #call, cudaGetErrorString(e_)); \
+      return 1;                                                                      \
+    }                                                                                \
+  } while (0)
+
+struct tb_ctx {
+  tb_config cfg;
+  Params params;
+  Scene<float> sc32;
+  Scene<double> sc64;
+  void *state = nullptr;
+  unsigned long long *stats = nullptr;
+  cudaStream_t own_stream = nullptr;
+  // device staging for the host-buffer entry points
+  float *d_actions = nullptr, *d_obs = nullptr, *d_reward = nullptr, *d_term = nullptr;
+  uint8_t *d_done = nullptr, *d_events = nullptr, *d_mask = nullptr;
+  int64_t launches = 0;
+};
+
+struct DeviceGuard {
+  int prev = -1;
+  bool ok;
+  explicit DeviceGuard(int dev) { ok = cudaGetDevice(&prev) == cudaSuccess && cudaSetDevice(dev) == cudaSuccess; }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+#define GUARD(ctx)                                               \
+  if (!(ctx)) return fail("%s", "context is NULL");              \
+  DeviceGuard guard_((ctx)->cfg.device);                         \
+  if (!guard_.ok) return fail("%s", "cudaSetDevice failed")
+
+static void rebuild(tb_ctx *c) {
+  build_scene<float>(c->params, c->sc32);
+  build_scene<double>(c->params, c->sc64);
+}
+static unsigned grid_for(int64_t n, int block) { return (unsigned)((n + block - 1) / block); }
+static StepIO make_io(tb_ctx *c) {
+  StepIO io;
+  std::memset(&io, 0, sizeof io);
+  io.state = c->state; io.n = c->cfg.num_envs; io.id_offset = c->cfg.env_id_offset; io.seed = c->cfg.seed;
+  io.auto_reset = c->cfg.auto_reset; io.stats = c->stats; io.k_steps = 1;
+  return io;
+}
+
+extern "C" {
+
+const char *tb_last_error(void) { return g_err; }
+int tb_abi_version(void) { return TB_ABI_VERSION; }
+int tb_obs_dim(int kind) { return kind == TB_ENV_SWING ? 6 : kind == TB_ENV_HIT ? 12 : -1; }
+int tb_act_dim(int kind) { return kind == TB_ENV_SWING ? 6 : kind == TB_ENV_HIT ? 2 : -1; }
+int tb_num_params(void) { return kNumParams; }
+const char *tb_param_name(int i) { return (i >= 0 && i < kNumParams) ? k_param_names[i] : nullptr; }
+
+int tb_scene_constant(const char *name, int index, double *value) {
+  if (!name || !value) return fail("%s", "tb_scene_constant: bad argument");
+  Params p;
+  params_default(p);
+  HostScene h;
+  build_host_scene(p, h);
+#define SC(nm, v) if (std::strcmp(name, nm) == 0) { *value = (v); return 0; }
+  SC("urdf_margin", TB_URDF_MARGIN) SC("ball_radius", TB_BALL_RADIUS) SC("ball_mass", TB_BALL_MASS)
+  SC("racket_mass", TB_RACKET_MASS) SC("racket_com_z", TB_RACKET_COM_Z) SC("racket_half_x", TB_RACKET_HALF_X)
+  SC("floor_hx", TB_FLOOR_HX) SC("floor_hy", TB_FLOOR_HY) SC("floor_hz", TB_FLOOR_HZ)
+  SC("net_hx", TB_NET_HX) SC("net_hy", TB_NET_HY) SC("net_hz", TB_NET_HZ)
+  SC("goal_radius", TB_GOAL_RADIUS) SC("goal_half_z", TB_GOAL_HALF_Z) SC("goal_sides", TB_GOAL_SIDES)
+  SC("racket_outline_n", TB_RACKET_OUTLINE_N) SC("contact_threshold", p.contact_threshold)
+#undef SC
+  if (!std::strcmp(name, "racket_inertia") && index >= 0 && index < 3) { *value = h.racket_inertia[index]; return 0; }
+  if (!std::strcmp(name, "racket_outline_y") && index >= 0 && index < kRacketEdges) { *value = TB_RACKET_OUTLINE[index][0]; return 0; }
+  if (!std::strcmp(name, "racket_outline_z") && index >= 0 && index < kRacketEdges) { *value = TB_RACKET_OUTLINE[index][1]; return 0; }
+  if (!std::strcmp(name, "goal_vertex_x") && index >= 0 && index < kGoalEdges) { *value = h.goal_v[index][0]; return 0; }
+  if (!std::strcmp(name, "goal_vertex_y") && index >= 0 && index < kGoalEdges) { *value = h.goal_v[index][1]; return 0; }
+  return fail("tb_scene_constant: unknown name or index '%s'", name);
+}
+
+int tb_create(const tb_config *cfg, tb_ctx **out) {
+  if (!cfg || !out) return fail("%s", "tb_create: bad argument");
+  if (cfg->struct_size != sizeof(tb_config)) return fail("%s", "tb_create: tb_config.struct_size mismatch");
+  if (cfg->env_kind != TB_ENV_SWING && cfg->env_kind != TB_ENV_HIT) return fail("%s", "tb_create: unknown env_kind");
+  if (cfg->precision != TB_F32 && cfg->precision != TB_F64) return fail("%s", "tb_create: unknown precision");
+  if (cfg->num_envs <= 0) return fail("%s", "tb_create: num_envs must be positive");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail("%s", "tb_create: no CUDA device (this library has no CPU fallback)");
+  if (cfg->device < 0 || cfg->device >= ndev) return fail("%s", "tb_create: device ordinal out of range");
+  cudaDeviceProp prop;
+  CU(cudaGetDeviceProperties(&prop, cfg->device));
+  if (prop.major != 10) return fail("%s", "tb_create: device is not sm_100 (library is built for sm_100a only)");
+  tb_ctx *c = new (std::nothrow) tb_ctx();
+  if (!c) return fail("%s", "tb_create: out of memory");
+  c->cfg = *cfg;
+  params_default(c->params);
+  rebuild(c);
+  DeviceGuard g(cfg->device);
+  if (!g.ok) { delete c; return fail("%s", "tb_create: cudaSetDevice failed"); }
+  size_t word = cfg->precision == TB_F64 ? 8 : 4;
+  size_t bytes = (size_t)cfg->num_envs * kPacks * 4 * word;
+  cudaError_t e = cudaMalloc(&c->state, bytes);
+  if (e == cudaSuccess) e = cudaMalloc(&c->stats, TB_NUM_STATS * sizeof(unsigned long long));
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaMemsetAsync(c->state, 0, bytes, c->own_stream);
+  if (e == cudaSuccess) e = cudaMemsetAsync(c->stats, 0, TB_NUM_STATS * sizeof(unsigned long long), c->own_stream);
+  if (e == cudaSuccess) {
+    // identity quaternion, episode = -1 so the first reset starts episode 0
+    std::size_t n = (size_t)cfg->num_envs;
+    double *tmp = (double *)std::calloc(n * TB_STATE_WORDS, sizeof(double));
+    double *dtmp = nullptr;
+    if (!tmp) e = cudaErrorMemoryAllocation;
+    if (e == cudaSuccess) {
+      for (size_t i = 0; i < n; ++i) { tmp[i * TB_STATE_WORDS + TB_S_RACKET_QUAT + 3] = 1.0; tmp[i * TB_STATE_WORDS + TB_S_EPISODE] = -1.0; }
+      e = cudaMalloc(&dtmp, n * TB_STATE_WORDS * sizeof(double));
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dtmp, tmp, n * TB_STATE_WORDS * sizeof(double), cudaMemcpyHostToDevice, c->own_stream);
+    if (e == cudaSuccess) {
+      if (cfg->precision == TB_F64) set_state_kernel<double><<<grid_for(cfg->num_envs, 256), 256, 0, c->own_stream>>>((double *)c->state, cfg->num_envs, dtmp);
+      else set_state_kernel<float><<<grid_for(cfg->num_envs, 256), 256, 0, c->own_stream>>>((float *)c->state, cfg->num_envs, dtmp);
+      e = cudaGetLastError();
+      c->launches++;
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->own_stream);
+    if (dtmp) cudaFree(dtmp);
+    std::free(tmp);
+  }
+  if (e != cudaSuccess) {
+    std::snprintf(g_err, sizeof g_err, "tb_create: %s", cudaGetErrorString(e));
+    tb_destroy(c);
+    return 1;
+  }
+  *out = c;
+  return 0;
+}
+
+int tb_destroy(tb_ctx *c) {
+  if (!c) return 0;
+  DeviceGuard g(c->cfg.device);
+  if (c->own_stream) { cudaStreamSynchronize(c->own_stream); cudaStreamDestroy(c->own_stream); }
+  cudaFree(c->state); cudaFree(c->stats);
+  cudaFree(c->d_actions); cudaFree(c->d_obs); cudaFree(c->d_reward); cudaFree(c->d_term);
+  cudaFree(c->d_done); cudaFree(c->d_events); cudaFree(c->d_mask);
+  delete c;
+  return 0;
+}
+
+int tb_set_param(tb_ctx *c, const char *name, double value) {
+  if (!c || !name) return fail("%s", "tb_set_param: bad argument");
+  double *slots = reinterpret_cast<double *>(&c->params);
+  for (int i = 0; i < kNumParams; ++i)
+    if (!std::strcmp(name, k_param_names[i])) { slots[i] = value; rebuild(c); return 0; }
+  return fail("tb_set_param: unknown parameter '%s'", name);
+}
+int tb_get_param(tb_ctx *c, const char *name, double *value) {
+  if (!c || !name || !value) return fail("%s", "tb_get_param: bad argument");
+  const double *slots = reinterpret_cast<const double *>(&c->params);
+  for (int i = 0; i < kNumParams; ++i)
+    if (!std::strcmp(name, k_param_names[i])) { *value = slots[i]; return 0; }
+  return fail("tb_get_param: unknown parameter '%s'", name);
+}
+
+#define DISPATCH(KERNEL, grid, block, stream, ...)                                                          \
+  do {                                                                                                      \
+    if (c->cfg.precision == TB_F64) {                                                                       \
+      if (c->cfg.env_kind == TB_ENV_SWING) KERNEL<double, TB_ENV_SWING><<<grid, block, 0, stream>>>(c->sc64, __VA_ARGS__); \
+      else KERNEL<double, TB_ENV_HIT><<<grid, block, 0, stream>>>(c->sc64, __VA_ARGS__);                      \
+    } else {                                                                                                \
+      if (c->cfg.env_kind == TB_ENV_SWING) KERNEL<float, TB_ENV_SWING><<<grid, block, 0, stream>>>(c->sc32, __VA_ARGS__); \
+      else KERNEL<float, TB_ENV_HIT><<<grid, block, 0, stream>>>(c->sc32, __VA_ARGS__);                       \
+    }                                                                                                       \
+    c->launches++;                                                                                          \
+  } while (0)
+
+static int reset_impl(tb_ctx *c, const double *d_init, const uint8_t *d_mask, float *d_obs, void *stream) {
+  GUARD(c);
+  StepIO io = make_io(c);
+  io.obs = d_obs;
+  DISPATCH(reset_kernel, grid_for(io.n, kBlock), kBlock, (cudaStream_t)stream, io, d_init, d_mask);
+  CU(cudaGetLastError());
+  return 0;
+}
+int tb_reset(tb_ctx *c, const uint8_t *d_mask, float *d_obs, void *stream) { return reset_impl(c, nullptr, d_mask, d_obs, stream); }
+int tb_reset_from(tb_ctx *c, const double *d_init, const uint8_t *d_mask, float *d_obs, void *stream) {
+  if (!d_init) return fail("%s", "tb_reset_from: d_init is NULL");
+  return reset_impl(c, d_init, d_mask, d_obs, stream);
+}
+
+int tb_step(tb_ctx *c, const float *d_actions, float *d_obs, float *d_reward, uint8_t *d_done, float *d_terminal_obs,
+            uint8_t *d_events, void *stream) {
+  GUARD(c);
+  if (!d_actions || !d_obs || !d_reward || !d_done) return fail("%s", "tb_step: actions, obs, reward and done are required");
+  StepIO io = make_io(c);
+  io.actions = d_actions; io.obs = d_obs; io.reward = d_reward; io.done = d_done; io.term_obs = d_terminal_obs;
+  io.events = d_events;
+  DISPATCH(step_kernel, grid_for(io.n, kBlock), kBlock, (cudaStream_t)stream, io);
+  CU(cudaGetLastError());
+  return 0;
+}
+
+int tb_rollout(tb_ctx *c, int action_mode, int k_steps, float *d_obs, float *d_reward_sum, int32_t *d_done_count, void *stream) {
+  GUARD(c);
+  if (action_mode != TB_ACT_RANDOM) return fail("%s", "tb_rollout: unknown action mode");
+  if (k_steps < 0) return fail("%s", "tb_rollout: k_steps must be >= 0");
+  StepIO io = make_io(c);
+  io.k_steps = k_steps; io.obs = d_obs; io.reward_sum = d_reward_sum; io.done_count = d_done_count;
+  DISPATCH(rollout_kernel, grid_for(io.n, kBlock), kBlock, (cudaStream_t)stream, io);
+  CU(cudaGetLastError());
+  return 0;
+}
+
+int tb_get_state(tb_ctx *c, double *d_state, void *stream) {
+  GUARD(c);
+  if (!d_state) return fail("%s", "tb_get_state: d_state is NULL");
+  int64_t n = c->cfg.num_envs;
+  if (c->cfg.precision == TB_F64) get_state_kernel<double><<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>((const double *)c->state, n, d_state);
+  else get_state_kernel<float><<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>((const float *)c->state, n, d_state);
+  c->launches++;
+  CU(cudaGetLastError());
+  return 0;
+}
+int tb_set_state(tb_ctx *c, const double *d_state, void *stream) {
+  GUARD(c);
+  if (!d_state) return fail("%s", "tb_set_state: d_state is NULL");
+  int64_t n = c->cfg.num_envs;
+  if (c->cfg.precision == TB_F64) set_state_kernel<double><<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>((double *)c->state, n, d_state);
+  else set_state_kernel<float><<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>((float *)c->state, n, d_state);
+  c->launches++;
+  CU(cudaGetLastError());
+  return 0;
+}
+
+int tb_stats_device_ptr(tb_ctx *c, int64_t **d_stats) {
+  if (!c || !d_stats) return fail("%s", "tb_stats_device_ptr: bad argument");
+  *d_stats = reinterpret_cast<int64_t *>(c->stats);
+  return 0;
+}
+int tb_read_stats(tb_ctx *c, int64_t *h_stats, int clear, void *stream) {
+  GUARD(c);
+  if (!h_stats) return fail("%s", "tb_read_stats: h_stats is NULL");
+  cudaStream_t s = (cudaStream_t)stream;
+  CU(cudaMemcpyAsync(h_stats, c->stats, TB_NUM_STATS * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+  if (clear) CU(cudaMemsetAsync(c->stats, 0, TB_NUM_STATS * sizeof(int64_t), s));
+  CU(cudaStreamSynchronize(s));
+  return 0;
+}
+
+static int ensure_staging(tb_ctx *c) {
+  if (c->d_actions) return 0;
+  size_t n = (size_t)c->cfg.num_envs, od = (size_t)tb_obs_dim(c->cfg.env_kind), ad = (size_t)tb_act_dim(c->cfg.env_kind);
+  CU(cudaMalloc(&c->d_actions, n * ad * sizeof(float)));
+  CU(cudaMalloc(&c->d_obs, n * od * sizeof(float)));
+  CU(cudaMalloc(&c->d_term, n * od * sizeof(float)));
+  CU(cudaMalloc(&c->d_reward, n * sizeof(float)));
+  CU(cudaMalloc(&c->d_done, n));
+  CU(cudaMalloc(&c->d_events, n));
+  CU(cudaMalloc(&c->d_mask, n));
+  return 0;
+}
+
+int tb_reset_host(tb_ctx *c, const uint8_t *h_mask, float *h_obs) {
+  GUARD(c);
+  if (ensure_staging(c)) return 1;
+  size_t n = (size_t)c->cfg.num_envs, od = (size_t)tb_obs_dim(c->cfg.env_kind);
+  cudaStream_t s = c->own_stream;
+  if (h_mask) CU(cudaMemcpyAsync(c->d_mask, h_mask, n, cudaMemcpyHostToDevice, s));
+  if (reset_impl(c, nullptr, h_mask ? c->d_mask : nullptr, c->d_obs, s)) return 1;
+  if (h_obs) CU(cudaMemcpyAsync(h_obs, c->d_obs, n * od * sizeof(float), cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));
+  return 0;
+}
+
+int tb_step_host(tb_ctx *c, const float *h_actions, float *h_obs, float *h_reward, uint8_t *h_done, float *h_terminal_obs,
+                 uint8_t *h_events) {
+  GUARD(c);
+  if (!h_actions || !h_obs || !h_reward || !h_done) return fail("%s", "tb_step_host: actions, obs, reward and done are required");
+  if (ensure_staging(c)) return 1;
+  size_t n = (size_t)c->cfg.num_envs, od = (size_t)tb_obs_dim(c->cfg.env_kind), ad = (size_t)tb_act_dim(c->cfg.env_kind);
+  cudaStream_t s = c->own_stream;
+  CU(cudaMemcpyAsync(c->d_actions, h_actions, n * ad * sizeof(float), cudaMemcpyHostToDevice, s));
+  if (tb_step(c, c->d_actions, c->d_obs, c->d_reward, c->d_done, h_terminal_obs ? c->d_term : nullptr,
+              h_events ? c->d_events : nullptr, s))
+    return 1;
+  CU(cudaMemcpyAsync(h_obs, c->d_obs, n * od * sizeof(float), cudaMemcpyDeviceToHost, s));
+  CU(cudaMemcpyAsync(h_reward, c->d_reward, n * sizeof(float), cudaMemcpyDeviceToHost, s));
+  CU(cudaMemcpyAsync(h_done, c->d_done, n, cudaMemcpyDeviceToHost, s));
+  if (h_terminal_obs) CU(cudaMemcpyAsync(h_terminal_obs, c->d_term, n * od * sizeof(float), cudaMemcpyDeviceToHost, s));
+  if (h_events) CU(cudaMemcpyAsync(h_events, c->d_events, n, cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));
+  return 0;
+}
+
+int tb_launch_count(tb_ctx *c, int64_t *launches) {
+  if (!c || !launches) return fail("%s", "tb_launch_count: bad argument");
+  *launches = c->launches;
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,106 @@
+"""GPU parity tests: CUDA path (through the C ABI) vs the CPU oracle on identical seeded inputs.
+
+Bars (north star): contact / hit events and done flags exact; poses and rewards within a float tolerance.
+  f64 path: every event and done flag identical over the whole horizon; state within 1e-9, float32 outputs 2e-6.
+  f32 path: identical except for near-threshold flips, i.e. discrete mismatches where the oracle's own margin
+            |quantity - threshold| is below BAND_F32; envs that flipped are dropped from then on and counted.
+"""
+import numpy as np
+import pytest
+
+from tests.harness import reference_reset_params, run_parity
+
+pytestmark = pytest.mark.gpu
+
+TOL_F64_STATE = 5e-8   # absolute, on a state record whose spin entries reach ~50 rad/s after a bounce
+TOL_F64_OUT = 2e-6      # float32 rounding of the outputs at |x| <= 20
+BAND_F32 = 2e-3         # metres: fp32 position drift over an 800-substep flight stays far below this
+TOL_F32_OUT = 5e-3
+
+
+def _make(env, n, precision, seed, oracle_lib):
+    from tennisbot_rl_b200.batch import TennisBatch
+
+    b = TennisBatch(env, n, device=0, seed=seed, precision=precision)
+    o = oracle_lib.OracleEnv(env, n, seed=seed, threads=8)
+    return b, o
+
+
+@pytest.mark.parametrize("env,steps", [("SwingRacket-v0", 80), ("Tennisbot-v0", 1200)])
+def test_f64_parity_random_actions(oracle_lib, env, steps):
+    """config 2 shape: 4096 envs, random actions, explicit initial states, horizon > 3 episodes (swing) /
+    beyond the 1000-step time-out (hit); crosses in-kernel auto-resets (Philox placement parity)."""
+    n = 4096
+    b, o = _make(env, n, "f64", 11, oracle_lib)
+    rng = np.random.default_rng(5)
+    init = reference_reset_params(o.kind, n, rng)
+    g0 = b.reset(init=init).cpu().numpy()
+    o0 = o.reset(init=init)
+    np.testing.assert_array_equal(g0, o0)
+    rep, valid = run_parity(b, o, steps, lambda t, _obs: rng.uniform(-1, 1, (n, o.act_dim)), band=0.0, check_state_every=20)
+    print(rep)
+    assert rep.event_mismatch_hard == 0 and rep.event_mismatch_near == 0
+    assert rep.max_state_err < TOL_F64_STATE
+    assert rep.max_obs_err < TOL_F64_OUT and rep.max_reward_err < TOL_F64_OUT
+    np.testing.assert_array_equal(b.read_stats(), o.read_stats())
+
+
+def test_f64_parity_trained_policy(oracle_lib):
+    """Saved PPO policy (tests/golden/ppo_swing_policy.npz): ~100 % of episodes hit the ball, exercising the
+    racket-ball contact solve and deep-penetration path that random actions rarely reach."""
+    from pathlib import Path
+
+    n = 2048
+    w = np.load(Path(__file__).parent / "golden" / "ppo_swing_policy.npz")
+    b, o = _make("SwingRacket-v0", n, "f64", 3, oracle_lib)
+    rng = np.random.default_rng(9)
+    obs0 = o.reset()
+    np.testing.assert_array_equal(b.reset().cpu().numpy(), obs0)
+    std = np.exp(w["log_std"])
+
+    def policy(t, obs):
+        h = obs
+        for l in (0, 2, 4):
+            h = np.tanh(h @ w[f"mlp_extractor__policy_net__{l}__weight"].T + w[f"mlp_extractor__policy_net__{l}__bias"])
+        mean = h @ w["action_net__weight"].T + w["action_net__bias"]
+        return np.clip(mean + std * rng.standard_normal((n, 6)), -1, 1)
+
+    rep, valid = run_parity(b, o, 52, policy, band=0.0, check_state_every=13, obs0=obs0)
+    print(rep)
+    assert rep.event_mismatch_hard == 0 and rep.event_mismatch_near == 0
+    assert rep.max_state_err < TOL_F64_STATE and rep.max_obs_err < TOL_F64_OUT and rep.max_reward_err < TOL_F64_OUT
+    st = b.read_stats()
+    np.testing.assert_array_equal(st, o.read_stats())
+    assert st[2] > 0.8 * st[0]  # racket hits in most episodes
+
+
+@pytest.mark.parametrize("env,steps", [("SwingRacket-v0", 52), ("Tennisbot-v0", 700)])
+def test_f32_parity_with_band(oracle_lib, env, steps):
+    n = 4096
+    b, o = _make(env, n, "f32", 21, oracle_lib)
+    rng = np.random.default_rng(6)
+    init = reference_reset_params(o.kind, n, rng)
+    b.reset(init=init)
+    o.reset(init=init)
+    rep, valid = run_parity(b, o, steps, lambda t, _obs: rng.uniform(-1, 1, (n, o.act_dim)), band=BAND_F32)
+    print(rep)
+    assert rep.event_mismatch_hard == 0
+    assert rep.dropped < 0.02 * n
+    assert rep.max_obs_err < TOL_F32_OUT and rep.max_reward_err < 10 * TOL_F32_OUT
+
+
+@pytest.mark.parametrize("env", ["SwingRacket-v0", "Tennisbot-v0"])
+def test_fused_rollout_matches_stepwise(oracle_lib, env):
+    """tb_rollout (K fused env steps, in-kernel Philox actions) == oracle rollout with the same streams."""
+    n = 2048
+    b, o = _make(env, n, "f64", 77, oracle_lib)
+    b.reset()
+    o.reset()
+    k = 60 if env == "SwingRacket-v0" else 300
+    gobs, grs, gdc = (x.cpu().numpy() for x in b.rollout(k))
+    r = o.rollout(k)
+    np.testing.assert_array_equal(gdc, r["done_count"])
+    assert np.abs(gobs.astype(np.float64) - r["obs"]).max() < TOL_F64_OUT
+    assert np.abs(grs - r["reward_sum"]).max() < 1e-3
+    np.testing.assert_array_equal(b.read_stats(), o.read_stats())
+    assert np.abs(b.get_state().cpu().numpy() - o.get_state()).max() < TOL_F64_STATE
