@@ -1,0 +1,319 @@
+#!/usr/bin/env python3
+"""bench.py - env-steps/s of the SwingRacket-v0 step path on B200 (BASELINE.json metric), one JSON line.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...   # CPU arm (restated oracle; PyBullet is not in the image)
+    torchrun --nproc-per-node N bench.py --gpus N ...         # one rank per GPU, weak scaling
+
+A "step" is one pass of the hot path over the batch: one agent-visible env step for every env of the batch
+(SwingRacket's 26th step, which fast-forwards up to 776 physics substeps, counts once).  Workload = config 5's
+per-GPU slice: 1 048 576 SwingRacket-v0 envs per GPU, uniform random actions, initial states from the env's own
+reset ranges.  Episode phases are staggered per 128-env group (group g starts g mod 26 steps late) so every
+launch carries the same mix of 25/26 control steps and 1/26 fast-forward steps and any K measures whole-episode
+throughput.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "env-steps/sec SwingRacket-v0"
+UNIT = "env-steps/s"
+ALGO_BYTES = {  # action + obs + reward + done + state read + state written, per env step
+    ("SwingRacket-v0", "f32"): 24 + 24 + 4 + 1 + 128 + 128,
+    ("SwingRacket-v0", "f64"): 24 + 24 + 4 + 1 + 256 + 256,
+    ("Tennisbot-v0", "f32"): 8 + 48 + 4 + 1 + 128 + 128,
+    ("Tennisbot-v0", "f64"): 8 + 48 + 4 + 1 + 256 + 256,
+}
+EPISODE_STEPS = 26
+GROUP = 128
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=104)
+    ap.add_argument("--warmup", type=int, default=26)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--env", default="SwingRacket-v0", choices=["SwingRacket-v0", "Tennisbot-v0"])
+    ap.add_argument("--envs-per-gpu", type=int, default=1 << 20)
+    ap.add_argument("--precision", default="f64", choices=["f32", "f64"])
+    ap.add_argument("--e2e-steps", type=int, default=26)
+    ap.add_argument("--cpu-sample-envs", type=int, default=16384)
+    ap.add_argument("--no-stagger", action="store_true")
+    ap.add_argument("--skip-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------------------------------------- helpers
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons while the timed region runs (B200_PROFILING.md's clocks line)."""
+
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self._stop_evt = index, [], threading.Event()
+
+    def run(self):
+        while not self._stop_evt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                parts = [p.strip() for p in out.strip().split(",")]
+                if len(parts) >= 6:
+                    self.rows.append(parts)
+            except Exception:
+                pass
+            self._stop_evt.wait(0.2)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=6)
+        sm = sorted(int(r[0]) for r in self.rows if r[0].isdigit())
+        reasons = set()
+        for r in self.rows:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None,
+                "sm_max_mhz": int(self.rows[0][1]) if self.rows and self.rows[0][1].isdigit() else None,
+                "reasons": sorted(reasons), "samples": len(self.rows)}
+
+
+def measured_peak():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "measured"
+        except Exception:
+            pass
+    return 6650.0, "fallback"
+
+
+def cpu_oracle_rate(env, n_envs, steps, threads):
+    """Env-steps/s of the restated CPU oracle (PyBullet is not installable here) on `threads` host threads."""
+    import numpy as np
+
+    from oracle import binding as ob
+
+    ob.build()
+    o = ob.OracleEnv(env, n_envs, seed=0, threads=threads)
+    o.reset()
+    rng = np.random.default_rng(0)
+    acts = rng.uniform(-1, 1, (steps, n_envs, o.act_dim)).astype(np.float32)
+    t0 = time.perf_counter()
+    for t in range(steps):
+        o.step(acts[t])
+    dt = time.perf_counter() - t0
+    phys = o.physics_steps()
+    o.close()
+    return n_envs * steps / dt, dt, phys
+
+
+# ---------------------------------------------------------------------------------------------- reference arm
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    n = args.cpu_sample_envs
+    for _ in range(max(args.warmup, 0)):
+        cpu_oracle_rate(args.env, n, 1, cores)
+    # each "step" = one full 26-step episode of a bounded sample (so the fast-forward step is weighted as in the GPU arm)
+    t0 = time.perf_counter()
+    total = 0
+    phys = 0
+    for _ in range(args.steps):
+        rate, dt, ph = cpu_oracle_rate(args.env, n, EPISODE_STEPS, cores)
+        total += n * EPISODE_STEPS
+        phys += ph
+    wall = time.perf_counter() - t0
+    value = total / wall
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * wall / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"{args.env} random actions, CPU sample of {n} envs x {EPISODE_STEPS} steps per bench step",
+                   "note": "restated double-precision CPU oracle (oracle/tb_oracle.c) - NOT PyBullet: pybullet, gym and "
+                           "stable-baselines3 are absent from this image and cannot be installed offline"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{n} envs x {EPISODE_STEPS} env steps x {args.steps} repeats, {phys} physics substeps"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------- B200 arm
+def stagger_phases(batch, torch):
+    """Group g (128 envs) starts g mod 26 steps late: step everyone, then restart the groups whose turn it is."""
+    n = batch.num_envs
+    group = torch.arange(n, device=batch.device) // GROUP % EPISODE_STEPS
+    act = torch.zeros((n, batch.act_dim), dtype=torch.float32, device=batch.device)
+    batch.reset()
+    for p in range(1, EPISODE_STEPS):
+        act.uniform_(-1, 1)
+        batch.step(act)
+        batch.reset(mask=(group == p))
+    return EPISODE_STEPS - 1
+
+
+def run_b200(args, rank, world):
+    import numpy as np
+    import torch
+
+    from tennisbot_rl_b200.batch import TennisBatch
+
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    n = args.envs_per_gpu
+    batch = TennisBatch(args.env, n, device=local, seed=0, precision=args.precision, env_id_offset=rank * n)
+    dev = batch.device
+    stats = batch.stats_tensor()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # action buffers: a ring of pre-drawn U(-1,1) batches resident in HBM (synthetic actions = action_space.sample())
+    ring = [torch.empty((n, batch.act_dim), dtype=torch.float32, device=dev).uniform_(-1, 1) for _ in range(4)]
+    pre_launch = 0
+    if args.no_stagger:
+        batch.reset()
+    else:
+        pre_launch = stagger_phases(batch, torch)
+    for w in range(args.warmup):
+        batch.step(ring[w % len(ring)])
+    if dist is not None:
+        dist.all_reduce(stats)  # warm the NCCL communicator
+    batch.read_stats(clear=True)
+    l0 = batch.launch_count()
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for k in range(args.steps):
+        batch.step(ring[k % len(ring)])
+        if dist is not None and (k + 1) % EPISODE_STEPS == 0:
+            dist.all_reduce(stats)  # per-iteration reduction of the episode statistics (10 x int64)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if sampler else None
+    launches = batch.launch_count() - l0
+    st = batch.read_stats() if dist is None else None
+    if dist is not None:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        st_local = torch.from_numpy(batch.read_stats()).to(dev)
+        # steps after the last in-loop all-reduce hold un-reduced increments; a fresh sum is exact either way
+        stats.copy_(st_local)
+        dist.all_reduce(stats)
+        st = stats.cpu().numpy()
+
+    # ---- end to end through the host-buffer entry point (pinned numpy in, pinned numpy out)
+    hb = batch.host_buffers()
+    rng = np.random.default_rng(rank)
+    host_actions = rng.uniform(-1, 1, (n, batch.act_dim)).astype(np.float32)
+    np.copyto(hb["actions"], host_actions)
+    for _ in range(3):
+        batch.step_host(want_terminal=False, want_events=False)
+    barrier()
+    t0 = time.perf_counter()
+    ret_sum = 0.0
+    for _ in range(args.e2e_steps):
+        out = batch.step_host(want_terminal=False, want_events=False)
+        ret_sum += float(out["reward"][0])  # the result is consumed on the host
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    if dist is not None:
+        t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    h2d = n * batch.act_dim * 4
+    d2h = n * (batch.obs_dim * 4 + 4 + 1)
+
+    if rank == 0:
+        total_envs = n * world
+        value = total_envs * args.steps / (ms * 1e-3)
+        peak, peak_src = measured_peak()
+        algo = ALGO_BYTES[(args.env, args.precision)]
+        achieved = n * algo / (ms * 1e-3 / args.steps) / 1e9
+        line = {
+            "metric": METRIC if args.env == "SwingRacket-v0" else "env-steps/sec Tennisbot-v0",
+            "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": args.precision, "data": "synthetic",
+            "config": {"workload": f"{args.env} batched {n} envs per GPU (config 5 slice), uniform random actions, "
+                                   f"reset ranges of the env, auto-reset",
+                       "envs_per_gpu": n, "total_envs": total_envs,
+                       "phase_stagger": "none (lock-step episodes)" if args.no_stagger else f"per {GROUP}-env group, g mod {EPISODE_STEPS}",
+                       "l2_policy": "working set per launch %.0f MB > 126 MB L2 (inputs larger than L2)" % (n * algo / 1e6),
+                       "parallelism": f"env-sharded x{world}, no data-path collective; int64[10] stats all-reduce per {EPISODE_STEPS} steps"},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_env_step": algo,
+                         "kernel": "tb::step_kernel<%s,%s>" % ("double" if args.precision == "f64" else "float", args.env)},
+            "e2e": {"value": total_envs * args.e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "steps": args.e2e_steps, "api": "TennisBatch.step_host -> tb_step_host (pinned host buffers)"},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "episode_stats": {"episodes": int(st[0]), "mean_length": float(st[1]) / max(int(st[0]), 1),
+                              "mean_return": float(st[6]) / 1048576.0 / max(int(st[0]), 1),
+                              "physics_substeps": int(st[8]), "env_steps": int(st[9]),
+                              "physics_substeps_per_s": float(st[8]) / (ms * 1e-3)},
+        }
+        if not args.skip_cpu_baseline:
+            cores = os.cpu_count() or 1
+            cpu_n = args.cpu_sample_envs
+            cpu_oracle_rate(args.env, cpu_n, 2, cores)
+            reps, total, t_cpu = 0, 0, 0.0
+            while t_cpu < 10.0 and reps < 64:
+                _, dt, _ = cpu_oracle_rate(args.env, cpu_n, EPISODE_STEPS, cores)
+                t_cpu += dt
+                total += cpu_n * EPISODE_STEPS
+                reps += 1
+            line["cpu_baseline"] = {"value": total / t_cpu, "unit": UNIT, "cores": cores, "kind": "port",
+                                    "sample": f"{cpu_n} envs x {EPISODE_STEPS} env steps x {reps} repeats on {cores} threads; "
+                                              "restated CPU oracle, not PyBullet (absent from the image)"}
+        print(json.dumps(line), flush=True)
+    batch.close()
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    if world == 1 and args.gpus > 1:
+        # launched without torchrun: re-exec under torch.distributed.run
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", os.environ.get("MASTER_PORT", "29517"), __file__] + sys.argv[1:]
+        sys.exit(subprocess.call(cmd))
+    run_b200(args, rank, world)
+
+
+if __name__ == "__main__":
+    main()

@@ -118,11 +118,15 @@ class OracleEnv:
             self.set_threads(threads)
 
     def close(self):
-        if self.h:
+        if getattr(self, "h", None):
             lib().tbo_destroy(self.h)
             self.h = None
 
-    __del__ = close
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass  # interpreter shutdown
 
     def set_threads(self, n):
         _check(lib().tbo_set_threads(self.h, int(n)))

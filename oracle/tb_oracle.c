@@ -112,6 +112,7 @@ struct tbo_ctx {
   params_t p;
   prism_t racket, goal;
   double racket_inertia[3], racket_com_z;
+  double racket_box[3]; /* outline bounding box in the COM frame: max |y|, min z, max z */
   double *state; /* [n][32] */
   int64_t stats[TBO_NUM_STATS];
   int64_t physics_steps;
@@ -293,6 +294,9 @@ static void build_shapes(tbo_ctx *c) {
   }
   prism_build(&c->racket, (const double(*)[2])verts, TBO_RACKET_OUTLINE_N, s * TBO_RACKET_HALF_X);
   c->racket_com_z = s * TBO_RACKET_COM_Z;
+  c->racket_box[0] = s * fmax(fabs(ymin), fabs(ymax));
+  c->racket_box[1] = s * (zmin - TBO_RACKET_COM_Z);
+  c->racket_box[2] = s * (zmax - TBO_RACKET_COM_Z);
   /* inertia recomputed from the compound's AABB as a solid box (URDF inertia ignored) [R] (A.3) */
   double m = c->p.hull_margin;
   double ex = s * 2 * TBO_RACKET_HALF_X + 2 * m, ey = s * (ymax - ymin) + 2 * m, ez = s * (zmax - zmin) + 2 * m;
@@ -429,15 +433,14 @@ static int physics_step(const tbo_ctx *c, double *s, const double *f_racket, con
         }
       }
     }
-    /* racket vs floor is NOT modelled (SURVEY 7 "hard parts"); flag when the hull's lowest point reaches it */
+    /* racket vs floor is NOT modelled (SURVEY 7 "hard parts"): the racket falls through the court after the control
+     * phase.  TBO_EV_RACKET_LOW flags the steps from which its pose is outside the parity horizon: the lowest corner
+     * of the hull's oriented bounding box (outline box x plate thickness, margin included) is at or below the
+     * floor's contact threshold while the COM is over the court. */
     {
-      double zl[3] = {R[6], R[7], R[8]}; /* world z axis in the racket frame = third row of R */
-      double low = INFINITY;
-      for (int i = 0; i < c->racket.n; ++i) {
-        double h = zl[1] * c->racket.edge[i].a[0] + zl[2] * c->racket.edge[i].a[1];
-        if (h < low) low = h;
-      }
-      low += s[S_RP + 2] - fabs(zl[0]) * c->racket.half_thick - P->hull_margin;
+      double low = s[S_RP + 2] - fabs(R[6]) * c->racket.half_thick - fabs(R[7]) * c->racket_box[0] +
+                   fmin(R[8] * c->racket_box[1], R[8] * c->racket_box[2]) - P->hull_margin;
+      probe(pb, low - (TBO_FLOOR_HZ + T));
       if (low <= TBO_FLOOR_HZ + T && fabs(s[S_RP]) <= TBO_FLOOR_HX + 1 && fabs(s[S_RP + 1]) <= TBO_FLOOR_HY + 1)
         bits |= TBO_EV_RACKET_LOW;
     }

@@ -4,10 +4,11 @@ The library is the only implementation of the env step in this package: there is
 Loading fails loudly when the shared object is missing, and tb_create fails when no sm_100 device is usable.
 """
 import ctypes as C
+import os
 from pathlib import Path
 
 PKG = Path(__file__).resolve().parent
-LIB_PATH = PKG / "libtennisbot_b200.so"
+LIB_PATH = Path(os.environ.get("TB_LIB_PATH", PKG / "libtennisbot_b200.so"))  # override = kernel-variant experiments only
 
 ENV_SWING, ENV_HIT = 0, 1
 F32, F64 = 0, 1

@@ -23,6 +23,12 @@ namespace tb {
 template <typename T> struct M;
 template <> struct M<float> {
   static __device__ __forceinline__ float sqrt(float x) { return sqrtf(x); }
+  // 1-ulp hardware square root for the speed norms that only feed the damping factor k (1 + |v|)
+  static __device__ __forceinline__ float sqrt_fast(float x) {
+    float y;
+    asm("sqrt.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+  }
   static __device__ __forceinline__ float rsqrt(float x) { return 1.0f / sqrtf(x); }
   static __device__ __forceinline__ float abs(float x) { return fabsf(x); }
   static __device__ __forceinline__ void sincos(float x, float *s, float *c) { sincosf(x, s, c); }
@@ -30,13 +36,15 @@ template <> struct M<float> {
 };
 template <> struct M<double> {
   static __device__ __forceinline__ double sqrt(double x) { return ::sqrt(x); }
+  static __device__ __forceinline__ double sqrt_fast(double x) { return ::sqrt(x); }
   static __device__ __forceinline__ double rsqrt(double x) { return 1.0 / ::sqrt(x); }
   static __device__ __forceinline__ double abs(double x) { return fabs(x); }
   static __device__ __forceinline__ void sincos(double x, double *s, double *c) { ::sincos(x, s, c); }
   static __device__ __forceinline__ double inf() { return __longlong_as_double(0x7ff0000000000000LL); }
 };
 
-template <typename T> __device__ __forceinline__ T clampv(T x, T lo, T hi) { return x < lo ? lo : (x > hi ? hi : x); }
+__device__ __forceinline__ float clampv(float x, float lo, float hi) { return fminf(fmaxf(x, lo), hi); }
+__device__ __forceinline__ double clampv(double x, double lo, double hi) { return fmin(fmax(x, lo), hi); }
 template <typename T> __device__ __forceinline__ T dot3(const T *a, const T *b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
 template <typename T> __device__ __forceinline__ void cross3(const T *a, const T *b, T *o) {
   o[0] = a[1] * b[2] - a[2] * b[1];
@@ -44,6 +52,7 @@ template <typename T> __device__ __forceinline__ void cross3(const T *a, const T
   o[2] = a[0] * b[1] - a[1] * b[0];
 }
 template <typename T> __device__ __forceinline__ T norm3(const T *a) { return M<T>::sqrt(dot3(a, a)); }
+template <typename T> __device__ __forceinline__ T norm3_fast(const T *a) { return M<T>::sqrt_fast(dot3(a, a)); }
 
 // ------------------------------------------------------------------------------------------------ scene
 constexpr int kRacketEdges = TB_RACKET_OUTLINE_N;
@@ -67,6 +76,8 @@ template <typename T> struct Scene {
   T com_z;
   T swing_q[4], swing_off[3]; // spawn quaternion for rpy (0,0.5,0) and R*(0,0,com_z), built on the host in double
   T floor_h[3], net_h[3], goal_r, goal_hz;
+  T racket_box[3];  // outline bounding box in the COM frame: max |y|, min z, max z (grown by 1e-6: reject only)
+  T racket_obb[3];  // the same box, exact: TB_EV_RACKET_LOW
   Prism<T, kRacketEdges> racket;
   Prism<T, kGoalEdges> goal;
 };
@@ -223,6 +234,20 @@ template <typename T> struct Contact {
 template <typename T> struct Row {
   T u[3], rbxu[3], raxu[3], ia[3], jinv, rhs, lam;
 };
+// The rare-path functions below are out of line and exchange data through these records ONLY: no address of a
+// register-resident variable of the substep loop (state, control block) may escape into a call, or the compiler
+// would have to keep that variable in local memory for the whole loop.
+template <typename T> struct ContactSet {
+  Contact<T> c[kMaxContacts];
+};
+template <typename T> struct NarrowIn {
+  T rp[3], rq[4], bp[3], goal[2];
+};
+template <typename T> struct SolveIO {
+  T rq[4], bv[3], bw[3], rv[3], rw[3];  // in: pose + velocities after force integration
+  T dvb[3], dwb[3], dva[3], dwa[3];     // out: velocity changes
+};
+constexpr int kNeedRacket = 1, kNeedFloor = 2, kNeedNet = 4, kNeedGoal = 8;
 
 // Projected Gauss-Seidel over the ball's contacts: per contact one normal row and a friction pair with an
 // implicit cone clamp, early exit on the squared-residual threshold (A.6).  Rare path (about one physics step
@@ -230,16 +255,24 @@ template <typename T> struct Row {
 // by the float32 kernel: the residual early exit makes the impulse sensitive to the sweep count, and a float
 // solve that stops one sweep apart from the double oracle moves the ball's exit velocity by ~1e-2 m/s.
 template <typename T>
-__device__ __noinline__ void solve_contacts(const Scene<T> &sc, const Contact<T> *ct, int nc, const T *Rt,
-                                            const T *bvt, const T *bwt, const T *rvt, const T *rwt, T *dvb_o,
-                                            T *dwb_o, T *dva_o, T *dwa_o) {
+__device__ __noinline__ void solve_contacts(const Scene<T> &sc, const ContactSet<T> *cs, int nc, SolveIO<T> *io) {
   typedef double S;
+  const Contact<T> *ct = cs->c;
   const S rb = sc.ball_r, inv_mb = sc.ball_inv_m, inv_ib = sc.ball_inv_i, inv_mr = sc.racket_inv_m, dt = sc.dt;
   S R[9], bv[3], bw[3], rv[3], rw[3];
+  {
+    S q[4] = {(S)io->rq[0], (S)io->rq[1], (S)io->rq[2], (S)io->rq[3]};
+    if (sizeof(T) == sizeof(S)) {
+      quat_to_mat(q, R);
+    } else {  // the float kernel forms R in float everywhere else; keep the same matrix here
+      T qt[4] = {io->rq[0], io->rq[1], io->rq[2], io->rq[3]}, Rt[9];
+      quat_to_mat(qt, Rt);
 #pragma unroll
-  for (int i = 0; i < 9; ++i) R[i] = Rt[i];
+      for (int i = 0; i < 9; ++i) R[i] = Rt[i];
+    }
+  }
 #pragma unroll
-  for (int i = 0; i < 3; ++i) { bv[i] = bvt[i]; bw[i] = bwt[i]; rv[i] = rvt[i]; rw[i] = rwt[i]; }
+  for (int i = 0; i < 3; ++i) { bv[i] = io->bv[i]; bw[i] = io->bw[i]; rv[i] = io->rv[i]; rw[i] = io->rw[i]; }
   S dvb[3] = {0, 0, 0}, dwb[3] = {0, 0, 0}, dva[3] = {0, 0, 0}, dwa[3] = {0, 0, 0};
   Row<S> rows[kMaxContacts][3];
 #pragma unroll 1
@@ -338,138 +371,205 @@ __device__ __noinline__ void solve_contacts(const Scene<T> &sc, const Contact<T>
     if (resid <= (S)sc.solver_residual) break;
   }
 #pragma unroll
-  for (int i = 0; i < 3; ++i) { dvb_o[i] = (T)dvb[i]; dwb_o[i] = (T)dwb[i]; dva_o[i] = (T)dva[i]; dwa_o[i] = (T)dwa[i]; }
+  for (int i = 0; i < 3; ++i) { io->dvb[i] = (T)dvb[i]; io->dwb[i] = (T)dwb[i]; io->dva[i] = (T)dva[i]; io->dwa[i] = (T)dwa[i]; }
 }
 
-// Narrow phase of the three rare pairs, out of line.  Each appends to ct[] and returns the event bit.
-template <typename T>
-__device__ __noinline__ int detect_racket(const Scene<T> &sc, const T *R, const T *rel, Contact<T> *ct, int *nc) {
-  T pl[3], nl[3], ql[3];
-  matT_vec(R, rel, pl);
-  T dc = prism_distance<T, kRacketEdges>(sc.racket, pl[0], pl[1], pl[2], nl, ql);
-  T d = dc - (sc.ball_r + sc.hull_margin);
-  if (!(d <= sc.contact_threshold)) return 0;
-  Contact<T> &k = ct[(*nc)++];
-  k.dyn = 1;
-  mat_vec(R, nl, k.n);
-  T qs[3] = {ql[0] + sc.hull_margin * nl[0], ql[1] + sc.hull_margin * nl[1], ql[2] + sc.hull_margin * nl[2]};
-  mat_vec(R, qs, k.ra);
-  k.d = d; k.rest = sc.rest_racket; k.mu = sc.mu_racket;
-  return TB_EV_RACKET_BALL;
-}
-template <typename T>
-__device__ __noinline__ int detect_box(const Scene<T> &sc, const T *h, const T *p, int bit, Contact<T> *ct, int *nc) {
-  T n[3];
-  T dc = box_distance(h, sc.box_margin, p, n);
-  T d = dc - (sc.ball_r + sc.box_margin);
-  if (!(d <= sc.contact_threshold)) return 0;
-  Contact<T> &k = ct[(*nc)++];
-  k.dyn = 0;
-  k.n[0] = n[0]; k.n[1] = n[1]; k.n[2] = n[2];
-  k.ra[0] = k.ra[1] = k.ra[2] = 0;
-  k.d = d; k.rest = sc.rest_court; k.mu = sc.mu_court;
-  return bit;
-}
-template <typename T>
-__device__ __noinline__ int detect_goal(const Scene<T> &sc, const T *p, Contact<T> *ct, int *nc) {
-  T nl[3], ql[3];
-  T dc = prism_distance<T, kGoalEdges>(sc.goal, p[2], p[0], p[1], nl, ql);
-  T d = dc - (sc.ball_r + sc.hull_margin);
-  if (!(d <= sc.contact_threshold)) return 0;
-  Contact<T> &k = ct[(*nc)++];
-  k.dyn = 0;
-  k.n[0] = nl[1]; k.n[1] = nl[2]; k.n[2] = nl[0];
-  k.ra[0] = k.ra[1] = k.ra[2] = 0;
-  k.d = d; k.rest = sc.rest_goal; k.mu = sc.mu_goal;
-  return TB_EV_GOAL_BALL;
-}
-template <typename T> __device__ __noinline__ int racket_low(const Scene<T> &sc, const T *R, T rpz) {
-  T low = M<T>::inf();
-#pragma unroll 1
-  for (int i = 0; i < kRacketEdges; ++i) {
-    T h = R[7] * sc.racket.e[i].ax + R[8] * sc.racket.e[i].ay;
-    if (h < low) low = h;
+// Narrow phase of every pair whose broad-phase test passed, one out-of-line call.  Appends to cs->c[] in the
+// fixed order racket, floor, net, goal; returns event bits | (number of contacts << 8).
+template <typename T, bool WITH_GOAL>
+__device__ __noinline__ int narrow_phase(const Scene<T> &sc, int need, const NarrowIn<T> *in, ContactSet<T> *cs) {
+  int nc = 0, bits = 0;
+  const T thr = sc.contact_threshold;
+  T R[9];
+  if (need & kNeedRacket) quat_to_mat(in->rq, R);
+  if (need & kNeedRacket) {
+    T rel[3] = {in->bp[0] - in->rp[0], in->bp[1] - in->rp[1], in->bp[2] - in->rp[2]}, pl[3];
+    matT_vec(R, rel, pl);
+    // second-level reject in the racket frame (plate slab and outline bounding box, both grown by the reach):
+    // conservative, so the oracle, which runs the narrow phase whenever the bounding sphere is entered, agrees
+    T reach = sc.ball_r + sc.hull_margin + thr;
+    if (!(M<T>::abs(pl[0]) - sc.racket.half_thick > reach || M<T>::abs(pl[1]) - sc.racket_box[0] > reach ||
+          pl[2] - sc.racket_box[2] > reach || sc.racket_box[1] - pl[2] > reach)) {
+      T nl[3], ql[3];
+      T dc = prism_distance<T, kRacketEdges>(sc.racket, pl[0], pl[1], pl[2], nl, ql);
+      T d = dc - (sc.ball_r + sc.hull_margin);
+      if (d <= thr) {
+        Contact<T> &k = cs->c[nc++];
+        k.dyn = 1;
+        mat_vec(R, nl, k.n);
+        T qs[3] = {ql[0] + sc.hull_margin * nl[0], ql[1] + sc.hull_margin * nl[1], ql[2] + sc.hull_margin * nl[2]};
+        mat_vec(R, qs, k.ra);
+        k.d = d; k.rest = sc.rest_racket; k.mu = sc.mu_racket;
+        bits |= TB_EV_RACKET_BALL;
+      }
+    }
   }
-  low += rpz - M<T>::abs(R[6]) * sc.racket.half_thick - sc.hull_margin;
-  return low <= sc.floor_h[2] + sc.contact_threshold ? TB_EV_RACKET_LOW : 0;
+#pragma unroll 1
+  for (int b = 0; b < 2; ++b) {
+    if (!(need & (b ? kNeedNet : kNeedFloor))) continue;
+    const T *h = b ? sc.net_h : sc.floor_h;
+    T n[3];
+    T dc = box_distance(h, sc.box_margin, in->bp, n);
+    T d = dc - (sc.ball_r + sc.box_margin);
+    if (d <= thr) {
+      Contact<T> &k = cs->c[nc++];
+      k.dyn = 0;
+      k.n[0] = n[0]; k.n[1] = n[1]; k.n[2] = n[2];
+      k.ra[0] = k.ra[1] = k.ra[2] = 0;
+      k.d = d; k.rest = sc.rest_court; k.mu = sc.mu_court;
+      bits |= TB_EV_COURT_BALL | (b ? TB_EV_NET_BALL : 0);
+    }
+  }
+  if (WITH_GOAL && (need & kNeedGoal)) {
+    T nl[3], ql[3];
+    T dc = prism_distance<T, kGoalEdges>(sc.goal, in->bp[2], in->bp[0] - in->goal[0], in->bp[1] - in->goal[1], nl, ql);
+    T d = dc - (sc.ball_r + sc.hull_margin);
+    if (d <= thr) {
+      Contact<T> &k = cs->c[nc++];
+      k.dyn = 0;
+      k.n[0] = nl[1]; k.n[1] = nl[2]; k.n[2] = nl[0];
+      k.ra[0] = k.ra[1] = k.ra[2] = 0;
+      k.d = d; k.rest = sc.rest_goal; k.mu = sc.mu_goal;
+      bits |= TB_EV_GOAL_BALL;
+    }
+  }
+  return bits | (nc << 8);
 }
+
+// sin and cos of the half rotation angle of one substep.  |x| = |omega| dt / 2 <= 0.37 because every velocity
+// coordinate is clamped to +-100, so a short Taylor series is exact to the last bit or two and replaces the
+// general-range library routine (the oracle calls libm; the difference is below 1 ulp).
+__device__ __forceinline__ void sincos_small(float x, float *s, float *c) {
+  float x2 = x * x;
+  *s = x * (1.0f + x2 * (-1.0f / 6 + x2 * (1.0f / 120 + x2 * (-1.0f / 5040 + x2 * (1.0f / 362880)))));
+  *c = 1.0f + x2 * (-0.5f + x2 * (1.0f / 24 + x2 * (-1.0f / 720 + x2 * (1.0f / 40320 + x2 * (-1.0f / 3628800)))));
+}
+__device__ __forceinline__ void sincos_small(double x, double *s, double *c) {
+  double x2 = x * x;
+  *s = x * (1.0 + x2 * (-1.0 / 6 + x2 * (1.0 / 120 + x2 * (-1.0 / 5040 + x2 * (1.0 / 362880 + x2 * (-1.0 / 39916800 +
+       x2 * (1.0 / 6227020800.0 + x2 * (-1.0 / 1307674368000.0 + x2 * (1.0 / 355687428096000.0)))))))));
+  *c = 1.0 + x2 * (-0.5 + x2 * (1.0 / 24 + x2 * (-1.0 / 720 + x2 * (1.0 / 40320 + x2 * (-1.0 / 3628800 +
+       x2 * (1.0 / 479001600.0 + x2 * (-1.0 / 87178291200.0 + x2 * (1.0 / 20922789888000.0 +
+       x2 * (-1.0 / 6402373705728000.0)))))))));
+}
+__device__ __forceinline__ float fast_rsqrt(float x) {
+  float y = rsqrtf(x);
+  return y * (1.5f - 0.5f * x * y * y);  // one Newton step on the 2-ulp hardware estimate
+}
+__device__ __forceinline__ double fast_rsqrt(double x) { return ::rsqrt(x); }
 
 // One stepSimulation(): detect at the start-of-step poses, integrate velocities with Bullet's multibody
 // damping, solve contacts, integrate poses.  Returns the TB_EV_* contact bits getContactPoints would report.
+// known_bits: event bits already latched for this env step (lets the sticky RACKET_LOW diagnostic skip its loop).
 template <typename T, bool WITH_GOAL>
 __device__ __forceinline__ int physics_step(const Scene<T> &sc, St<T> &s, const T *f_racket, const T *t_racket,
-                                            const T *f_ball) {
+                                            const T *f_ball, int known_bits) {
   const T dt = sc.dt, thr = sc.contact_threshold, rb = sc.ball_r;
-  T R[9];
-  quat_to_mat(s.rq, R);
-  Contact<T> ct[kMaxContacts];
+  ContactSet<T> cs;  // lives in local memory; touched on the rare path only
   int nc = 0, bits = 0;
 
-  // ---- (1) detection: cheap conservative rejects in line, narrow phase out of line
+  // ---- (1) detection: cheap conservative broad-phase rejects in line, every narrow phase in one rare call
   {
+    int need = 0;
     T rel[3] = {s.bp[0] - s.rp[0], s.bp[1] - s.rp[1], s.bp[2] - s.rp[2]};
     T reach = sc.racket.bound_radius + rb + sc.hull_margin + thr;
-    if (dot3(rel, rel) <= reach * reach) bits |= detect_racket(sc, R, rel, ct, &nc);
+    if (dot3(rel, rel) <= reach * reach) need |= kNeedRacket;
     const T reach_b = rb + sc.box_margin + thr;
-    if (!(M<T>::abs(s.bp[0]) - sc.floor_h[0] > reach_b || M<T>::abs(s.bp[1]) - sc.floor_h[1] > reach_b ||
-          M<T>::abs(s.bp[2]) - sc.floor_h[2] > reach_b))
-      bits |= detect_box(sc, sc.floor_h, s.bp, TB_EV_COURT_BALL, ct, &nc);
-    if (!(M<T>::abs(s.bp[0]) - sc.net_h[0] > reach_b || M<T>::abs(s.bp[1]) - sc.net_h[1] > reach_b ||
-          M<T>::abs(s.bp[2]) - sc.net_h[2] > reach_b))
-      bits |= detect_box(sc, sc.net_h, s.bp, TB_EV_COURT_BALL | TB_EV_NET_BALL, ct, &nc);
+    if (!(M<T>::abs(s.bp[2]) - sc.floor_h[2] > reach_b || M<T>::abs(s.bp[0]) - sc.floor_h[0] > reach_b ||
+          M<T>::abs(s.bp[1]) - sc.floor_h[1] > reach_b))
+      need |= kNeedFloor;
+    if (!(M<T>::abs(s.bp[0]) - sc.net_h[0] > reach_b || M<T>::abs(s.bp[2]) - sc.net_h[2] > reach_b ||
+          M<T>::abs(s.bp[1]) - sc.net_h[1] > reach_b))
+      need |= kNeedNet;
     if (WITH_GOAL) {
-      T p[3] = {s.bp[0] - s.goal[0], s.bp[1] - s.goal[1], s.bp[2]};
-      T reach_g = rb + sc.hull_margin + thr, rxy = sc.goal_r + reach_g;
-      if (M<T>::abs(p[2]) - sc.goal_hz <= reach_g && p[0] * p[0] + p[1] * p[1] <= rxy * rxy)
-        bits |= detect_goal(sc, p, ct, &nc);
+      T reach_g = rb + sc.hull_margin + thr;
+      if (M<T>::abs(s.bp[2]) - sc.goal_hz <= reach_g) {
+        T gx = s.bp[0] - s.goal[0], gy = s.bp[1] - s.goal[1], rxy = sc.goal_r + reach_g;
+        if (gx * gx + gy * gy <= rxy * rxy) need |= kNeedGoal;
+      }
     }
-    if (s.rp[2] - sc.racket.bound_radius - sc.hull_margin <= sc.floor_h[2] + thr &&
-        M<T>::abs(s.rp[0]) <= sc.floor_h[0] + 1 && M<T>::abs(s.rp[1]) <= sc.floor_h[1] + 1)
-      bits |= racket_low(sc, R, s.rp[2]);
+    // Racket vs floor is not modelled (the racket falls through the court once the episode's control phase is
+    // over); TB_EV_RACKET_LOW marks the steps from which its pose is outside the parity horizon: the lowest
+    // corner of the hull's oriented bounding box (outline box x plate thickness, margin included) is at or below
+    // the floor's contact threshold while the COM is over the court.
+    if (!(known_bits & TB_EV_RACKET_LOW) && s.rp[2] - sc.racket.bound_radius - sc.hull_margin <= sc.floor_h[2] + thr) {
+      const T *q = s.rq;
+      T r6 = 2 * (q[0] * q[2] - q[1] * q[3]), r7 = 2 * (q[1] * q[2] + q[0] * q[3]), r8 = 1 - 2 * (q[0] * q[0] + q[1] * q[1]);
+      T zlo = r8 * sc.racket_obb[1], zhi = r8 * sc.racket_obb[2];
+      T low = s.rp[2] - M<T>::abs(r6) * sc.racket.half_thick - M<T>::abs(r7) * sc.racket_obb[0] + (zlo < zhi ? zlo : zhi) -
+              sc.hull_margin;
+      if (low <= sc.floor_h[2] + thr && M<T>::abs(s.rp[0]) <= sc.floor_h[0] + 1 && M<T>::abs(s.rp[1]) <= sc.floor_h[1] + 1)
+        bits |= TB_EV_RACKET_LOW;
+    }
+    if (need) {
+      NarrowIn<T> in;
+#pragma unroll
+      for (int i = 0; i < 3; ++i) { in.rp[i] = s.rp[i]; in.bp[i] = s.bp[i]; }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) in.rq[i] = s.rq[i];
+      in.goal[0] = s.goal[0]; in.goal[1] = s.goal[1];
+      int r = narrow_phase<T, WITH_GOAL>(sc, need, &in, &cs);
+      bits |= r & 0xff;
+      nc = r >> 8;
+    }
   }
 
   // ---- (2) velocities: v += dt (F/m + g - v (k + k|v|)); omega likewise in the body frame with the gyro term
   const T vmax = sc.max_coord_vel;
   {
-    T kv = sc.lin_damping * (1 + norm3(s.bv)), kw = sc.ang_damping * (1 + norm3(s.bw));
+    T kv = sc.lin_damping * (1 + norm3_fast(s.bv));
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
       T g = i == 2 ? sc.gravity_z : (T)0;
       s.bv[i] = clampv(s.bv[i] + dt * (f_ball[i] * sc.ball_inv_m + g - s.bv[i] * kv), -vmax, vmax);
-      s.bw[i] = clampv(s.bw[i] + dt * (-s.bw[i] * kw), -vmax, vmax);
+    }
+    if (s.bw[0] != 0 || s.bw[1] != 0 || s.bw[2] != 0) {  // the ball spins only after a frictional contact
+      T kw = sc.ang_damping * (1 + norm3_fast(s.bw));
+#pragma unroll
+      for (int i = 0; i < 3; ++i) s.bw[i] = clampv(s.bw[i] + dt * (-s.bw[i] * kw), -vmax, vmax);
     }
   }
+  T R[9];
+  const bool rotating = s.rw[0] != 0 || s.rw[1] != 0 || s.rw[2] != 0 || t_racket[0] != 0 || t_racket[1] != 0 ||
+                        t_racket[2] != 0;
   {
-    T kv = sc.lin_damping * (1 + norm3(s.rv));
+    T kv = sc.lin_damping * (1 + norm3_fast(s.rv));
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
       T g = i == 2 ? sc.gravity_z : (T)0;
       s.rv[i] = clampv(s.rv[i] + dt * (f_racket[i] * sc.racket_inv_m + g - s.rv[i] * kv), -vmax, vmax);
     }
-    T wl[3], tl[3], iw[3], gy[3], al[3], aw[3];
-    matT_vec(R, s.rw, wl);
-    matT_vec(R, t_racket, tl);
+    if (rotating) quat_to_mat(s.rq, R);
+    if (rotating) {  // the hit env's racket never rotates: no torque is ever applied to it
+      T wl[3], tl[3], iw[3], gy[3], al[3], aw[3];
+      matT_vec(R, s.rw, wl);
+      matT_vec(R, t_racket, tl);
 #pragma unroll
-    for (int i = 0; i < 3; ++i) iw[i] = sc.racket_i[i] * wl[i];
-    cross3(wl, iw, gy);
-    T kw = sc.ang_damping * (1 + norm3(wl));
+      for (int i = 0; i < 3; ++i) iw[i] = sc.racket_i[i] * wl[i];
+      cross3(wl, iw, gy);
+      T kw = sc.ang_damping * (1 + norm3_fast(wl));
 #pragma unroll
-    for (int i = 0; i < 3; ++i) al[i] = (tl[i] - sc.gyro * gy[i]) * sc.racket_inv_i[i] - wl[i] * kw;
-    mat_vec(R, al, aw);
+      for (int i = 0; i < 3; ++i) al[i] = (tl[i] - sc.gyro * gy[i]) * sc.racket_inv_i[i] - wl[i] * kw;
+      mat_vec(R, al, aw);
 #pragma unroll
-    for (int i = 0; i < 3; ++i) s.rw[i] = clampv(s.rw[i] + dt * aw[i], -vmax, vmax);
+      for (int i = 0; i < 3; ++i) s.rw[i] = clampv(s.rw[i] + dt * aw[i], -vmax, vmax);
+    }
   }
 
   // ---- (3) contact solve
   if (nc > 0) {
-    T dvb[3], dwb[3], dva[3], dwa[3];
-    solve_contacts(sc, ct, nc, R, s.bv, s.bw, s.rv, s.rw, dvb, dwb, dva, dwa);
+    SolveIO<T> io;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { io.bv[i] = s.bv[i]; io.bw[i] = s.bw[i]; io.rv[i] = s.rv[i]; io.rw[i] = s.rw[i]; }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) io.rq[i] = s.rq[i];
+    solve_contacts(sc, &cs, nc, &io);
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
-      s.bv[i] = clampv(s.bv[i] + dvb[i], -vmax, vmax);
-      s.bw[i] = clampv(s.bw[i] + dwb[i], -vmax, vmax);
-      s.rv[i] = clampv(s.rv[i] + dva[i], -vmax, vmax);
-      s.rw[i] = clampv(s.rw[i] + dwa[i], -vmax, vmax);
+      s.bv[i] = clampv(s.bv[i] + io.dvb[i], -vmax, vmax);
+      s.bw[i] = clampv(s.bw[i] + io.dwb[i], -vmax, vmax);
+      s.rv[i] = clampv(s.rv[i] + io.dva[i], -vmax, vmax);
+      s.rw[i] = clampv(s.rw[i] + io.dwa[i], -vmax, vmax);
     }
   }
 
@@ -479,16 +579,16 @@ __device__ __forceinline__ int physics_step(const Scene<T> &sc, St<T> &s, const 
     s.bp[i] += dt * s.bv[i];
     s.rp[i] += dt * s.rv[i];
   }
-  {
-    T ang = norm3(s.rw), k, cw;
-    if (ang < (T)0.001) {
-      k = (T)0.5 * dt - dt * dt * dt * (T)0.020833333333 * ang * ang;
-      T sn;
-      M<T>::sincos((T)0.5 * ang * dt, &sn, &cw);
+  if (s.rw[0] != 0 || s.rw[1] != 0 || s.rw[2] != 0) {
+    T a2 = dot3(s.rw, s.rw), k, sn, cw;
+    if (a2 < (T)1e-6) {  // |omega| < 0.001: Taylor form of sin(x)/x, as Bullet does
+      T ang = M<T>::sqrt(a2);
+      k = (T)0.5 * dt - dt * dt * dt * (T)0.020833333333 * a2;
+      sincos_small((T)0.5 * ang * dt, &sn, &cw);
     } else {
-      T sn;
-      M<T>::sincos((T)0.5 * ang * dt, &sn, &cw);
-      k = sn / ang;
+      T inv_ang = fast_rsqrt(a2), ang = a2 * inv_ang;
+      sincos_small((T)0.5 * ang * dt, &sn, &cw);
+      k = sn * inv_ang;
     }
     T ax = s.rw[0] * k, ay = s.rw[1] * k, az = s.rw[2] * k;
     const T *q = s.rq;
@@ -496,7 +596,7 @@ __device__ __forceinline__ int physics_step(const Scene<T> &sc, St<T> &s, const 
     T y = cw * q[1] - ax * q[2] + ay * q[3] + az * q[0];
     T z = cw * q[2] + ax * q[1] - ay * q[0] + az * q[3];
     T w = cw * q[3] - ax * q[0] - ay * q[1] - az * q[2];
-    T inv = M<T>::rsqrt(x * x + y * y + z * z + w * w);
+    T inv = fast_rsqrt(x * x + y * y + z * z + w * w);
     s.rq[0] = x * inv; s.rq[1] = y * inv; s.rq[2] = z * inv; s.rq[3] = w * inv;
   }
   return bits;
@@ -565,11 +665,6 @@ template <typename T, int KIND> __device__ __forceinline__ void pack_obs(const S
   }
 }
 
-struct StepOut {
-  float reward;
-  int done, events, hit_steps, nphys;
-};
-
 template <typename T> __device__ __forceinline__ T moved_dist_to_goal(const St<T> &s) {
   T dx = s.bp[0] - s.goal[0], dy = s.bp[1] - s.goal[1];
   return (s.d0 - M<T>::sqrt(dx * dx + dy * dy)) / s.d0 * (T)20;
@@ -578,60 +673,65 @@ template <typename T> __device__ __forceinline__ T dist_to_reward(T d) {
   return d < (T)0.5 ? (T)20 : d < 1 ? (T)15 : d < 2 ? (T)10 : d < 3 ? (T)5 : d < 4 ? (T)1 : (T)0;
 }
 
-// One agent-visible step().  The physics call appears once; SwingRacket's fast-forward re-enters it.
+// Per-lane progress of one agent-visible step().  SwingRacket's 26th step re-enters the substep many times:
+//   phase 0: the substep driven by the action (swingracket_env.py:76-83)
+//   phase 1: first fast-forward substep, no external force (the step above cleared them) (:105-107)
+//   phase 2: later fast-forward substeps, driven by the "hack" force queued after the previous one (:135-141)
+struct StepCtl {
+  int phase, events, hit;
+  float reward;
+  bool done;
+};
+
+// One physics substep of the env step in flight plus the env logic that follows it.  Returns true when the
+// env step is complete (reward / done / events are final).
 template <typename T, int KIND>
-__device__ __forceinline__ void env_step(const Scene<T> &sc, St<T> &s, const float *a, StepOut &o) {
+__device__ __forceinline__ bool env_substep(const Scene<T> &sc, St<T> &s, const float *a, StepCtl &c) {
   T zero[3] = {0, 0, 0};
-  o.hit_steps = 0;
   if (KIND == TB_ENV_SWING) {
-    T F[3] = {(T)a[0] * 400, (T)a[1] * 400, (T)a[2] * 400 + (T)(4 * 9.81)};
-    T Tq[3] = {(T)a[3] * 5, (T)a[4] * 5, (T)a[5] * 5};
-    int k = s.step, ev = 0, nphys = 0;
-    bool done = s.flags & 1, first = true;
-    T reward = 0;
-    while (true) {
-      int bits = physics_step<T, true>(sc, s, F, Tq, zero);
-      ++nphys; ++k;
-      ev |= bits;
-      if (first) {
-        if (k < 25 && (bits & TB_EV_RACKET_BALL)) { reward += 2; o.hit_steps = 1; }
-        first = false;
-        F[0] = F[1] = F[2] = 0;
-        Tq[0] = Tq[1] = Tq[2] = 0;
-        if (!(k > 25)) break;
-      } else {
-        if (bits & TB_EV_COURT_BALL) { done = true; reward += moved_dist_to_goal(s); }
-        if (bits & TB_EV_GOAL_BALL) { reward += moved_dist_to_goal(s); reward += 50; done = true; }
-        if (k > 800) { done = true; ev |= TB_EV_TIMEOUT; }
-        F[0] = -50 * (s.rp[0] - s.aux[0]);
-        F[1] = -2 * (s.rp[1] - s.aux[1]);
-        F[2] = -2 * (s.rp[2] - s.aux[2] - 4);
-      }
-      if (done) break;
+    T F[3], Tq[3] = {0, 0, 0};
+    if (c.phase == 0) {
+      F[0] = (T)a[0] * 400; F[1] = (T)a[1] * 400; F[2] = (T)a[2] * 400 + (T)(4 * 9.81);
+      Tq[0] = (T)a[3] * 5; Tq[1] = (T)a[4] * 5; Tq[2] = (T)a[5] * 5;
+    } else if (c.phase == 1) {
+      F[0] = F[1] = F[2] = 0;
+    } else {  // the force the reference queued from the post-step pose of the previous substep = this one's pre-step pose
+      F[0] = -50 * (s.rp[0] - s.aux[0]);
+      F[1] = -2 * (s.rp[1] - s.aux[1]);
+      F[2] = -2 * (s.rp[2] - s.aux[2] - 4);
     }
-    s.step = k;
-    s.flags = done ? 1 : 0;
-    o.reward = (float)reward; o.done = done; o.events = ev; o.nphys = nphys;
+    int bits = physics_step<T, true>(sc, s, F, Tq, zero, c.events);
+    int k = ++s.step;
+    c.events |= bits;
+    if (c.phase == 0) {
+      if (k < 25 && (bits & TB_EV_RACKET_BALL)) { c.reward += 2.0f; c.hit = 1; }
+      c.phase = 1;
+      return !(k > 25) || c.done;
+    }
+    c.phase = 2;
+    T reward = 0;
+    if (bits & TB_EV_COURT_BALL) { c.done = true; reward += moved_dist_to_goal(s); }
+    if (bits & TB_EV_GOAL_BALL) { reward += moved_dist_to_goal(s); reward += 50; c.done = true; }
+    if (k > 800) { c.done = true; c.events |= TB_EV_TIMEOUT; }
+    if (c.done) c.reward = (float)reward;
+    return c.done;
   } else {
     T F[3] = {(T)a[0] * 10, (T)a[1] * 10, (T)(4 * 9.81)};
-    int k = s.step;
     T Fb[3] = {0, 0, 0};
-    if (k < 5) { Fb[0] = s.aux[0]; Fb[1] = s.aux[1]; Fb[2] = s.aux[2]; }
-    int bits = physics_step<T, false>(sc, s, F, zero, Fb);
-    ++k;
-    s.step = k;
-    bool done = s.flags & 1;
-    o.events = bits; o.reward = 0; o.done = 0; o.nphys = 1;
-    if (k < 5) return;
+    if (s.step < 5) { Fb[0] = s.aux[0]; Fb[1] = s.aux[1]; Fb[2] = s.aux[2]; }
+    int bits = physics_step<T, false>(sc, s, F, zero, Fb, 0);
+    int k = ++s.step;
+    c.events = bits;
+    if (k < 5) { c.done = false; return true; }  // returns False regardless of self.done (tennisbot_env.py:138-139)
     T dz = s.bp[2] - s.rp[2], dy = s.bp[1] - s.rp[1];
     T delta = M<T>::sqrt(dz * dz + dy * dy);
     T reward = 0;
-    if (bits & TB_EV_RACKET_BALL) { reward += 25; reward += dist_to_reward(delta); o.hit_steps = 1; }
+    if (bits & TB_EV_RACKET_BALL) { reward += 25; reward += dist_to_reward(delta); c.hit = 1; }
     T xbr = s.bp[0] - s.rp[0];
-    if (!(xbr < (T)0.5)) { done = true; reward += dist_to_reward(delta); o.events |= TB_EV_BALL_PASSED; }
-    if (k > 1000) { done = true; o.events |= TB_EV_TIMEOUT; }
-    s.flags = done ? 1 : 0;
-    o.reward = (float)reward; o.done = done;
+    if (!(xbr < (T)0.5)) { c.done = true; reward += dist_to_reward(delta); c.events |= TB_EV_BALL_PASSED; }
+    if (k > 1000) { c.done = true; c.events |= TB_EV_TIMEOUT; }
+    c.reward = (float)reward;
+    return true;
   }
 }
 

@@ -20,7 +20,24 @@
 namespace tb {
 
 constexpr int kPacks = 8;
-constexpr int kBlock = 128;
+constexpr int kBlock = 128;     // threads per CTA of the step kernel
+#ifndef TB_MINB32
+#define TB_MINB32 4
+#endif
+#ifndef TB_MINB64
+#define TB_MINB64 2
+#endif
+// CTAs per SM the register budget is held to: 4 x 128 threads -> 128 regs/thread (f32), 2 -> 255 (f64)
+template <typename T> struct MinBlocks { static constexpr int v = TB_MINB32; };
+template <> struct MinBlocks<double> { static constexpr int v = TB_MINB64; };
+#ifndef TB_REFILL_MIN
+#define TB_REFILL_MIN 8
+#endif
+#ifndef TB_CHUNK
+#define TB_CHUNK 128
+#endif
+constexpr int kRefillMin = TB_REFILL_MIN;   // idle lanes that trigger a refill before the periodic one
+constexpr int kChunk = TB_CHUNK;     // envs a warp claims per grab from the launch-wide work counter
 
 // ------------------------------------------------------------------------------------------------ pack I/O
 template <typename T> struct Pack { T x, y, z, w; };
@@ -71,43 +88,6 @@ template <typename T> __device__ __forceinline__ void store_state(T *base, int64
   st_pack(base, n, 7, i, Pack<T>{s.ret, int_as(T(), s.step), int_as(T(), s.flags), int_as(T(), (int64_t)s.episode)});
 }
 
-// ------------------------------------------------------------------------------------------------ statistics
-struct Acc {
-  int episodes, sum_len, hits, goals, courts, timeouts, nphys, nsteps;
-  long long ret_q20, ret2_q10;
-};
-// warp-level reduction: one redux.sync per 32-bit counter, shuffles only for the two 64-bit sums and only when
-// some lane finished an episode; lane 0 issues one atomic per non-zero counter.
-__device__ __forceinline__ void flush_stats(const Acc &a, unsigned long long *stats) {
-  const unsigned full = 0xffffffffu;
-  int lane = threadIdx.x & 31;
-  int nphys = __reduce_add_sync(full, a.nphys), nsteps = __reduce_add_sync(full, a.nsteps);
-  int hits = __reduce_add_sync(full, a.hits), episodes = __reduce_add_sync(full, a.episodes);
-  if (lane == 0) {
-    atomicAdd(stats + TB_STAT_PHYSICS_STEPS, (unsigned long long)nphys);
-    atomicAdd(stats + TB_STAT_ENV_STEPS, (unsigned long long)nsteps);
-    if (hits) atomicAdd(stats + TB_STAT_RACKET_HITS, (unsigned long long)hits);
-  }
-  if (episodes == 0) return;
-  int sum_len = __reduce_add_sync(full, a.sum_len), goals = __reduce_add_sync(full, a.goals);
-  int courts = __reduce_add_sync(full, a.courts), timeouts = __reduce_add_sync(full, a.timeouts);
-  long long r1 = a.ret_q20, r2 = a.ret2_q10;
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    r1 += __shfl_down_sync(full, r1, o);
-    r2 += __shfl_down_sync(full, r2, o);
-  }
-  if (lane == 0) {
-    atomicAdd(stats + TB_STAT_EPISODES, (unsigned long long)episodes);
-    atomicAdd(stats + TB_STAT_SUM_LENGTH, (unsigned long long)sum_len);
-    if (goals) atomicAdd(stats + TB_STAT_GOALS, (unsigned long long)goals);
-    if (courts) atomicAdd(stats + TB_STAT_COURT, (unsigned long long)courts);
-    if (timeouts) atomicAdd(stats + TB_STAT_TIMEOUTS, (unsigned long long)timeouts);
-    atomicAdd(stats + TB_STAT_SUM_RETURN_Q20, (unsigned long long)r1);
-    atomicAdd(stats + TB_STAT_SUM_RETURN2_Q10, (unsigned long long)r2);
-  }
-}
-
 // ------------------------------------------------------------------------------------------------ kernels
 struct StepIO {
   void *state;
@@ -119,6 +99,7 @@ struct StepIO {
   uint8_t *done, *events;
   int32_t *done_count;
   unsigned long long *stats;
+  unsigned long long *chunk_ctr, *chunk_ctr_next;  // dynamic work distribution: this launch's counter, the next one's
 };
 
 template <int KIND> struct Dims {
@@ -146,94 +127,174 @@ template <int KIND> __device__ __forceinline__ void store_obs(float *obs, int64_
     p[2] = make_float4(o[8], o[9], o[10], o[11]);
   }
 }
-
-// Episode bookkeeping shared by the API-mode and fused-rollout kernels.
-template <typename T, int KIND>
-__device__ __forceinline__ void finish_step(const Scene<T> &sc, const StepIO &io, int64_t i, St<T> &s, const StepOut &o,
-                                            Acc &acc, float *ob, bool write_terminal) {
-  s.ret += (T)o.reward;
-  acc.nphys += o.nphys;
-  acc.nsteps += 1;
-  acc.hits += o.hit_steps;
-  pack_obs<T, KIND>(s, ob);
-  if (o.done) {
-    acc.episodes += 1;
-    acc.sum_len += s.step;
-    acc.goals += (o.events & TB_EV_GOAL_BALL) ? 1 : 0;
-    acc.courts += (o.events & TB_EV_COURT_BALL) ? 1 : 0;
-    acc.timeouts += ((o.events & TB_EV_TIMEOUT) && !(o.events & (TB_EV_GOAL_BALL | TB_EV_COURT_BALL | TB_EV_BALL_PASSED))) ? 1 : 0;
-    double r = (double)s.ret;
-    acc.ret_q20 += __double2ll_rn(r * 1048576.0);
-    acc.ret2_q10 += __double2ll_rn(r * r * 1024.0);
-    if (write_terminal && io.term_obs) store_obs<KIND>(io.term_obs, i, ob);
-    if (io.auto_reset) {
-      uint32_t ep = s.episode + 1;
-      T in[TB_INIT_WORDS];
-      draw_init<T, KIND>(io.seed, (uint64_t)(io.id_offset + i), ep, in);
-      start_episode<T, KIND>(sc, s, in, ep);
-      pack_obs<T, KIND>(s, ob);
-    }
+template <int KIND> __device__ __forceinline__ void random_action(uint64_t seed, uint64_t gid, uint32_t episode, int step, float *a) {
+  uint32_t r[4];
+#pragma unroll
+  for (int b = 0; b * 4 < Dims<KIND>::act; ++b) {
+    philox4x32(seed, gid, episode, stream_word(kStreamAction, (uint32_t)step, b), r);
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      if (b * 4 + q < 8) a[b * 4 + q] = 2.0f * u01<float>(r[q]) - 1.0f;
   }
 }
 
-// API mode: one env step per launch, actions from HBM, obs/reward/done to HBM.
-template <typename T, int KIND>
-__global__ void __launch_bounds__(kBlock) step_kernel(const __grid_constant__ Scene<T> sc, const __grid_constant__ StepIO io) {
-  int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
-  Acc acc = {};
-  if (i < io.n) {
-    T *base = static_cast<T *>(io.state);
-    St<T> s;
-    load_state(base, io.n, i, s);
-    float a[6];
-    load_action<KIND>(io.actions, i, a);
-    StepOut o;
-    env_step<T, KIND>(sc, s, a, o);
-    float ob[12];
-    finish_step<T, KIND>(sc, io, i, s, o, acc, ob, true);
-    store_obs<KIND>(io.obs, i, ob);
-    io.reward[i] = o.reward;
-    io.done[i] = (uint8_t)o.done;
-    if (io.events) io.events[i] = (uint8_t)o.events;
-    store_state(base, io.n, i, s);
-  }
-  flush_stats(acc, io.stats);
-}
+// The env-step kernel.  Persistent warps, each owning a contiguous range of envs; every LANE is a little state
+// machine: idle lanes pick the next env of the warp's range (128-bit coalesced loads when the whole warp refills,
+// which is every iteration while envs are in their one-substep control phase), active lanes advance their env by
+// one physics substep per loop iteration with the state in registers, and a lane whose env step completed
+// writes obs / reward / done, auto-resets if the episode ended, stores the state and goes idle.  A lane stuck in
+// SwingRacket's fast-forward (up to 776 substeps) therefore delays nobody: its neighbours keep taking new envs.
+//   ROLLOUT = false: one env step per env, actions from HBM (gym / VecEnv step()).
+//   ROLLOUT = true : k_steps env steps per env with in-kernel Philox actions; state never leaves registers.
+// Episode statistics are warp-uniform popc()/redux sums kept in shared memory, one atomic per counter per warp.
+template <typename T, int KIND, bool ROLLOUT>
+__global__ void __launch_bounds__(kBlock, MinBlocks<T>::v) step_kernel(const __grid_constant__ Scene<T> sc, const __grid_constant__ StepIO io) {
+  __shared__ unsigned long long sacc[kBlock / 32][TB_NUM_STATS];
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int64_t warp = (int64_t)blockIdx.x * (kBlock / 32) + wib, nwarps = (int64_t)gridDim.x * (kBlock / 32);
+  // work distribution: chunk `warp` is owned statically, further chunks come from an atomic counter, fetched one
+  // grab ahead so its latency hides behind the chunk being processed
+  const int64_t nchunks = (io.n + kChunk - 1) / kChunk;
+  int64_t next = warp * kChunk, hi = next + kChunk;
+  if (next > io.n) next = io.n;
+  if (hi > io.n) hi = io.n;
+  unsigned long long pending = 0;
+  bool exhausted = false;
+  if (lane == 0) pending = atomicAdd(io.chunk_ctr, 1ULL) + (unsigned long long)nwarps;
+  if (blockIdx.x == 0 && threadIdx.x == 0) *io.chunk_ctr_next = 0;
+  if (lane < TB_NUM_STATS) sacc[wib][lane] = 0;
+  __syncwarp();
 
-// Fused mode: K env steps per launch with in-kernel actions; state stays in registers for the whole rollout.
-template <typename T, int KIND>
-__global__ void __launch_bounds__(kBlock) rollout_kernel(const __grid_constant__ Scene<T> sc, const __grid_constant__ StepIO io) {
-  int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
-  Acc acc = {};
-  if (i < io.n) {
-    T *base = static_cast<T *>(io.state);
-    St<T> s;
-    load_state(base, io.n, i, s);
-    float ob[12] = {0};
-    float rsum = 0;
-    int dcount = 0;
+  T *base = static_cast<T *>(io.state);
+  St<T> s;
+  StepCtl c = {0, 0, 0, 0.0f, false};
+  float a[8];
+  int64_t me = 0;
+  int left = 0, dcount = 0;
+  float rsum = 0;
+  bool active = false;
+
 #pragma unroll 1
-    for (int t = 0; t < io.k_steps; ++t) {
-      float a[8];
-      uint32_t r[4];
-#pragma unroll
-      for (int b = 0; b * 4 < Dims<KIND>::act; ++b) {
-        philox4x32(io.seed, (uint64_t)(io.id_offset + i), s.episode, stream_word(kStreamAction, (uint32_t)s.step, b), r);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) a[b * 4 + q] = 2.0f * u01<float>(r[q]) - 1.0f;
+  for (unsigned iter = 0;; ++iter) {
+    // ---- refill idle lanes from the warp's range
+    unsigned idle = __ballot_sync(full, !active);
+    if (idle && next >= hi && !exhausted) {
+      long long ch = (long long)__shfl_sync(full, pending, 0);
+      if (ch < nchunks) {
+        next = ch * kChunk;
+        hi = next + kChunk < io.n ? next + kChunk : io.n;
+        if (lane == 0) pending = atomicAdd(io.chunk_ctr, 1ULL) + (unsigned long long)nwarps;
+      } else {
+        exhausted = true;
       }
-      StepOut o;
-      env_step<T, KIND>(sc, s, a, o);
-      finish_step<T, KIND>(sc, io, i, s, o, acc, ob, false);
-      rsum += o.reward;
-      dcount += o.done;
     }
-    if (io.obs) store_obs<KIND>(io.obs, i, ob);
-    if (io.reward_sum) io.reward_sum[i] = rsum;
-    if (io.done_count) io.done_count[i] = dcount;
-    store_state(base, io.n, i, s);
+    if (idle && next < hi && (idle == full || __popc(idle) >= kRefillMin || (iter & 15u) == 0)) {
+      int rank = __popc(idle & ((1u << lane) - 1u));
+      int64_t avail = hi - next;
+      int take = __popc(idle) < avail ? __popc(idle) : (int)avail;
+      if (!active && rank < take) {
+        me = next + rank;
+        load_state(base, io.n, me, s);
+        if (!ROLLOUT) load_action<KIND>(io.actions, me, a);
+        else random_action<KIND>(io.seed, (uint64_t)(io.id_offset + me), s.episode, s.step, a);
+        c.phase = 0; c.events = 0; c.hit = 0; c.reward = 0.0f; c.done = s.flags & 1;
+        left = ROLLOUT ? io.k_steps : 1;
+        rsum = 0; dcount = 0;
+        active = left > 0;
+      }
+      next += take;
+    }
+    unsigned act_mask = __ballot_sync(full, active);
+    if (!act_mask) break;
+
+    // ---- one physics substep for every active lane
+    bool fin = false;
+    if (active) fin = env_substep<T, KIND>(sc, s, a, c);
+
+    // ---- warp-uniform statistics
+    unsigned fin_mask = __ballot_sync(full, fin);
+    if (lane == 0) sacc[wib][TB_STAT_PHYSICS_STEPS] += __popc(act_mask);
+#ifdef TB_DEBUG_ITERS  // experiment only: count warp iterations x 32 in the env-steps slot to read lane utilisation
+    if (lane == 0) sacc[wib][TB_STAT_ENV_STEPS] += 32;
+#endif
+    if (fin_mask) {
+      bool dn = fin && c.done;
+      unsigned done_mask = __ballot_sync(full, dn), hit_mask = __ballot_sync(full, fin && c.hit);
+      if (fin) s.ret += (T)c.reward;
+      if (done_mask) {
+        unsigned goal_m = __ballot_sync(full, dn && (c.events & TB_EV_GOAL_BALL));
+        unsigned court_m = __ballot_sync(full, dn && (c.events & TB_EV_COURT_BALL));
+        unsigned to_m = __ballot_sync(full, dn && (c.events & TB_EV_TIMEOUT) &&
+                                                !(c.events & (TB_EV_GOAL_BALL | TB_EV_COURT_BALL | TB_EV_BALL_PASSED)));
+        int len = __reduce_add_sync(full, dn ? s.step : 0);
+        double r = dn ? (double)s.ret : 0.0;
+        long long r1 = __double2ll_rn(r * 1048576.0), r2 = __double2ll_rn(r * r * 1024.0);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          r1 += __shfl_down_sync(full, r1, o);
+          r2 += __shfl_down_sync(full, r2, o);
+        }
+        if (lane == 0) {
+          sacc[wib][TB_STAT_EPISODES] += __popc(done_mask);
+          sacc[wib][TB_STAT_SUM_LENGTH] += len;
+          sacc[wib][TB_STAT_GOALS] += __popc(goal_m);
+          sacc[wib][TB_STAT_COURT] += __popc(court_m);
+          sacc[wib][TB_STAT_TIMEOUTS] += __popc(to_m);
+          sacc[wib][TB_STAT_SUM_RETURN_Q20] += (unsigned long long)r1;
+          sacc[wib][TB_STAT_SUM_RETURN2_Q10] += (unsigned long long)r2;
+        }
+      }
+      if (lane == 0) {
+        sacc[wib][TB_STAT_ENV_STEPS] += __popc(fin_mask);
+        sacc[wib][TB_STAT_RACKET_HITS] += __popc(hit_mask);
+      }
+    }
+
+    // ---- lanes whose env step completed: outputs, auto-reset, then next rollout step or state store
+    if (fin) {
+      float ob[12];
+      pack_obs<T, KIND>(s, ob);
+      if (c.done) {
+        if (!ROLLOUT && io.term_obs) store_obs<KIND>(io.term_obs, me, ob);
+        if (io.auto_reset) {
+          uint32_t ep = s.episode + 1;
+          T in[TB_INIT_WORDS];
+          draw_init<T, KIND>(io.seed, (uint64_t)(io.id_offset + me), ep, in);
+          start_episode<T, KIND>(sc, s, in, ep);
+          pack_obs<T, KIND>(s, ob);
+        } else {
+          s.flags |= 1;
+        }
+      }
+      if (!ROLLOUT) {
+        store_obs<KIND>(io.obs, me, ob);
+        io.reward[me] = c.reward;
+        io.done[me] = (uint8_t)c.done;
+        if (io.events) io.events[me] = (uint8_t)c.events;
+      } else {
+        rsum += c.reward;
+        dcount += c.done ? 1 : 0;
+      }
+      if (--left > 0) {
+        random_action<KIND>(io.seed, (uint64_t)(io.id_offset + me), s.episode, s.step, a);
+        c.phase = 0; c.events = 0; c.hit = 0; c.reward = 0.0f; c.done = s.flags & 1;
+      } else {
+        if (ROLLOUT) {
+          if (io.obs) store_obs<KIND>(io.obs, me, ob);
+          if (io.reward_sum) io.reward_sum[me] = rsum;
+          if (io.done_count) io.done_count[me] = dcount;
+        }
+        store_state(base, io.n, me, s);
+        active = false;
+      }
+    }
   }
-  flush_stats(acc, io.stats);
+  __syncwarp();
+  if (lane < TB_NUM_STATS) {
+    unsigned long long v = sacc[wib][lane];
+    if (v) atomicAdd(io.stats + lane, v);
+  }
 }
 
 template <typename T, int KIND>
@@ -402,6 +463,17 @@ template <typename T> static void build_scene(const Params &p, Scene<T> &sc) {
   sc.net_h[0] = (T)TB_NET_HX; sc.net_h[1] = (T)TB_NET_HY; sc.net_h[2] = (T)TB_NET_HZ;
   sc.goal_r = (T)TB_GOAL_RADIUS; sc.goal_hz = (T)TB_GOAL_HALF_Z;
   build_prism<T, kRacketEdges>(sc.racket, h.racket_v, h.racket_half_x);
+  {
+    double ay = 0, zlo = 1e30, zhi = -1e30;
+    for (int i = 0; i < kRacketEdges; ++i) {
+      ay = std::fmax(ay, std::fabs(h.racket_v[i][0]));
+      zlo = std::fmin(zlo, h.racket_v[i][1]);
+      zhi = std::fmax(zhi, h.racket_v[i][1]);
+    }
+    // rounded outward in T so the reject stays conservative after the conversion
+    sc.racket_box[0] = (T)(ay * (1 + 1e-6)); sc.racket_box[1] = (T)(zlo - 1e-6); sc.racket_box[2] = (T)(zhi + 1e-6);
+    sc.racket_obb[0] = (T)ay; sc.racket_obb[1] = (T)zlo; sc.racket_obb[2] = (T)zhi;
+  }
   build_prism<T, kGoalEdges>(sc.goal, h.goal_v, TB_GOAL_HALF_Z);
 }
 
@@ -436,6 +508,9 @@ struct tb_ctx {
   float *d_actions = nullptr, *d_obs = nullptr, *d_reward = nullptr, *d_term = nullptr;
   uint8_t *d_done = nullptr, *d_events = nullptr, *d_mask = nullptr;
   int64_t launches = 0;
+  unsigned step_grid[2] = {0, 0};
+  unsigned long long *chunk_ctr = nullptr;  // two work counters used alternately by successive step launches
+  int ctr_parity = 0;  // persistent grid of step_kernel<.., ROLLOUT=false/true>
 };
 
 struct DeviceGuard {
@@ -460,6 +535,56 @@ static StepIO make_io(tb_ctx *c) {
   io.state = c->state; io.n = c->cfg.num_envs; io.id_offset = c->cfg.env_id_offset; io.seed = c->cfg.seed;
   io.auto_reset = c->cfg.auto_reset; io.stats = c->stats; io.k_steps = 1;
   return io;
+}
+
+#define DISPATCH(KERNEL, grid, block, stream, ...)                                                          \
+  do {                                                                                                      \
+    if (c->cfg.precision == TB_F64) {                                                                       \
+      if (c->cfg.env_kind == TB_ENV_SWING) KERNEL<double, TB_ENV_SWING><<<grid, block, 0, stream>>>(c->sc64, __VA_ARGS__); \
+      else KERNEL<double, TB_ENV_HIT><<<grid, block, 0, stream>>>(c->sc64, __VA_ARGS__);                      \
+    } else {                                                                                                \
+      if (c->cfg.env_kind == TB_ENV_SWING) KERNEL<float, TB_ENV_SWING><<<grid, block, 0, stream>>>(c->sc32, __VA_ARGS__); \
+      else KERNEL<float, TB_ENV_HIT><<<grid, block, 0, stream>>>(c->sc32, __VA_ARGS__);                       \
+    }                                                                                                       \
+    c->launches++;                                                                                          \
+  } while (0)
+
+// The step kernel is persistent: one CTA per resident slot (SMs x CTAs/SM from the occupancy calculator),
+// fewer when the batch has fewer 32-env groups than that many warps.
+template <typename T, int KIND, bool ROLLOUT> static int step_grid(tb_ctx *c, unsigned *grid) {
+  int per_sm = 0, sms = 0;
+  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, step_kernel<T, KIND, ROLLOUT>, kBlock, 0));
+  CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->cfg.device));
+  int64_t resident = (int64_t)sms * (per_sm > 0 ? per_sm : 1);
+  int64_t chunks = (c->cfg.num_envs + kChunk - 1) / kChunk, need = (chunks + kBlock / 32 - 1) / (kBlock / 32);
+  *grid = (unsigned)(need < resident ? need : resident);
+  return 0;
+}
+template <bool ROLLOUT> static int launch_step(tb_ctx *c, StepIO &io, cudaStream_t stream) {
+  io.chunk_ctr = c->chunk_ctr + c->ctr_parity;
+  io.chunk_ctr_next = c->chunk_ctr + (c->ctr_parity ^ 1);
+  c->ctr_parity ^= 1;
+  unsigned &grid = c->step_grid[ROLLOUT ? 1 : 0];
+  if (c->cfg.precision == TB_F64) {
+    if (c->cfg.env_kind == TB_ENV_SWING) {
+      if (!grid && step_grid<double, TB_ENV_SWING, ROLLOUT>(c, &grid)) return 1;
+      step_kernel<double, TB_ENV_SWING, ROLLOUT><<<grid, kBlock, 0, stream>>>(c->sc64, io);
+    } else {
+      if (!grid && step_grid<double, TB_ENV_HIT, ROLLOUT>(c, &grid)) return 1;
+      step_kernel<double, TB_ENV_HIT, ROLLOUT><<<grid, kBlock, 0, stream>>>(c->sc64, io);
+    }
+  } else {
+    if (c->cfg.env_kind == TB_ENV_SWING) {
+      if (!grid && step_grid<float, TB_ENV_SWING, ROLLOUT>(c, &grid)) return 1;
+      step_kernel<float, TB_ENV_SWING, ROLLOUT><<<grid, kBlock, 0, stream>>>(c->sc32, io);
+    } else {
+      if (!grid && step_grid<float, TB_ENV_HIT, ROLLOUT>(c, &grid)) return 1;
+      step_kernel<float, TB_ENV_HIT, ROLLOUT><<<grid, kBlock, 0, stream>>>(c->sc32, io);
+    }
+  }
+  c->launches++;
+  CU(cudaGetLastError());
+  return 0;
 }
 
 extern "C" {
@@ -517,9 +642,11 @@ int tb_create(const tb_config *cfg, tb_ctx **out) {
   size_t bytes = (size_t)cfg->num_envs * kPacks * 4 * word;
   cudaError_t e = cudaMalloc(&c->state, bytes);
   if (e == cudaSuccess) e = cudaMalloc(&c->stats, TB_NUM_STATS * sizeof(unsigned long long));
+  if (e == cudaSuccess) e = cudaMalloc(&c->chunk_ctr, 2 * sizeof(unsigned long long));
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaMemsetAsync(c->state, 0, bytes, c->own_stream);
   if (e == cudaSuccess) e = cudaMemsetAsync(c->stats, 0, TB_NUM_STATS * sizeof(unsigned long long), c->own_stream);
+  if (e == cudaSuccess) e = cudaMemsetAsync(c->chunk_ctr, 0, 2 * sizeof(unsigned long long), c->own_stream);
   if (e == cudaSuccess) {
     // identity quaternion, episode = -1 so the first reset starts episode 0
     std::size_t n = (size_t)cfg->num_envs;
@@ -554,7 +681,7 @@ int tb_destroy(tb_ctx *c) {
   if (!c) return 0;
   DeviceGuard g(c->cfg.device);
   if (c->own_stream) { cudaStreamSynchronize(c->own_stream); cudaStreamDestroy(c->own_stream); }
-  cudaFree(c->state); cudaFree(c->stats);
+  cudaFree(c->state); cudaFree(c->stats); cudaFree(c->chunk_ctr);
   cudaFree(c->d_actions); cudaFree(c->d_obs); cudaFree(c->d_reward); cudaFree(c->d_term);
   cudaFree(c->d_done); cudaFree(c->d_events); cudaFree(c->d_mask);
   delete c;
@@ -575,18 +702,6 @@ int tb_get_param(tb_ctx *c, const char *name, double *value) {
     if (!std::strcmp(name, k_param_names[i])) { *value = slots[i]; return 0; }
   return fail("tb_get_param: unknown parameter '%s'", name);
 }
-
-#define DISPATCH(KERNEL, grid, block, stream, ...)                                                          \
-  do {                                                                                                      \
-    if (c->cfg.precision == TB_F64) {                                                                       \
-      if (c->cfg.env_kind == TB_ENV_SWING) KERNEL<double, TB_ENV_SWING><<<grid, block, 0, stream>>>(c->sc64, __VA_ARGS__); \
-      else KERNEL<double, TB_ENV_HIT><<<grid, block, 0, stream>>>(c->sc64, __VA_ARGS__);                      \
-    } else {                                                                                                \
-      if (c->cfg.env_kind == TB_ENV_SWING) KERNEL<float, TB_ENV_SWING><<<grid, block, 0, stream>>>(c->sc32, __VA_ARGS__); \
-      else KERNEL<float, TB_ENV_HIT><<<grid, block, 0, stream>>>(c->sc32, __VA_ARGS__);                       \
-    }                                                                                                       \
-    c->launches++;                                                                                          \
-  } while (0)
 
 static int reset_impl(tb_ctx *c, const double *d_init, const uint8_t *d_mask, float *d_obs, void *stream) {
   GUARD(c);
@@ -609,9 +724,7 @@ int tb_step(tb_ctx *c, const float *d_actions, float *d_obs, float *d_reward, ui
   StepIO io = make_io(c);
   io.actions = d_actions; io.obs = d_obs; io.reward = d_reward; io.done = d_done; io.term_obs = d_terminal_obs;
   io.events = d_events;
-  DISPATCH(step_kernel, grid_for(io.n, kBlock), kBlock, (cudaStream_t)stream, io);
-  CU(cudaGetLastError());
-  return 0;
+  return launch_step<false>(c, io, (cudaStream_t)stream);
 }
 
 int tb_rollout(tb_ctx *c, int action_mode, int k_steps, float *d_obs, float *d_reward_sum, int32_t *d_done_count, void *stream) {
@@ -620,9 +733,7 @@ int tb_rollout(tb_ctx *c, int action_mode, int k_steps, float *d_obs, float *d_r
   if (k_steps < 0) return fail("%s", "tb_rollout: k_steps must be >= 0");
   StepIO io = make_io(c);
   io.k_steps = k_steps; io.obs = d_obs; io.reward_sum = d_reward_sum; io.done_count = d_done_count;
-  DISPATCH(rollout_kernel, grid_for(io.n, kBlock), kBlock, (cudaStream_t)stream, io);
-  CU(cudaGetLastError());
-  return 0;
+  return launch_step<true>(c, io, (cudaStream_t)stream);
 }
 
 int tb_get_state(tb_ctx *c, double *d_state, void *stream) {

@@ -14,8 +14,8 @@ pytestmark = pytest.mark.gpu
 
 TOL_F64_STATE = 5e-8   # absolute, on a state record whose spin entries reach ~50 rad/s after a bounce
 TOL_F64_OUT = 2e-6      # float32 rounding of the outputs at |x| <= 20
-BAND_F32 = 2e-3         # metres: fp32 position drift over an 800-substep flight stays far below this
-TOL_F32_OUT = 5e-3
+BAND_F32 = 2e-4         # metres: fp32 position drift over an 800-substep flight stays below this
+TOL_F32_OUT = 1e-3
 
 
 def _make(env, n, precision, seed, oracle_lib):
@@ -85,7 +85,7 @@ def test_f32_parity_with_band(oracle_lib, env, steps):
     rep, valid = run_parity(b, o, steps, lambda t, _obs: rng.uniform(-1, 1, (n, o.act_dim)), band=BAND_F32)
     print(rep)
     assert rep.event_mismatch_hard == 0
-    assert rep.dropped < 0.02 * n
+    assert rep.dropped < 0.05 * n
     assert rep.max_obs_err < TOL_F32_OUT and rep.max_reward_err < 10 * TOL_F32_OUT
 
 
