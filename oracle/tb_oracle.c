@@ -440,7 +440,6 @@ static int physics_step(const tbo_ctx *c, double *s, const double *f_racket, con
     {
       double low = s[S_RP + 2] - fabs(R[6]) * c->racket.half_thick - fabs(R[7]) * c->racket_box[0] +
                    fmin(R[8] * c->racket_box[1], R[8] * c->racket_box[2]) - P->hull_margin;
-      probe(pb, low - (TBO_FLOOR_HZ + T));
       if (low <= TBO_FLOOR_HZ + T && fabs(s[S_RP]) <= TBO_FLOOR_HX + 1 && fabs(s[S_RP + 1]) <= TBO_FLOOR_HY + 1)
         bits |= TBO_EV_RACKET_LOW;
     }

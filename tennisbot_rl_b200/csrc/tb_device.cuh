@@ -78,6 +78,7 @@ template <typename T> struct Scene {
   T floor_h[3], net_h[3], goal_r, goal_hz;
   T racket_box[3];  // outline bounding box in the COM frame: max |y|, min z, max z (grown by 1e-6: reject only)
   T racket_obb[3];  // the same box, exact: TB_EV_RACKET_LOW
+  T racket_obb_radius;  // distance of its farthest corner from the COM (pre-check of the same test)
   Prism<T, kRacketEdges> racket;
   Prism<T, kGoalEdges> goal;
 };
@@ -492,7 +493,7 @@ __device__ __forceinline__ int physics_step(const Scene<T> &sc, St<T> &s, const 
     // over); TB_EV_RACKET_LOW marks the steps from which its pose is outside the parity horizon: the lowest
     // corner of the hull's oriented bounding box (outline box x plate thickness, margin included) is at or below
     // the floor's contact threshold while the COM is over the court.
-    if (!(known_bits & TB_EV_RACKET_LOW) && s.rp[2] - sc.racket.bound_radius - sc.hull_margin <= sc.floor_h[2] + thr) {
+    if (!(known_bits & TB_EV_RACKET_LOW) && s.rp[2] - sc.racket_obb_radius - sc.hull_margin <= sc.floor_h[2] + thr) {
       const T *q = s.rq;
       T r6 = 2 * (q[0] * q[2] - q[1] * q[3]), r7 = 2 * (q[1] * q[2] + q[0] * q[3]), r8 = 1 - 2 * (q[0] * q[0] + q[1] * q[1]);
       T zlo = r8 * sc.racket_obb[1], zhi = r8 * sc.racket_obb[2];

@@ -33,11 +33,7 @@ template <> struct MinBlocks<double> { static constexpr int v = TB_MINB64; };
 #ifndef TB_REFILL_MIN
 #define TB_REFILL_MIN 8
 #endif
-#ifndef TB_CHUNK
-#define TB_CHUNK 128
-#endif
 constexpr int kRefillMin = TB_REFILL_MIN;   // idle lanes that trigger a refill before the periodic one
-constexpr int kChunk = TB_CHUNK;     // envs a warp claims per grab from the launch-wide work counter
 
 // ------------------------------------------------------------------------------------------------ pack I/O
 template <typename T> struct Pack { T x, y, z, w; };
@@ -99,7 +95,10 @@ struct StepIO {
   uint8_t *done, *events;
   int32_t *done_count;
   unsigned long long *stats;
-  unsigned long long *chunk_ctr, *chunk_ctr_next;  // dynamic work distribution: this launch's counter, the next one's
+  int *queue;                        // env indices waiting for ff_kernel
+  unsigned long long *queue_ctr;     // [0] entries appended by this step's step_kernel
+  unsigned long long *queue_head;    // [1] entries claimed by ff_kernel lanes
+  unsigned long long *queue_ctr_next;  // the pair the NEXT step uses; step_kernel zeroes it
 };
 
 template <int KIND> struct Dims {
@@ -138,125 +137,247 @@ template <int KIND> __device__ __forceinline__ void random_action(uint64_t seed,
   }
 }
 
-// The env-step kernel.  Persistent warps, each owning a contiguous range of envs; every LANE is a little state
-// machine: idle lanes pick the next env of the warp's range (128-bit coalesced loads when the whole warp refills,
-// which is every iteration while envs are in their one-substep control phase), active lanes advance their env by
-// one physics substep per loop iteration with the state in registers, and a lane whose env step completed
-// writes obs / reward / done, auto-resets if the episode ended, stores the state and goes idle.  A lane stuck in
-// SwingRacket's fast-forward (up to 776 substeps) therefore delays nobody: its neighbours keep taking new envs.
-//   ROLLOUT = false: one env step per env, actions from HBM (gym / VecEnv step()).
-//   ROLLOUT = true : k_steps env steps per env with in-kernel Philox actions; state never leaves registers.
+// ------------------------------------------------------------------------------------------------ step kernels
+// An env step is one physics substep for every env, except SwingRacket's 26th step, which goes on for up to
+// 775 more.  The step is therefore issued as two launches on the same stream:
+//
+//   step_kernel  one thread per env, plain grid: loads state + action (128-bit coalesced), runs the substep the
+//                action drives and the env logic; envs whose step is complete write obs / reward / done,
+//                auto-reset and store their state.  HBM-bound.  Envs that enter the fast-forward store their state
+//                with the in-flight mark and append their index to a work queue (one atomic per CTA).
+//   ff_kernel    persistent warps; every LANE is a small state machine that pulls an env from the queue, keeps
+//                its state in registers for the whole fast-forward (one substep per loop iteration) and, when the
+//                ball lands / times out, finishes the env step and goes back for another env.  A lane stuck in an
+//                800-substep flight delays nobody.  ALU/latency-bound; launched on every step, exits at once
+//                when the queue is empty.
+//
 // Episode statistics are warp-uniform popc()/redux sums kept in shared memory, one atomic per counter per warp.
-template <typename T, int KIND, bool ROLLOUT>
-__global__ void __launch_bounds__(kBlock, MinBlocks<T>::v) step_kernel(const __grid_constant__ Scene<T> sc, const __grid_constant__ StepIO io) {
+constexpr int kFlagDone = 1, kFlagInFlight = 2, kFlagEventShift = 8;
+
+struct WarpStats {
+  unsigned long long *acc;  // this warp's row of the CTA's shared accumulators
+  int lane;
+  __device__ __forceinline__ void init(unsigned long long *row, int l) {
+    acc = row; lane = l;
+    if (lane < TB_NUM_STATS) acc[lane] = 0;
+    __syncwarp();
+  }
+  __device__ __forceinline__ void flush(unsigned long long *global) {
+    __syncwarp();
+    if (lane < TB_NUM_STATS) {
+      unsigned long long v = acc[lane];
+      if (v) atomicAdd(global + lane, v);
+    }
+  }
+};
+
+// Bookkeeping of completed env steps, called by all 32 lanes (fin = this lane's env step completed now).
+template <typename T>
+__device__ __forceinline__ void account(WarpStats &ws, bool fin, bool done, int hit, int events, int step, T ret) {
+  const unsigned full = 0xffffffffu;
+  unsigned fin_mask = __ballot_sync(full, fin);
+  if (!fin_mask) return;
+  bool dn = fin && done;
+  unsigned done_mask = __ballot_sync(full, dn), hit_mask = __ballot_sync(full, fin && hit);
+  if (done_mask) {
+    unsigned goal_m = __ballot_sync(full, dn && (events & TB_EV_GOAL_BALL));
+    unsigned court_m = __ballot_sync(full, dn && (events & TB_EV_COURT_BALL));
+    unsigned to_m = __ballot_sync(full, dn && (events & TB_EV_TIMEOUT) &&
+                                            !(events & (TB_EV_GOAL_BALL | TB_EV_COURT_BALL | TB_EV_BALL_PASSED)));
+    int len = __reduce_add_sync(full, dn ? step : 0);
+    double r = dn ? (double)ret : 0.0;
+    long long r1 = __double2ll_rn(r * 1048576.0), r2 = __double2ll_rn(r * r * 1024.0);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      r1 += __shfl_down_sync(full, r1, o);
+      r2 += __shfl_down_sync(full, r2, o);
+    }
+    if (ws.lane == 0) {
+      ws.acc[TB_STAT_EPISODES] += __popc(done_mask);
+      ws.acc[TB_STAT_SUM_LENGTH] += len;
+      ws.acc[TB_STAT_GOALS] += __popc(goal_m);
+      ws.acc[TB_STAT_COURT] += __popc(court_m);
+      ws.acc[TB_STAT_TIMEOUTS] += __popc(to_m);
+      ws.acc[TB_STAT_SUM_RETURN_Q20] += (unsigned long long)r1;
+      ws.acc[TB_STAT_SUM_RETURN2_Q10] += (unsigned long long)r2;
+    }
+  }
+  if (ws.lane == 0) {
+    ws.acc[TB_STAT_ENV_STEPS] += __popc(fin_mask);
+    ws.acc[TB_STAT_RACKET_HITS] += __popc(hit_mask);
+  }
+}
+
+// Completion of an env step for one lane: terminal observation, auto-reset, outputs.  The caller stores the state.
+template <typename T, int KIND>
+__device__ __forceinline__ void finish_api(const Scene<T> &sc, const StepIO &io, int64_t me, St<T> &s, float reward,
+                                           bool done, int events) {
+  float ob[12];
+  pack_obs<T, KIND>(s, ob);
+  if (done) {
+    if (io.term_obs) store_obs<KIND>(io.term_obs, me, ob);
+    if (io.auto_reset) {
+      uint32_t ep = s.episode + 1;
+      T in[TB_INIT_WORDS];
+      draw_init<T, KIND>(io.seed, (uint64_t)(io.id_offset + me), ep, in);
+      start_episode<T, KIND>(sc, s, in, ep);
+      pack_obs<T, KIND>(s, ob);
+    } else {
+      s.flags |= kFlagDone;
+    }
+  }
+  store_obs<KIND>(io.obs, me, ob);
+  io.reward[me] = reward;
+  io.done[me] = (uint8_t)done;
+  if (io.events) io.events[me] = (uint8_t)events;
+}
+
+template <typename T, int KIND>
+__global__ void __launch_bounds__(kBlock) step_kernel(const __grid_constant__ Scene<T> sc, const __grid_constant__ StepIO io) {
   __shared__ unsigned long long sacc[kBlock / 32][TB_NUM_STATS];
+  __shared__ int s_cnt[kBlock / 32];
+  __shared__ unsigned long long s_base;
   const unsigned full = 0xffffffffu;
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  const int64_t warp = (int64_t)blockIdx.x * (kBlock / 32) + wib, nwarps = (int64_t)gridDim.x * (kBlock / 32);
-  // work distribution: chunk `warp` is owned statically, further chunks come from an atomic counter, fetched one
-  // grab ahead so its latency hides behind the chunk being processed
-  const int64_t nchunks = (io.n + kChunk - 1) / kChunk;
-  int64_t next = warp * kChunk, hi = next + kChunk;
-  if (next > io.n) next = io.n;
-  if (hi > io.n) hi = io.n;
-  unsigned long long pending = 0;
-  bool exhausted = false;
-  if (lane == 0) pending = atomicAdd(io.chunk_ctr, 1ULL) + (unsigned long long)nwarps;
-  if (blockIdx.x == 0 && threadIdx.x == 0) *io.chunk_ctr_next = 0;
-  if (lane < TB_NUM_STATS) sacc[wib][lane] = 0;
-  __syncwarp();
+  WarpStats ws;
+  ws.init(sacc[wib], lane);
+  if (blockIdx.x == 0 && threadIdx.x == 0) { io.queue_ctr_next[0] = 0; io.queue_ctr_next[1] = 0; }
 
+  const int64_t me = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+  const bool valid = me < io.n;
   T *base = static_cast<T *>(io.state);
   St<T> s;
   StepCtl c = {0, 0, 0, 0.0f, false};
-  float a[8];
-  int64_t me = 0;
-  int left = 0, dcount = 0;
-  float rsum = 0;
-  bool active = false;
+  bool fin = false;
+  if (valid) {
+    float a[8];
+    load_state(base, io.n, me, s);
+    load_action<KIND>(io.actions, me, a);
+    c.done = s.flags & kFlagDone;
+    fin = env_substep<T, KIND>(sc, s, a, c);
+    if (fin) s.ret += (T)c.reward;
+  }
+  unsigned act_mask = __ballot_sync(full, valid);
+  if (lane == 0) ws.acc[TB_STAT_PHYSICS_STEPS] += __popc(act_mask);
+  account<T>(ws, fin, c.done, c.hit, c.events, s.step, s.ret);
+  if (valid && fin) finish_api<T, KIND>(sc, io, me, s, c.reward, c.done, c.events);
+
+  // envs entering the fast-forward: queue them for ff_kernel (only SwingRacket ever does)
+  bool queued = valid && !fin;
+  if (KIND == TB_ENV_SWING) {
+    unsigned qmask = __ballot_sync(full, queued);
+    if (lane == 0) s_cnt[wib] = __popc(qmask);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int tot = 0;
+#pragma unroll
+      for (int w = 0; w < kBlock / 32; ++w) { int t = s_cnt[w]; s_cnt[w] = tot; tot += t; }
+      s_base = tot ? atomicAdd(io.queue_ctr, (unsigned long long)tot) : 0ULL;
+    }
+    __syncthreads();
+    if (queued) {
+      io.queue[s_base + s_cnt[wib] + __popc(qmask & ((1u << lane) - 1u))] = (int)me;
+      s.flags = (s.flags & ~(0xff << kFlagEventShift)) | kFlagInFlight | (c.events << kFlagEventShift);
+    }
+  }
+  if (valid) store_state(base, io.n, me, s);
+  ws.flush(io.stats);
+}
+
+// Fast-forward continuation (SwingRacket only).
+template <typename T>
+__global__ void __launch_bounds__(kBlock, MinBlocks<T>::v) ff_kernel(const __grid_constant__ Scene<T> sc, const __grid_constant__ StepIO io) {
+  constexpr int KIND = TB_ENV_SWING;
+  __shared__ unsigned long long sacc[kBlock / 32][TB_NUM_STATS];
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const long long qn = (long long)*io.queue_ctr;  // number of queued envs (written by step_kernel, same stream)
+  if (qn == 0) return;
+  WarpStats ws;
+  ws.init(sacc[wib], lane);
+
+  T *base = static_cast<T *>(io.state);
+  St<T> s;
+  StepCtl c = {1, 0, 0, 0.0f, false};
+  int me = 0;
+  bool active = false, exhausted = false;
 
 #pragma unroll 1
   for (unsigned iter = 0;; ++iter) {
-    // ---- refill idle lanes from the warp's range
+    // ---- idle lanes claim queue entries (one atomic per refill event per warp)
     unsigned idle = __ballot_sync(full, !active);
-    if (idle && next >= hi && !exhausted) {
-      long long ch = (long long)__shfl_sync(full, pending, 0);
-      if (ch < nchunks) {
-        next = ch * kChunk;
-        hi = next + kChunk < io.n ? next + kChunk : io.n;
-        if (lane == 0) pending = atomicAdd(io.chunk_ctr, 1ULL) + (unsigned long long)nwarps;
-      } else {
-        exhausted = true;
+    if (idle && !exhausted && (idle == full || __popc(idle) >= kRefillMin || (iter & 15u) == 0)) {
+      int want = __popc(idle);
+      long long first = 0;
+      if (lane == 0) first = (long long)atomicAdd(io.queue_head, (unsigned long long)want);
+      first = __shfl_sync(full, first, 0);
+      if (first + want >= qn) exhausted = true;
+      long long idx = first + __popc(idle & ((1u << lane) - 1u));
+      if (!active && idx < qn) {
+        me = io.queue[idx];
+        load_state(base, io.n, (int64_t)me, s);
+        c.phase = 1;
+        c.events = (s.flags >> kFlagEventShift) & 0xff;
+        c.hit = 0; c.reward = 0.0f; c.done = false;
+        active = true;
       }
-    }
-    if (idle && next < hi && (idle == full || __popc(idle) >= kRefillMin || (iter & 15u) == 0)) {
-      int rank = __popc(idle & ((1u << lane) - 1u));
-      int64_t avail = hi - next;
-      int take = __popc(idle) < avail ? __popc(idle) : (int)avail;
-      if (!active && rank < take) {
-        me = next + rank;
-        load_state(base, io.n, me, s);
-        if (!ROLLOUT) load_action<KIND>(io.actions, me, a);
-        else random_action<KIND>(io.seed, (uint64_t)(io.id_offset + me), s.episode, s.step, a);
-        c.phase = 0; c.events = 0; c.hit = 0; c.reward = 0.0f; c.done = s.flags & 1;
-        left = ROLLOUT ? io.k_steps : 1;
-        rsum = 0; dcount = 0;
-        active = left > 0;
-      }
-      next += take;
     }
     unsigned act_mask = __ballot_sync(full, active);
     if (!act_mask) break;
 
     // ---- one physics substep for every active lane
     bool fin = false;
-    if (active) fin = env_substep<T, KIND>(sc, s, a, c);
-
-    // ---- warp-uniform statistics
-    unsigned fin_mask = __ballot_sync(full, fin);
-    if (lane == 0) sacc[wib][TB_STAT_PHYSICS_STEPS] += __popc(act_mask);
-#ifdef TB_DEBUG_ITERS  // experiment only: count warp iterations x 32 in the env-steps slot to read lane utilisation
-    if (lane == 0) sacc[wib][TB_STAT_ENV_STEPS] += 32;
+    if (active) fin = env_substep<T, KIND>(sc, s, nullptr, c);
+    if (lane == 0) ws.acc[TB_STAT_PHYSICS_STEPS] += __popc(act_mask);
+#ifdef TB_DEBUG_ITERS  // experiment only: warp iterations x 32 in the env-steps slot, to read lane utilisation
+    if (lane == 0) ws.acc[TB_STAT_ENV_STEPS] += 32;
 #endif
-    if (fin_mask) {
-      bool dn = fin && c.done;
-      unsigned done_mask = __ballot_sync(full, dn), hit_mask = __ballot_sync(full, fin && c.hit);
-      if (fin) s.ret += (T)c.reward;
-      if (done_mask) {
-        unsigned goal_m = __ballot_sync(full, dn && (c.events & TB_EV_GOAL_BALL));
-        unsigned court_m = __ballot_sync(full, dn && (c.events & TB_EV_COURT_BALL));
-        unsigned to_m = __ballot_sync(full, dn && (c.events & TB_EV_TIMEOUT) &&
-                                                !(c.events & (TB_EV_GOAL_BALL | TB_EV_COURT_BALL | TB_EV_BALL_PASSED)));
-        int len = __reduce_add_sync(full, dn ? s.step : 0);
-        double r = dn ? (double)s.ret : 0.0;
-        long long r1 = __double2ll_rn(r * 1048576.0), r2 = __double2ll_rn(r * r * 1024.0);
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-          r1 += __shfl_down_sync(full, r1, o);
-          r2 += __shfl_down_sync(full, r2, o);
-        }
-        if (lane == 0) {
-          sacc[wib][TB_STAT_EPISODES] += __popc(done_mask);
-          sacc[wib][TB_STAT_SUM_LENGTH] += len;
-          sacc[wib][TB_STAT_GOALS] += __popc(goal_m);
-          sacc[wib][TB_STAT_COURT] += __popc(court_m);
-          sacc[wib][TB_STAT_TIMEOUTS] += __popc(to_m);
-          sacc[wib][TB_STAT_SUM_RETURN_Q20] += (unsigned long long)r1;
-          sacc[wib][TB_STAT_SUM_RETURN2_Q10] += (unsigned long long)r2;
-        }
-      }
-      if (lane == 0) {
-        sacc[wib][TB_STAT_ENV_STEPS] += __popc(fin_mask);
-        sacc[wib][TB_STAT_RACKET_HITS] += __popc(hit_mask);
-      }
-    }
-
-    // ---- lanes whose env step completed: outputs, auto-reset, then next rollout step or state store
+    if (fin) s.ret += (T)c.reward;
+    account<T>(ws, fin, c.done, 0, c.events, s.step, s.ret);
     if (fin) {
-      float ob[12];
+      s.flags &= kFlagDone;  // drop the in-flight mark and the parked event bits
+      finish_api<T, KIND>(sc, io, (int64_t)me, s, c.reward, c.done, c.events);
+      store_state(base, io.n, (int64_t)me, s);
+      active = false;
+    }
+  }
+  ws.flush(io.stats);
+}
+
+// Fused rollout: K env steps per env in one launch with in-kernel Philox actions; one thread per env, the state
+// stays in registers for the whole rollout (the fast-forward runs in line).
+template <typename T, int KIND>
+__global__ void __launch_bounds__(kBlock) rollout_kernel(const __grid_constant__ Scene<T> sc, const __grid_constant__ StepIO io) {
+  __shared__ unsigned long long sacc[kBlock / 32][TB_NUM_STATS];
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  WarpStats ws;
+  ws.init(sacc[wib], lane);
+  const int64_t me = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+  T *base = static_cast<T *>(io.state);
+  St<T> s;
+  StepCtl c = {0, 0, 0, 0.0f, false};
+  float a[8], ob[12] = {0}, rsum = 0;
+  int left = 0, dcount = 0;
+  bool active = me < io.n && io.k_steps > 0;
+  if (me < io.n) load_state(base, io.n, me, s);
+  if (active) {
+    left = io.k_steps;
+    random_action<KIND>(io.seed, (uint64_t)(io.id_offset + me), s.episode, s.step, a);
+    c.done = s.flags & kFlagDone;
+  }
+#pragma unroll 1
+  while (true) {
+    unsigned act_mask = __ballot_sync(full, active);
+    if (!act_mask) break;
+    bool fin = false;
+    if (active) fin = env_substep<T, KIND>(sc, s, a, c);
+    if (lane == 0) ws.acc[TB_STAT_PHYSICS_STEPS] += __popc(act_mask);
+    if (fin) s.ret += (T)c.reward;
+    account<T>(ws, fin, c.done, c.hit, c.events, s.step, s.ret);
+    if (fin) {
       pack_obs<T, KIND>(s, ob);
       if (c.done) {
-        if (!ROLLOUT && io.term_obs) store_obs<KIND>(io.term_obs, me, ob);
         if (io.auto_reset) {
           uint32_t ep = s.episode + 1;
           T in[TB_INIT_WORDS];
@@ -264,37 +385,28 @@ __global__ void __launch_bounds__(kBlock, MinBlocks<T>::v) step_kernel(const __g
           start_episode<T, KIND>(sc, s, in, ep);
           pack_obs<T, KIND>(s, ob);
         } else {
-          s.flags |= 1;
+          s.flags |= kFlagDone;
         }
       }
-      if (!ROLLOUT) {
-        store_obs<KIND>(io.obs, me, ob);
-        io.reward[me] = c.reward;
-        io.done[me] = (uint8_t)c.done;
-        if (io.events) io.events[me] = (uint8_t)c.events;
-      } else {
-        rsum += c.reward;
-        dcount += c.done ? 1 : 0;
-      }
+      rsum += c.reward;
+      dcount += c.done ? 1 : 0;
       if (--left > 0) {
         random_action<KIND>(io.seed, (uint64_t)(io.id_offset + me), s.episode, s.step, a);
-        c.phase = 0; c.events = 0; c.hit = 0; c.reward = 0.0f; c.done = s.flags & 1;
+        c.phase = 0; c.events = 0; c.hit = 0; c.reward = 0.0f; c.done = s.flags & kFlagDone;
       } else {
-        if (ROLLOUT) {
-          if (io.obs) store_obs<KIND>(io.obs, me, ob);
-          if (io.reward_sum) io.reward_sum[me] = rsum;
-          if (io.done_count) io.done_count[me] = dcount;
-        }
-        store_state(base, io.n, me, s);
         active = false;
       }
     }
   }
-  __syncwarp();
-  if (lane < TB_NUM_STATS) {
-    unsigned long long v = sacc[wib][lane];
-    if (v) atomicAdd(io.stats + lane, v);
+  if (me < io.n) {
+    if (io.k_steps > 0) {
+      if (io.obs) store_obs<KIND>(io.obs, me, ob);
+      if (io.reward_sum) io.reward_sum[me] = rsum;
+      if (io.done_count) io.done_count[me] = dcount;
+    }
+    store_state(base, io.n, me, s);
   }
+  ws.flush(io.stats);
 }
 
 template <typename T, int KIND>
@@ -473,6 +585,8 @@ template <typename T> static void build_scene(const Params &p, Scene<T> &sc) {
     // rounded outward in T so the reject stays conservative after the conversion
     sc.racket_box[0] = (T)(ay * (1 + 1e-6)); sc.racket_box[1] = (T)(zlo - 1e-6); sc.racket_box[2] = (T)(zhi + 1e-6);
     sc.racket_obb[0] = (T)ay; sc.racket_obb[1] = (T)zlo; sc.racket_obb[2] = (T)zhi;
+    double zm = std::fmax(std::fabs(zlo), std::fabs(zhi));
+    sc.racket_obb_radius = (T)(std::sqrt(h.racket_half_x * h.racket_half_x + ay * ay + zm * zm) * (1 + 1e-6));
   }
   build_prism<T, kGoalEdges>(sc.goal, h.goal_v, TB_GOAL_HALF_Z);
 }
@@ -508,9 +622,10 @@ struct tb_ctx {
   float *d_actions = nullptr, *d_obs = nullptr, *d_reward = nullptr, *d_term = nullptr;
   uint8_t *d_done = nullptr, *d_events = nullptr, *d_mask = nullptr;
   int64_t launches = 0;
-  unsigned step_grid[2] = {0, 0};
-  unsigned long long *chunk_ctr = nullptr;  // two work counters used alternately by successive step launches
-  int ctr_parity = 0;  // persistent grid of step_kernel<.., ROLLOUT=false/true>
+  int *queue = nullptr;                      // fast-forward work queue (env indices), num_envs entries
+  unsigned long long *queue_ctrs = nullptr;  // two (appended, claimed) counter pairs used by alternate steps
+  int parity = 0;
+  unsigned ff_grid = 0;                      // persistent grid of ff_kernel  // persistent grid of step_kernel<.., ROLLOUT=false/true>
 };
 
 struct DeviceGuard {
@@ -549,41 +664,45 @@ static StepIO make_io(tb_ctx *c) {
     c->launches++;                                                                                          \
   } while (0)
 
-// The step kernel is persistent: one CTA per resident slot (SMs x CTAs/SM from the occupancy calculator),
-// fewer when the batch has fewer 32-env groups than that many warps.
-template <typename T, int KIND, bool ROLLOUT> static int step_grid(tb_ctx *c, unsigned *grid) {
+// ff_kernel is persistent: one CTA per resident slot (SMs x CTAs/SM from the occupancy calculator).
+template <typename T> static int ff_grid_size(tb_ctx *c, unsigned *grid) {
   int per_sm = 0, sms = 0;
-  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, step_kernel<T, KIND, ROLLOUT>, kBlock, 0));
+  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ff_kernel<T>, kBlock, 0));
   CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->cfg.device));
   int64_t resident = (int64_t)sms * (per_sm > 0 ? per_sm : 1);
-  int64_t chunks = (c->cfg.num_envs + kChunk - 1) / kChunk, need = (chunks + kBlock / 32 - 1) / (kBlock / 32);
+  int64_t need = (c->cfg.num_envs + kBlock - 1) / kBlock;
   *grid = (unsigned)(need < resident ? need : resident);
   return 0;
 }
-template <bool ROLLOUT> static int launch_step(tb_ctx *c, StepIO &io, cudaStream_t stream) {
-  io.chunk_ctr = c->chunk_ctr + c->ctr_parity;
-  io.chunk_ctr_next = c->chunk_ctr + (c->ctr_parity ^ 1);
-  c->ctr_parity ^= 1;
-  unsigned &grid = c->step_grid[ROLLOUT ? 1 : 0];
+// One env step = step_kernel (+ ff_kernel for SwingRacket) on `stream`.
+static int launch_step(tb_ctx *c, StepIO &io, cudaStream_t stream) {
+  io.queue = c->queue;
+  io.queue_ctr = c->queue_ctrs + 2 * c->parity;
+  io.queue_head = io.queue_ctr + 1;
+  io.queue_ctr_next = c->queue_ctrs + 2 * (c->parity ^ 1);
+  c->parity ^= 1;
+  const unsigned grid = grid_for(io.n, kBlock);
+  const bool swing = c->cfg.env_kind == TB_ENV_SWING;
   if (c->cfg.precision == TB_F64) {
-    if (c->cfg.env_kind == TB_ENV_SWING) {
-      if (!grid && step_grid<double, TB_ENV_SWING, ROLLOUT>(c, &grid)) return 1;
-      step_kernel<double, TB_ENV_SWING, ROLLOUT><<<grid, kBlock, 0, stream>>>(c->sc64, io);
-    } else {
-      if (!grid && step_grid<double, TB_ENV_HIT, ROLLOUT>(c, &grid)) return 1;
-      step_kernel<double, TB_ENV_HIT, ROLLOUT><<<grid, kBlock, 0, stream>>>(c->sc64, io);
-    }
+    if (swing) step_kernel<double, TB_ENV_SWING><<<grid, kBlock, 0, stream>>>(c->sc64, io);
+    else step_kernel<double, TB_ENV_HIT><<<grid, kBlock, 0, stream>>>(c->sc64, io);
   } else {
-    if (c->cfg.env_kind == TB_ENV_SWING) {
-      if (!grid && step_grid<float, TB_ENV_SWING, ROLLOUT>(c, &grid)) return 1;
-      step_kernel<float, TB_ENV_SWING, ROLLOUT><<<grid, kBlock, 0, stream>>>(c->sc32, io);
-    } else {
-      if (!grid && step_grid<float, TB_ENV_HIT, ROLLOUT>(c, &grid)) return 1;
-      step_kernel<float, TB_ENV_HIT, ROLLOUT><<<grid, kBlock, 0, stream>>>(c->sc32, io);
-    }
+    if (swing) step_kernel<float, TB_ENV_SWING><<<grid, kBlock, 0, stream>>>(c->sc32, io);
+    else step_kernel<float, TB_ENV_HIT><<<grid, kBlock, 0, stream>>>(c->sc32, io);
   }
   c->launches++;
   CU(cudaGetLastError());
+  if (swing) {
+    if (c->cfg.precision == TB_F64) {
+      if (!c->ff_grid && ff_grid_size<double>(c, &c->ff_grid)) return 1;
+      ff_kernel<double><<<c->ff_grid, kBlock, 0, stream>>>(c->sc64, io);
+    } else {
+      if (!c->ff_grid && ff_grid_size<float>(c, &c->ff_grid)) return 1;
+      ff_kernel<float><<<c->ff_grid, kBlock, 0, stream>>>(c->sc32, io);
+    }
+    c->launches++;
+    CU(cudaGetLastError());
+  }
   return 0;
 }
 
@@ -623,7 +742,7 @@ int tb_create(const tb_config *cfg, tb_ctx **out) {
   if (cfg->struct_size != sizeof(tb_config)) return fail("%s", "tb_create: tb_config.struct_size mismatch");
   if (cfg->env_kind != TB_ENV_SWING && cfg->env_kind != TB_ENV_HIT) return fail("%s", "tb_create: unknown env_kind");
   if (cfg->precision != TB_F32 && cfg->precision != TB_F64) return fail("%s", "tb_create: unknown precision");
-  if (cfg->num_envs <= 0) return fail("%s", "tb_create: num_envs must be positive");
+  if (cfg->num_envs <= 0 || cfg->num_envs > 0x7fffffffLL) return fail("%s", "tb_create: num_envs must be in [1, 2^31)");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
     return fail("%s", "tb_create: no CUDA device (this library has no CPU fallback)");
@@ -642,11 +761,12 @@ int tb_create(const tb_config *cfg, tb_ctx **out) {
   size_t bytes = (size_t)cfg->num_envs * kPacks * 4 * word;
   cudaError_t e = cudaMalloc(&c->state, bytes);
   if (e == cudaSuccess) e = cudaMalloc(&c->stats, TB_NUM_STATS * sizeof(unsigned long long));
-  if (e == cudaSuccess) e = cudaMalloc(&c->chunk_ctr, 2 * sizeof(unsigned long long));
+  if (e == cudaSuccess) e = cudaMalloc(&c->queue_ctrs, 4 * sizeof(unsigned long long));
+  if (e == cudaSuccess && cfg->env_kind == TB_ENV_SWING) e = cudaMalloc(&c->queue, (size_t)cfg->num_envs * sizeof(int));
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaMemsetAsync(c->state, 0, bytes, c->own_stream);
   if (e == cudaSuccess) e = cudaMemsetAsync(c->stats, 0, TB_NUM_STATS * sizeof(unsigned long long), c->own_stream);
-  if (e == cudaSuccess) e = cudaMemsetAsync(c->chunk_ctr, 0, 2 * sizeof(unsigned long long), c->own_stream);
+  if (e == cudaSuccess) e = cudaMemsetAsync(c->queue_ctrs, 0, 4 * sizeof(unsigned long long), c->own_stream);
   if (e == cudaSuccess) {
     // identity quaternion, episode = -1 so the first reset starts episode 0
     std::size_t n = (size_t)cfg->num_envs;
@@ -681,7 +801,7 @@ int tb_destroy(tb_ctx *c) {
   if (!c) return 0;
   DeviceGuard g(c->cfg.device);
   if (c->own_stream) { cudaStreamSynchronize(c->own_stream); cudaStreamDestroy(c->own_stream); }
-  cudaFree(c->state); cudaFree(c->stats); cudaFree(c->chunk_ctr);
+  cudaFree(c->state); cudaFree(c->stats); cudaFree(c->queue_ctrs); cudaFree(c->queue);
   cudaFree(c->d_actions); cudaFree(c->d_obs); cudaFree(c->d_reward); cudaFree(c->d_term);
   cudaFree(c->d_done); cudaFree(c->d_events); cudaFree(c->d_mask);
   delete c;
@@ -724,7 +844,7 @@ int tb_step(tb_ctx *c, const float *d_actions, float *d_obs, float *d_reward, ui
   StepIO io = make_io(c);
   io.actions = d_actions; io.obs = d_obs; io.reward = d_reward; io.done = d_done; io.term_obs = d_terminal_obs;
   io.events = d_events;
-  return launch_step<false>(c, io, (cudaStream_t)stream);
+  return launch_step(c, io, (cudaStream_t)stream);
 }
 
 int tb_rollout(tb_ctx *c, int action_mode, int k_steps, float *d_obs, float *d_reward_sum, int32_t *d_done_count, void *stream) {
@@ -733,7 +853,9 @@ int tb_rollout(tb_ctx *c, int action_mode, int k_steps, float *d_obs, float *d_r
   if (k_steps < 0) return fail("%s", "tb_rollout: k_steps must be >= 0");
   StepIO io = make_io(c);
   io.k_steps = k_steps; io.obs = d_obs; io.reward_sum = d_reward_sum; io.done_count = d_done_count;
-  return launch_step<true>(c, io, (cudaStream_t)stream);
+  DISPATCH(rollout_kernel, grid_for(io.n, kBlock), kBlock, (cudaStream_t)stream, io);
+  CU(cudaGetLastError());
+  return 0;
 }
 
 int tb_get_state(tb_ctx *c, double *d_state, void *stream) {

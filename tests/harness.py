@@ -45,16 +45,22 @@ class ParityReport:
                    self.event_mismatch_hard, self.event_mismatch_near, self.dropped))
 
 
-def run_parity(batch, oracle, steps, action_fn, band=0.0, check_state_every=0, obs0=None):
+def run_parity(batch, oracle, steps, action_fn, band=0.0, check_state_every=0, obs0=None, event_mask=0xff,
+               drop_after=None):
     """Step `batch` (TennisBatch) and `oracle` (OracleEnv) with the same actions = action_fn(t, last_oracle_obs).
     band: oracle margin (metres) under which a discrete mismatch counts as a near-threshold flip; such envs are
-    dropped from the comparison from then on (their trajectories legitimately diverge)."""
+    dropped from the comparison from then on (their trajectories legitimately diverge).
+    event_mask: event bits that are compared.  drop_after: {event bit: k} - an env leaves the comparison for good
+    once the oracle has reported that bit on more than k steps (float32 only: the contact model turns metres of
+    penetration into m/s with a factor 1/dt = 240, so every impact amplifies float32 position rounding; after a
+    racket impact or a couple of floor bounces no useful pose tolerance is left)."""
     import torch
 
     n = batch.num_envs
     rep = ParityReport()
     valid = np.ones(n, bool)
     last_obs = obs0
+    seen = {bit: np.zeros(n, np.int64) for bit in (drop_after or {})}
     for t in range(steps):
         a = action_fn(t, last_obs).astype(np.float32)
         g_obs, g_rew, g_done, g_term, g_ev = batch.step(torch.from_numpy(a).to(batch.device))
@@ -62,7 +68,7 @@ def run_parity(batch, oracle, steps, action_fn, band=0.0, check_state_every=0, o
         o = oracle.step(a, want_margin=True)
         last_obs = o["obs"]
         g_obs, g_rew, g_done, g_term, g_ev = (x.cpu().numpy() for x in (g_obs, g_rew, g_done, g_term, g_ev))
-        disc = (g_done != o["done"]) | (g_ev != o["events"])
+        disc = (g_done != o["done"]) | ((g_ev & event_mask) != (o["events"] & event_mask))
         # an env whose oracle margin |quantity - threshold| fell inside the band this step took a discrete
         # decision the float32 path may legitimately take one substep apart: it is "near", counted, and left
         # out of the value comparison from here on (band = 0 for the float64 path: nothing is excused)
@@ -70,6 +76,9 @@ def run_parity(batch, oracle, steps, action_fn, band=0.0, check_state_every=0, o
         rep.event_mismatch_near += int((near & disc).sum())
         rep.event_mismatch_hard += int((valid & ~near & disc).sum())
         valid &= ~(near | disc)
+        for bit, k in (drop_after or {}).items():
+            seen[bit] += (o["events"] & bit) != 0
+            valid &= seen[bit] <= k
         rep.dropped = int((~valid).sum())
         v = valid
         rep.compared += int(v.sum())
