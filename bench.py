@@ -8,9 +8,13 @@
 A "step" is one pass of the hot path over the batch: one agent-visible env step for every env of the batch
 (SwingRacket's 26th step, which fast-forwards up to 776 physics substeps, counts once).  Workload = config 5's
 per-GPU slice: 1 048 576 SwingRacket-v0 envs per GPU, uniform random actions, initial states from the env's own
-reset ranges.  Episode phases are staggered per 128-env group (group g starts g mod 26 steps late) so every
-launch carries the same mix of 25/26 control steps and 1/26 fast-forward steps and any K measures whole-episode
-throughput.
+reset ranges.  Every SwingRacket episode is exactly 26 agent steps (25 one-substep control steps + the fast-forward
+step), so the timed region must cover whole episodes to weight the two kinds of step correctly:
+  --steps a multiple of 26 (default 104): lock-step episodes (all envs reset together, as a VecEnv starts), the
+      timed region starts on an episode boundary and spans K/26 whole episodes;
+  any other --steps: episode phases are staggered per 128-env group (group g starts g mod 26 steps late) so that
+      every launch carries the same 25:1 mix and any K is representative (slower: each launch then waits for its own
+      800-substep time-out flights).
 """
 import argparse
 import json
@@ -47,7 +51,9 @@ def parse():
     ap.add_argument("--precision", default="f64", choices=["f32", "f64"])
     ap.add_argument("--e2e-steps", type=int, default=26)
     ap.add_argument("--cpu-sample-envs", type=int, default=16384)
-    ap.add_argument("--no-stagger", action="store_true")
+    ap.add_argument("--stagger", default="auto", choices=["auto", "on", "off"],
+                    help="episode phases: off = lock-step (all envs reset together), on = staggered per 128-env group; "
+                         "auto = off when --steps is a multiple of the 26-step episode, else on (uniform launches)")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     return ap.parse_args()
 
@@ -192,11 +198,13 @@ def run_b200(args, rank, world):
     # action buffers: a ring of pre-drawn U(-1,1) batches resident in HBM (synthetic actions = action_space.sample())
     ring = [torch.empty((n, batch.act_dim), dtype=torch.float32, device=dev).uniform_(-1, 1) for _ in range(4)]
     pre_launch = 0
-    if args.no_stagger:
+    stagger = args.stagger == "on" or (args.stagger == "auto" and args.steps % EPISODE_STEPS != 0 and args.env == "SwingRacket-v0")
+    if not stagger:
         batch.reset()
     else:
         pre_launch = stagger_phases(batch, torch)
-    for w in range(args.warmup):
+    align = 0 if stagger or args.env != "SwingRacket-v0" else (-args.warmup) % EPISODE_STEPS
+    for w in range(args.warmup + align):  # `align` extra untimed steps put the timed region on an episode boundary
         batch.step(ring[w % len(ring)])
     if dist is not None:
         dist.all_reduce(stats)  # warm the NCCL communicator
@@ -234,7 +242,7 @@ def run_b200(args, rank, world):
     rng = np.random.default_rng(rank)
     host_actions = rng.uniform(-1, 1, (n, batch.act_dim)).astype(np.float32)
     np.copyto(hb["actions"], host_actions)
-    for _ in range(3):
+    for _ in range(3 if stagger or args.env != "SwingRacket-v0" else EPISODE_STEPS):  # warm-up, whole episode in lock-step
         batch.step_host(want_terminal=False, want_events=False)
     barrier()
     t0 = time.perf_counter()
@@ -265,7 +273,8 @@ def run_b200(args, rank, world):
             "config": {"workload": f"{args.env} batched {n} envs per GPU (config 5 slice), uniform random actions, "
                                    f"reset ranges of the env, auto-reset",
                        "envs_per_gpu": n, "total_envs": total_envs,
-                       "phase_stagger": "none (lock-step episodes)" if args.no_stagger else f"per {GROUP}-env group, g mod {EPISODE_STEPS}",
+                       "phase_stagger": f"per {GROUP}-env group, g mod {EPISODE_STEPS}" if stagger else "none (lock-step episodes, timed region = whole episodes)",
+                       "alignment_steps": align,
                        "l2_policy": "working set per launch %.0f MB > 126 MB L2 (inputs larger than L2)" % (n * algo / 1e6),
                        "parallelism": f"env-sharded x{world}, no data-path collective; int64[10] stats all-reduce per {EPISODE_STEPS} steps"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
