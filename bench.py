@@ -237,6 +237,14 @@ def run_b200(args, rank, world):
         dist.all_reduce(stats)
         st = stats.cpu().numpy()
 
+    # ---- per-kernel device times over one more episode (events inside the library, stream synchronised per step:
+    #      outside the timed region by construction)
+    batch.set_kernel_timing(True)
+    for k in range(EPISODE_STEPS if args.env == "SwingRacket-v0" else 8):
+        batch.step(ring[k % len(ring)])
+    ms_a, ms_b, nk = batch.kernel_timing()
+    batch.set_kernel_timing(False)
+
     # ---- end to end through the host-buffer entry point (pinned numpy in, pinned numpy out)
     hb = batch.host_buffers()
     rng = np.random.default_rng(rank)
@@ -279,7 +287,13 @@ def run_b200(args, rank, world):
                        "parallelism": f"env-sharded x{world}, no data-path collective; int64[10] stats all-reduce per {EPISODE_STEPS} steps"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_env_step": algo,
-                         "kernel": "tb::step_kernel<%s,%s>" % ("double" if args.precision == "f64" else "float", args.env)},
+                         "scope": "whole env step = step_kernel + ff_kernel, algorithmic bytes of the step / mean step time",
+                         "kernels": {
+                             "step_kernel": {"ms_per_launch": ms_a / max(nk, 1), "achieved_gbs": n * algo / (ms_a / max(nk, 1) * 1e-3) / 1e9,
+                                             "frac": n * algo / (ms_a / max(nk, 1) * 1e-3) / 1e9 / peak, "bound": "hbm",
+                                             "share_of_step_time": ms_a / max(ms_a + ms_b, 1e-9)},
+                             "ff_kernel": {"ms_per_launch": ms_b / max(nk, 1), "bound": "alu/latency (fast-forward substeps; see profiles/)",
+                                           "share_of_step_time": ms_b / max(ms_a + ms_b, 1e-9)}}},
             "e2e": {"value": total_envs * args.e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "steps": args.e2e_steps, "api": "TennisBatch.step_host -> tb_step_host (pinned host buffers)"},
             "gpu_launches": int(launches),

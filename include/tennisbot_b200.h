@@ -147,6 +147,13 @@ int tb_step_host(tb_ctx *ctx, const float *h_actions, float *h_obs, float *h_rew
 /* number of kernels this context has launched (bench.py's gpu_launches) */
 int tb_launch_count(tb_ctx *ctx, int64_t *launches);
 
+/* Per-kernel device timing for roofline reports.  While enabled, every tb_step brackets its two kernels with CUDA
+ * events on the launch stream and synchronises the stream to accumulate their durations (so do not enable it
+ * inside a throughput measurement).  tb_get_kernel_timing returns the accumulated milliseconds of step_kernel and
+ * ff_kernel and the number of steps they cover, and clears the accumulators. */
+int tb_set_kernel_timing(tb_ctx *ctx, int enabled);
+int tb_get_kernel_timing(tb_ctx *ctx, double *ms_step_kernel, double *ms_ff_kernel, int64_t *steps);
+
 #ifdef __cplusplus
 }
 #endif

@@ -140,6 +140,15 @@ class TennisBatch:
         _lib.check(self.lib.tb_launch_count(self.h, C.byref(v)))
         return v.value
 
+    def set_kernel_timing(self, enabled):
+        _lib.check(self.lib.tb_set_kernel_timing(self.h, int(bool(enabled))))
+
+    def kernel_timing(self):
+        """(ms in step_kernel, ms in ff_kernel, steps covered) accumulated since the last call."""
+        a, b, n = C.c_double(), C.c_double(), C.c_int64()
+        _lib.check(self.lib.tb_get_kernel_timing(self.h, C.byref(a), C.byref(b), C.byref(n)))
+        return a.value, b.value, n.value
+
     # ------------------------------------------------------------------ host-buffer API (pinned numpy in/out)
     def host_buffers(self):
         """Pinned host arrays reused by reset_host/step_host (views of torch pinned tensors)."""

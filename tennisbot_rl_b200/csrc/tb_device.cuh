@@ -79,6 +79,11 @@ template <typename T> struct Scene {
   T racket_box[3];  // outline bounding box in the COM frame: max |y|, min z, max z (grown by 1e-6: reject only)
   T racket_obb[3];  // the same box, exact: TB_EV_RACKET_LOW
   T racket_obb_radius;  // distance of its farthest corner from the COM (pre-check of the same test)
+  // derived thresholds of the fast-forward fast path (all conservative, see ff_try_fast)
+  T ff_z_clear;         // ball centre above this height cannot touch floor, net or goal this step
+  T ff_low_clear;       // racket COM above this height cannot set TB_EV_RACKET_LOW
+  T ff_reach_racket2;   // squared radius of the hull's bounding sphere grown by ball radius + margin + threshold
+  T ff_reach_hull;      // ball radius + hull margin + contact threshold
   Prism<T, kRacketEdges> racket;
   Prism<T, kGoalEdges> goal;
 };
@@ -459,6 +464,31 @@ __device__ __forceinline__ float fast_rsqrt(float x) {
 }
 __device__ __forceinline__ double fast_rsqrt(double x) { return ::rsqrt(x); }
 
+// q <- exp(omega dt) q by the exponential map, then normalise (btMultiBody::stepPositionsMultiDof [R]).
+template <typename T> __device__ __forceinline__ void integrate_quat(const Scene<T> &sc, St<T> &s) {
+  const T dt = sc.dt;
+  if (s.rw[0] != 0 || s.rw[1] != 0 || s.rw[2] != 0) {
+    T a2 = dot3(s.rw, s.rw), k, sn, cw;
+    if (a2 < (T)1e-6) {  // |omega| < 0.001: Taylor form of sin(x)/x, as Bullet does
+      T ang = M<T>::sqrt(a2);
+      k = (T)0.5 * dt - dt * dt * dt * (T)0.020833333333 * a2;
+      sincos_small((T)0.5 * ang * dt, &sn, &cw);
+    } else {
+      T inv_ang = fast_rsqrt(a2), ang = a2 * inv_ang;
+      sincos_small((T)0.5 * ang * dt, &sn, &cw);
+      k = sn * inv_ang;
+    }
+    T ax = s.rw[0] * k, ay = s.rw[1] * k, az = s.rw[2] * k;
+    const T *q = s.rq;
+    T x = cw * q[0] + ax * q[3] + ay * q[2] - az * q[1];
+    T y = cw * q[1] - ax * q[2] + ay * q[3] + az * q[0];
+    T z = cw * q[2] + ax * q[1] - ay * q[0] + az * q[3];
+    T w = cw * q[3] - ax * q[0] - ay * q[1] - az * q[2];
+    T inv = fast_rsqrt(x * x + y * y + z * z + w * w);
+    s.rq[0] = x * inv; s.rq[1] = y * inv; s.rq[2] = z * inv; s.rq[3] = w * inv;
+  }
+}
+
 // One stepSimulation(): detect at the start-of-step poses, integrate velocities with Bullet's multibody
 // damping, solve contacts, integrate poses.  Returns the TB_EV_* contact bits getContactPoints would report.
 // known_bits: event bits already latched for this env step (lets the sticky RACKET_LOW diagnostic skip its loop).
@@ -580,27 +610,75 @@ __device__ __forceinline__ int physics_step(const Scene<T> &sc, St<T> &s, const 
     s.bp[i] += dt * s.bv[i];
     s.rp[i] += dt * s.rv[i];
   }
-  if (s.rw[0] != 0 || s.rw[1] != 0 || s.rw[2] != 0) {
-    T a2 = dot3(s.rw, s.rw), k, sn, cw;
-    if (a2 < (T)1e-6) {  // |omega| < 0.001: Taylor form of sin(x)/x, as Bullet does
-      T ang = M<T>::sqrt(a2);
-      k = (T)0.5 * dt - dt * dt * dt * (T)0.020833333333 * a2;
-      sincos_small((T)0.5 * ang * dt, &sn, &cw);
-    } else {
-      T inv_ang = fast_rsqrt(a2), ang = a2 * inv_ang;
-      sincos_small((T)0.5 * ang * dt, &sn, &cw);
-      k = sn * inv_ang;
-    }
-    T ax = s.rw[0] * k, ay = s.rw[1] * k, az = s.rw[2] * k;
-    const T *q = s.rq;
-    T x = cw * q[0] + ax * q[3] + ay * q[2] - az * q[1];
-    T y = cw * q[1] - ax * q[2] + ay * q[3] + az * q[0];
-    T z = cw * q[2] + ax * q[1] - ay * q[0] + az * q[3];
-    T w = cw * q[3] - ax * q[0] - ay * q[1] - az * q[2];
-    T inv = fast_rsqrt(x * x + y * y + z * z + w * w);
-    s.rq[0] = x * inv; s.rq[1] = y * inv; s.rq[2] = z * inv; s.rq[3] = w * inv;
-  }
+  integrate_quat(sc, s);
   return bits;
+}
+
+// Fast path of the fast-forward: one substep of an env that provably touches nothing this step (ball clear of
+// floor / net / goal and outside the racket's slab or outline box, racket clear of the floor-flag test, hack force
+// phase, no time-out).  Straight-line code, no out-of-line call.  Returns false without touching the state when the
+// env does not qualify; the caller then runs the general substep.  Every test is the conservative side of the
+// corresponding broad-phase test of physics_step, so both paths take identical decisions; path selection depends on
+// the lane's own state only, which keeps trajectories independent of the neighbouring lanes.
+template <typename T>
+__device__ __forceinline__ bool ff_try_fast(const Scene<T> &sc, St<T> &s, int phase, int events) {
+  if (phase != 2 || s.step >= 800) return false;
+  if (!(s.bp[2] > sc.ff_z_clear)) return false;
+  if (!((events & TB_EV_RACKET_LOW) || s.rp[2] > sc.ff_low_clear)) return false;
+  T R[9];
+  quat_to_mat(s.rq, R);
+  {
+    T rel[3] = {s.bp[0] - s.rp[0], s.bp[1] - s.rp[1], s.bp[2] - s.rp[2]};
+    if (dot3(rel, rel) <= sc.ff_reach_racket2) {
+      T pl[3];
+      matT_vec(R, rel, pl);
+      const T reach = sc.ff_reach_hull;
+      if (!(M<T>::abs(pl[0]) - sc.racket.half_thick > reach || M<T>::abs(pl[1]) - sc.racket_box[0] > reach ||
+            pl[2] - sc.racket_box[2] > reach || sc.racket_box[1] - pl[2] > reach))
+        return false;
+    }
+  }
+  const T dt = sc.dt, vmax = sc.max_coord_vel;
+  // the force the reference queued from the previous substep's post-step pose (swingracket_env.py:135-141)
+  T F[3] = {-50 * (s.rp[0] - s.aux[0]), -2 * (s.rp[1] - s.aux[1]), -2 * (s.rp[2] - s.aux[2] - 4)};
+  {
+    T kv = sc.lin_damping * (1 + norm3_fast(s.bv));
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      T g = i == 2 ? sc.gravity_z : (T)0;
+      s.bv[i] = clampv(s.bv[i] + dt * (g - s.bv[i] * kv), -vmax, vmax);
+    }
+    T kw = sc.ang_damping * (1 + norm3_fast(s.bw));  // exact zero stays exact zero: no branch needed
+#pragma unroll
+    for (int i = 0; i < 3; ++i) s.bw[i] = clampv(s.bw[i] + dt * (-s.bw[i] * kw), -vmax, vmax);
+  }
+  {
+    T kv = sc.lin_damping * (1 + norm3_fast(s.rv));
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      T g = i == 2 ? sc.gravity_z : (T)0;
+      s.rv[i] = clampv(s.rv[i] + dt * (F[i] * sc.racket_inv_m + g - s.rv[i] * kv), -vmax, vmax);
+    }
+    T wl[3], iw[3], gy[3], al[3], aw[3];
+    matT_vec(R, s.rw, wl);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) iw[i] = sc.racket_i[i] * wl[i];
+    cross3(wl, iw, gy);
+    T kw = sc.ang_damping * (1 + norm3_fast(wl));
+#pragma unroll
+    for (int i = 0; i < 3; ++i) al[i] = ((T)0 - sc.gyro * gy[i]) * sc.racket_inv_i[i] - wl[i] * kw;
+    mat_vec(R, al, aw);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) s.rw[i] = clampv(s.rw[i] + dt * aw[i], -vmax, vmax);
+  }
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    s.bp[i] += dt * s.bv[i];
+    s.rp[i] += dt * s.rv[i];
+  }
+  integrate_quat(sc, s);
+  ++s.step;
+  return true;
 }
 
 // ------------------------------------------------------------------------------------------------ episodes

@@ -586,7 +586,15 @@ template <typename T> static void build_scene(const Params &p, Scene<T> &sc) {
     sc.racket_box[0] = (T)(ay * (1 + 1e-6)); sc.racket_box[1] = (T)(zlo - 1e-6); sc.racket_box[2] = (T)(zhi + 1e-6);
     sc.racket_obb[0] = (T)ay; sc.racket_obb[1] = (T)zlo; sc.racket_obb[2] = (T)zhi;
     double zm = std::fmax(std::fabs(zlo), std::fabs(zhi));
+    double reach_hull = TB_BALL_RADIUS + p.hull_margin + p.contact_threshold, reach_box = TB_BALL_RADIUS + p.box_margin + p.contact_threshold;
+    double top = std::fmax(std::fmax(TB_FLOOR_HZ, TB_NET_HZ), TB_GOAL_HALF_Z);
+    // thresholds of the fast path, each rounded to the safe side so float and double kernels stay conservative
+    sc.ff_z_clear = (T)((top + std::fmax(reach_hull, reach_box)) * (1 + 1e-6));
+    sc.ff_reach_hull = (T)(reach_hull * (1 + 1e-6));
     sc.racket_obb_radius = (T)(std::sqrt(h.racket_half_x * h.racket_half_x + ay * ay + zm * zm) * (1 + 1e-6));
+    sc.ff_low_clear = (T)(((double)sc.racket_obb_radius + p.hull_margin + TB_FLOOR_HZ + p.contact_threshold) * (1 + 1e-6));
+    double rr = (double)sc.racket.bound_radius + reach_hull;
+    sc.ff_reach_racket2 = (T)(rr * rr * (1 + 1e-5));
   }
   build_prism<T, kGoalEdges>(sc.goal, h.goal_v, TB_GOAL_HALF_Z);
 }
@@ -625,7 +633,11 @@ struct tb_ctx {
   int *queue = nullptr;                      // fast-forward work queue (env indices), num_envs entries
   unsigned long long *queue_ctrs = nullptr;  // two (appended, claimed) counter pairs used by alternate steps
   int parity = 0;
-  unsigned ff_grid = 0;                      // persistent grid of ff_kernel  // persistent grid of step_kernel<.., ROLLOUT=false/true>
+  unsigned ff_grid = 0;                      // persistent grid of ff_kernel
+  bool timing = false;                       // tb_set_kernel_timing
+  cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+  double ms_step = 0, ms_ff = 0;
+  int64_t timed_steps = 0;  // persistent grid of step_kernel<.., ROLLOUT=false/true>
 };
 
 struct DeviceGuard {
@@ -683,6 +695,7 @@ static int launch_step(tb_ctx *c, StepIO &io, cudaStream_t stream) {
   c->parity ^= 1;
   const unsigned grid = grid_for(io.n, kBlock);
   const bool swing = c->cfg.env_kind == TB_ENV_SWING;
+  if (c->timing) CU(cudaEventRecord(c->ev[0], stream));
   if (c->cfg.precision == TB_F64) {
     if (swing) step_kernel<double, TB_ENV_SWING><<<grid, kBlock, 0, stream>>>(c->sc64, io);
     else step_kernel<double, TB_ENV_HIT><<<grid, kBlock, 0, stream>>>(c->sc64, io);
@@ -692,6 +705,7 @@ static int launch_step(tb_ctx *c, StepIO &io, cudaStream_t stream) {
   }
   c->launches++;
   CU(cudaGetLastError());
+  if (c->timing) CU(cudaEventRecord(c->ev[1], stream));
   if (swing) {
     if (c->cfg.precision == TB_F64) {
       if (!c->ff_grid && ff_grid_size<double>(c, &c->ff_grid)) return 1;
@@ -702,6 +716,14 @@ static int launch_step(tb_ctx *c, StepIO &io, cudaStream_t stream) {
     }
     c->launches++;
     CU(cudaGetLastError());
+  }
+  if (c->timing) {
+    float a = 0, b = 0;
+    CU(cudaEventRecord(c->ev[2], stream));
+    CU(cudaEventSynchronize(c->ev[2]));
+    CU(cudaEventElapsedTime(&a, c->ev[0], c->ev[1]));
+    CU(cudaEventElapsedTime(&b, c->ev[1], c->ev[2]));
+    c->ms_step += a; c->ms_ff += b; c->timed_steps++;
   }
   return 0;
 }
@@ -801,6 +823,7 @@ int tb_destroy(tb_ctx *c) {
   if (!c) return 0;
   DeviceGuard g(c->cfg.device);
   if (c->own_stream) { cudaStreamSynchronize(c->own_stream); cudaStreamDestroy(c->own_stream); }
+  for (int i = 0; i < 3; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
   cudaFree(c->state); cudaFree(c->stats); cudaFree(c->queue_ctrs); cudaFree(c->queue);
   cudaFree(c->d_actions); cudaFree(c->d_obs); cudaFree(c->d_reward); cudaFree(c->d_term);
   cudaFree(c->d_done); cudaFree(c->d_events); cudaFree(c->d_mask);
@@ -936,6 +959,20 @@ int tb_step_host(tb_ctx *c, const float *h_actions, float *h_obs, float *h_rewar
   if (h_terminal_obs) CU(cudaMemcpyAsync(h_terminal_obs, c->d_term, n * od * sizeof(float), cudaMemcpyDeviceToHost, s));
   if (h_events) CU(cudaMemcpyAsync(h_events, c->d_events, n, cudaMemcpyDeviceToHost, s));
   CU(cudaStreamSynchronize(s));
+  return 0;
+}
+
+int tb_set_kernel_timing(tb_ctx *c, int enabled) {
+  GUARD(c);
+  if (enabled && !c->ev[0])
+    for (int i = 0; i < 3; ++i) CU(cudaEventCreate(&c->ev[i]));
+  c->timing = enabled != 0;
+  return 0;
+}
+int tb_get_kernel_timing(tb_ctx *c, double *ms_step_kernel, double *ms_ff_kernel, int64_t *steps) {
+  if (!c || !ms_step_kernel || !ms_ff_kernel || !steps) return fail("%s", "tb_get_kernel_timing: bad argument");
+  *ms_step_kernel = c->ms_step; *ms_ff_kernel = c->ms_ff; *steps = c->timed_steps;
+  c->ms_step = c->ms_ff = 0; c->timed_steps = 0;
   return 0;
 }
 
