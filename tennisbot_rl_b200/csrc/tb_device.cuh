@@ -19,6 +19,9 @@
 
 namespace tb {
 
+// rare-path hint: lets the compiler lay the cold block out of the substep loop's straight line (I-cache)
+#define TB_UNLIKELY(x) __builtin_expect(!!(x), 0)
+
 // ------------------------------------------------------------------------------------------------ math shims
 template <typename T> struct M;
 template <> struct M<float> {
@@ -45,6 +48,25 @@ template <> struct M<double> {
 
 __device__ __forceinline__ float clampv(float x, float lo, float hi) { return fminf(fmaxf(x, lo), hi); }
 __device__ __forceinline__ double clampv(double x, double lo, double hi) { return fmin(fmax(x, lo), hi); }
+// |x| >= vmax, decided on the exponent/high mantissa word alone (an integer compare; double min/max are multi-
+// instruction sequences on sm_100).  `thr` is the high word of vmax; for double the test may fire a little below
+// vmax, which only sends the caller into the exact clamp for nothing.
+__device__ __forceinline__ bool near_limit(float x, unsigned thr) { return (__float_as_uint(x) & 0x7fffffffu) >= thr; }
+__device__ __forceinline__ bool near_limit(double x, unsigned thr) { return ((unsigned)__double2hiint(x) & 0x7fffffffu) >= thr; }
+// Bullet clamps every velocity coordinate to +-max_coord_vel whenever it writes one (btMultiBody::applyDeltaVee).
+// The bound is never reached in these envs, so test all twelve coordinates with integer compares and clamp out of line.
+template <typename T> __device__ __forceinline__ void clamp_velocities(T *bv, T *bw, T *rv, T *rw, T vmax, unsigned thr) {
+  bool over = false;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) over = over | near_limit(bv[i], thr) | near_limit(bw[i], thr) | near_limit(rv[i], thr) | near_limit(rw[i], thr);
+  if (TB_UNLIKELY(over)) {
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      bv[i] = clampv(bv[i], -vmax, vmax); bw[i] = clampv(bw[i], -vmax, vmax);
+      rv[i] = clampv(rv[i], -vmax, vmax); rw[i] = clampv(rw[i], -vmax, vmax);
+    }
+  }
+}
 template <typename T> __device__ __forceinline__ T dot3(const T *a, const T *b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
 template <typename T> __device__ __forceinline__ void cross3(const T *a, const T *b, T *o) {
   o[0] = a[1] * b[2] - a[2] * b[1];
@@ -71,6 +93,7 @@ template <typename T> struct Scene {
   T rest_racket, rest_court, rest_goal, mu_racket, mu_court, mu_goal;
   T erp, slop, rest_vel_threshold, solver_residual, contact_threshold, hull_margin, box_margin, gyro;
   int iters;
+  unsigned vmax_hi;  // high 32 bits of max_coord_vel in T's format (clamp_velocities)
   T ball_r, ball_inv_m, ball_inv_i, racket_inv_m;
   T racket_i[3], racket_inv_i[3];
   T com_z;
@@ -79,11 +102,6 @@ template <typename T> struct Scene {
   T racket_box[3];  // outline bounding box in the COM frame: max |y|, min z, max z (grown by 1e-6: reject only)
   T racket_obb[3];  // the same box, exact: TB_EV_RACKET_LOW
   T racket_obb_radius;  // distance of its farthest corner from the COM (pre-check of the same test)
-  // derived thresholds of the fast-forward fast path (all conservative, see ff_try_fast)
-  T ff_z_clear;         // ball centre above this height cannot touch floor, net or goal this step
-  T ff_low_clear;       // racket COM above this height cannot set TB_EV_RACKET_LOW
-  T ff_reach_racket2;   // squared radius of the hull's bounding sphere grown by ball radius + margin + threshold
-  T ff_reach_hull;      // ball radius + hull margin + contact threshold
   Prism<T, kRacketEdges> racket;
   Prism<T, kGoalEdges> goal;
 };
@@ -469,7 +487,7 @@ template <typename T> __device__ __forceinline__ void integrate_quat(const Scene
   const T dt = sc.dt;
   if (s.rw[0] != 0 || s.rw[1] != 0 || s.rw[2] != 0) {
     T a2 = dot3(s.rw, s.rw), k, sn, cw;
-    if (a2 < (T)1e-6) {  // |omega| < 0.001: Taylor form of sin(x)/x, as Bullet does
+    if (TB_UNLIKELY(a2 < (T)1e-6)) {  // |omega| < 0.001: Taylor form of sin(x)/x, as Bullet does
       T ang = M<T>::sqrt(a2);
       k = (T)0.5 * dt - dt * dt * dt * (T)0.020833333333 * a2;
       sincos_small((T)0.5 * ang * dt, &sn, &cw);
@@ -532,7 +550,7 @@ __device__ __forceinline__ int physics_step(const Scene<T> &sc, St<T> &s, const 
       if (low <= sc.floor_h[2] + thr && M<T>::abs(s.rp[0]) <= sc.floor_h[0] + 1 && M<T>::abs(s.rp[1]) <= sc.floor_h[1] + 1)
         bits |= TB_EV_RACKET_LOW;
     }
-    if (need) {
+    if (TB_UNLIKELY(need)) {
       NarrowIn<T> in;
 #pragma unroll
       for (int i = 0; i < 3; ++i) { in.rp[i] = s.rp[i]; in.bp[i] = s.bp[i]; }
@@ -552,12 +570,12 @@ __device__ __forceinline__ int physics_step(const Scene<T> &sc, St<T> &s, const 
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
       T g = i == 2 ? sc.gravity_z : (T)0;
-      s.bv[i] = clampv(s.bv[i] + dt * (f_ball[i] * sc.ball_inv_m + g - s.bv[i] * kv), -vmax, vmax);
+      s.bv[i] = s.bv[i] + dt * (f_ball[i] * sc.ball_inv_m + g - s.bv[i] * kv);
     }
     if (s.bw[0] != 0 || s.bw[1] != 0 || s.bw[2] != 0) {  // the ball spins only after a frictional contact
       T kw = sc.ang_damping * (1 + norm3_fast(s.bw));
 #pragma unroll
-      for (int i = 0; i < 3; ++i) s.bw[i] = clampv(s.bw[i] + dt * (-s.bw[i] * kw), -vmax, vmax);
+      for (int i = 0; i < 3; ++i) s.bw[i] = s.bw[i] + dt * (-s.bw[i] * kw);
     }
   }
   T R[9];
@@ -568,7 +586,7 @@ __device__ __forceinline__ int physics_step(const Scene<T> &sc, St<T> &s, const 
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
       T g = i == 2 ? sc.gravity_z : (T)0;
-      s.rv[i] = clampv(s.rv[i] + dt * (f_racket[i] * sc.racket_inv_m + g - s.rv[i] * kv), -vmax, vmax);
+      s.rv[i] = s.rv[i] + dt * (f_racket[i] * sc.racket_inv_m + g - s.rv[i] * kv);
     }
     if (rotating) quat_to_mat(s.rq, R);
     if (rotating) {  // the hit env's racket never rotates: no torque is ever applied to it
@@ -583,12 +601,13 @@ __device__ __forceinline__ int physics_step(const Scene<T> &sc, St<T> &s, const 
       for (int i = 0; i < 3; ++i) al[i] = (tl[i] - sc.gyro * gy[i]) * sc.racket_inv_i[i] - wl[i] * kw;
       mat_vec(R, al, aw);
 #pragma unroll
-      for (int i = 0; i < 3; ++i) s.rw[i] = clampv(s.rw[i] + dt * aw[i], -vmax, vmax);
+      for (int i = 0; i < 3; ++i) s.rw[i] = s.rw[i] + dt * aw[i];
     }
   }
+  clamp_velocities(s.bv, s.bw, s.rv, s.rw, vmax, sc.vmax_hi);
 
   // ---- (3) contact solve
-  if (nc > 0) {
+  if (TB_UNLIKELY(nc > 0)) {
     SolveIO<T> io;
 #pragma unroll
     for (int i = 0; i < 3; ++i) { io.bv[i] = s.bv[i]; io.bw[i] = s.bw[i]; io.rv[i] = s.rv[i]; io.rw[i] = s.rw[i]; }
@@ -597,11 +616,9 @@ __device__ __forceinline__ int physics_step(const Scene<T> &sc, St<T> &s, const 
     solve_contacts(sc, &cs, nc, &io);
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
-      s.bv[i] = clampv(s.bv[i] + io.dvb[i], -vmax, vmax);
-      s.bw[i] = clampv(s.bw[i] + io.dwb[i], -vmax, vmax);
-      s.rv[i] = clampv(s.rv[i] + io.dva[i], -vmax, vmax);
-      s.rw[i] = clampv(s.rw[i] + io.dwa[i], -vmax, vmax);
+      s.bv[i] += io.dvb[i]; s.bw[i] += io.dwb[i]; s.rv[i] += io.dva[i]; s.rw[i] += io.dwa[i];
     }
+    clamp_velocities(s.bv, s.bw, s.rv, s.rw, vmax, sc.vmax_hi);
   }
 
   // ---- (4) poses: x += dt v ; q <- exp(omega dt) q
@@ -612,73 +629,6 @@ __device__ __forceinline__ int physics_step(const Scene<T> &sc, St<T> &s, const 
   }
   integrate_quat(sc, s);
   return bits;
-}
-
-// Fast path of the fast-forward: one substep of an env that provably touches nothing this step (ball clear of
-// floor / net / goal and outside the racket's slab or outline box, racket clear of the floor-flag test, hack force
-// phase, no time-out).  Straight-line code, no out-of-line call.  Returns false without touching the state when the
-// env does not qualify; the caller then runs the general substep.  Every test is the conservative side of the
-// corresponding broad-phase test of physics_step, so both paths take identical decisions; path selection depends on
-// the lane's own state only, which keeps trajectories independent of the neighbouring lanes.
-template <typename T>
-__device__ __forceinline__ bool ff_try_fast(const Scene<T> &sc, St<T> &s, int phase, int events) {
-  if (phase != 2 || s.step >= 800) return false;
-  if (!(s.bp[2] > sc.ff_z_clear)) return false;
-  if (!((events & TB_EV_RACKET_LOW) || s.rp[2] > sc.ff_low_clear)) return false;
-  T R[9];
-  quat_to_mat(s.rq, R);
-  {
-    T rel[3] = {s.bp[0] - s.rp[0], s.bp[1] - s.rp[1], s.bp[2] - s.rp[2]};
-    if (dot3(rel, rel) <= sc.ff_reach_racket2) {
-      T pl[3];
-      matT_vec(R, rel, pl);
-      const T reach = sc.ff_reach_hull;
-      if (!(M<T>::abs(pl[0]) - sc.racket.half_thick > reach || M<T>::abs(pl[1]) - sc.racket_box[0] > reach ||
-            pl[2] - sc.racket_box[2] > reach || sc.racket_box[1] - pl[2] > reach))
-        return false;
-    }
-  }
-  const T dt = sc.dt, vmax = sc.max_coord_vel;
-  // the force the reference queued from the previous substep's post-step pose (swingracket_env.py:135-141)
-  T F[3] = {-50 * (s.rp[0] - s.aux[0]), -2 * (s.rp[1] - s.aux[1]), -2 * (s.rp[2] - s.aux[2] - 4)};
-  {
-    T kv = sc.lin_damping * (1 + norm3_fast(s.bv));
-#pragma unroll
-    for (int i = 0; i < 3; ++i) {
-      T g = i == 2 ? sc.gravity_z : (T)0;
-      s.bv[i] = clampv(s.bv[i] + dt * (g - s.bv[i] * kv), -vmax, vmax);
-    }
-    T kw = sc.ang_damping * (1 + norm3_fast(s.bw));  // exact zero stays exact zero: no branch needed
-#pragma unroll
-    for (int i = 0; i < 3; ++i) s.bw[i] = clampv(s.bw[i] + dt * (-s.bw[i] * kw), -vmax, vmax);
-  }
-  {
-    T kv = sc.lin_damping * (1 + norm3_fast(s.rv));
-#pragma unroll
-    for (int i = 0; i < 3; ++i) {
-      T g = i == 2 ? sc.gravity_z : (T)0;
-      s.rv[i] = clampv(s.rv[i] + dt * (F[i] * sc.racket_inv_m + g - s.rv[i] * kv), -vmax, vmax);
-    }
-    T wl[3], iw[3], gy[3], al[3], aw[3];
-    matT_vec(R, s.rw, wl);
-#pragma unroll
-    for (int i = 0; i < 3; ++i) iw[i] = sc.racket_i[i] * wl[i];
-    cross3(wl, iw, gy);
-    T kw = sc.ang_damping * (1 + norm3_fast(wl));
-#pragma unroll
-    for (int i = 0; i < 3; ++i) al[i] = ((T)0 - sc.gyro * gy[i]) * sc.racket_inv_i[i] - wl[i] * kw;
-    mat_vec(R, al, aw);
-#pragma unroll
-    for (int i = 0; i < 3; ++i) s.rw[i] = clampv(s.rw[i] + dt * aw[i], -vmax, vmax);
-  }
-#pragma unroll
-  for (int i = 0; i < 3; ++i) {
-    s.bp[i] += dt * s.bv[i];
-    s.rp[i] += dt * s.rv[i];
-  }
-  integrate_quat(sc, s);
-  ++s.step;
-  return true;
 }
 
 // ------------------------------------------------------------------------------------------------ episodes

@@ -95,10 +95,10 @@ struct StepIO {
   uint8_t *done, *events;
   int32_t *done_count;
   unsigned long long *stats;
-  int *queue;                        // env indices waiting for ff_kernel
-  unsigned long long *queue_ctr;     // [0] entries appended by this step's step_kernel
-  unsigned long long *queue_head;    // [1] entries claimed by ff_kernel lanes
-  unsigned long long *queue_ctr_next;  // the pair the NEXT step uses; step_kernel zeroes it
+  int *queue;                        // env indices waiting for ff_kernel: long flights from the front, short from the back
+  unsigned long long *queue_ctr;     // [0] front entries, [1] back entries appended by this step's step_kernel,
+                                     // [2] entries claimed by ff_kernel lanes
+  unsigned long long *queue_ctr_next;  // the triple the NEXT step uses; step_kernel zeroes it
 };
 
 template <int KIND> struct Dims {
@@ -176,7 +176,7 @@ template <typename T>
 __device__ __forceinline__ void account(WarpStats &ws, bool fin, bool done, int hit, int events, int step, T ret) {
   const unsigned full = 0xffffffffu;
   unsigned fin_mask = __ballot_sync(full, fin);
-  if (!fin_mask) return;
+  if (!TB_UNLIKELY(fin_mask)) return;
   bool dn = fin && done;
   unsigned done_mask = __ballot_sync(full, dn), hit_mask = __ballot_sync(full, fin && hit);
   if (done_mask) {
@@ -235,13 +235,13 @@ __device__ __forceinline__ void finish_api(const Scene<T> &sc, const StepIO &io,
 template <typename T, int KIND>
 __global__ void __launch_bounds__(kBlock) step_kernel(const __grid_constant__ Scene<T> sc, const __grid_constant__ StepIO io) {
   __shared__ unsigned long long sacc[kBlock / 32][TB_NUM_STATS];
-  __shared__ int s_cnt[kBlock / 32];
-  __shared__ unsigned long long s_base;
+  __shared__ int s_cnt[2 * (kBlock / 32)];
+  __shared__ unsigned long long s_base[2];
   const unsigned full = 0xffffffffu;
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   WarpStats ws;
   ws.init(sacc[wib], lane);
-  if (blockIdx.x == 0 && threadIdx.x == 0) { io.queue_ctr_next[0] = 0; io.queue_ctr_next[1] = 0; }
+  if (blockIdx.x == 0 && threadIdx.x == 0) { io.queue_ctr_next[0] = 0; io.queue_ctr_next[1] = 0; io.queue_ctr_next[2] = 0; }
 
   const int64_t me = (int64_t)blockIdx.x * kBlock + threadIdx.x;
   const bool valid = me < io.n;
@@ -262,21 +262,32 @@ __global__ void __launch_bounds__(kBlock) step_kernel(const __grid_constant__ Sc
   account<T>(ws, fin, c.done, c.hit, c.events, s.step, s.ret);
   if (valid && fin) finish_api<T, KIND>(sc, io, me, s, c.reward, c.done, c.events);
 
-  // envs entering the fast-forward: queue them for ff_kernel (only SwingRacket ever does)
+  // envs entering the fast-forward: queue them for ff_kernel (only SwingRacket ever does).  Longest-job-first:
+  // a ball the racket has hit flies for up to 775 more substeps and is queued from the FRONT, a ball still in free
+  // fall lands after ~100 and is queued from the BACK, so the long flights start first and the short ones fill
+  // the tail of ff_kernel.
   bool queued = valid && !fin;
   if (KIND == TB_ENV_SWING) {
-    unsigned qmask = __ballot_sync(full, queued);
-    if (lane == 0) s_cnt[wib] = __popc(qmask);
+    bool is_long = queued && dot3(s.bv, s.bv) > (T)9;
+    unsigned lmask = __ballot_sync(full, is_long), smask = __ballot_sync(full, queued && !is_long);
+    if (lane == 0) { s_cnt[wib] = __popc(lmask); s_cnt[kBlock / 32 + wib] = __popc(smask); }
     __syncthreads();
     if (threadIdx.x == 0) {
-      int tot = 0;
+      int tl = 0, ts = 0;
 #pragma unroll
-      for (int w = 0; w < kBlock / 32; ++w) { int t = s_cnt[w]; s_cnt[w] = tot; tot += t; }
-      s_base = tot ? atomicAdd(io.queue_ctr, (unsigned long long)tot) : 0ULL;
+      for (int w = 0; w < kBlock / 32; ++w) {
+        int a = s_cnt[w], b = s_cnt[kBlock / 32 + w];
+        s_cnt[w] = tl; s_cnt[kBlock / 32 + w] = ts;
+        tl += a; ts += b;
+      }
+      s_base[0] = tl ? atomicAdd(io.queue_ctr, (unsigned long long)tl) : 0ULL;
+      s_base[1] = ts ? atomicAdd(io.queue_ctr + 1, (unsigned long long)ts) : 0ULL;
     }
     __syncthreads();
     if (queued) {
-      io.queue[s_base + s_cnt[wib] + __popc(qmask & ((1u << lane) - 1u))] = (int)me;
+      const unsigned lt = (1u << lane) - 1u;
+      if (is_long) io.queue[s_base[0] + s_cnt[wib] + __popc(lmask & lt)] = (int)me;
+      else io.queue[io.n - 1 - (int64_t)(s_base[1] + s_cnt[kBlock / 32 + wib] + __popc(smask & lt))] = (int)me;
       s.flags = (s.flags & ~(0xff << kFlagEventShift)) | kFlagInFlight | (c.events << kFlagEventShift);
     }
   }
@@ -291,7 +302,8 @@ __global__ void __launch_bounds__(kBlock, MinBlocks<T>::v) ff_kernel(const __gri
   __shared__ unsigned long long sacc[kBlock / 32][TB_NUM_STATS];
   const unsigned full = 0xffffffffu;
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  const long long qn = (long long)*io.queue_ctr;  // number of queued envs (written by step_kernel, same stream)
+  const long long qfront = (long long)io.queue_ctr[0];  // queued envs (written by step_kernel, same stream)
+  const long long qn = qfront + (long long)io.queue_ctr[1];
   if (qn == 0) return;
   WarpStats ws;
   ws.init(sacc[wib], lane);
@@ -306,15 +318,15 @@ __global__ void __launch_bounds__(kBlock, MinBlocks<T>::v) ff_kernel(const __gri
   for (unsigned iter = 0;; ++iter) {
     // ---- idle lanes claim queue entries (one atomic per refill event per warp)
     unsigned idle = __ballot_sync(full, !active);
-    if (idle && !exhausted && (idle == full || __popc(idle) >= kRefillMin || (iter & 15u) == 0)) {
+    if (TB_UNLIKELY(idle && !exhausted && (idle == full || __popc(idle) >= kRefillMin || (iter & 15u) == 0))) {
       int want = __popc(idle);
       long long first = 0;
-      if (lane == 0) first = (long long)atomicAdd(io.queue_head, (unsigned long long)want);
+      if (lane == 0) first = (long long)atomicAdd(io.queue_ctr + 2, (unsigned long long)want);
       first = __shfl_sync(full, first, 0);
       if (first + want >= qn) exhausted = true;
       long long idx = first + __popc(idle & ((1u << lane) - 1u));
       if (!active && idx < qn) {
-        me = io.queue[idx];
+        me = io.queue[idx < qfront ? idx : io.n - 1 - (idx - qfront)];
         load_state(base, io.n, (int64_t)me, s);
         c.phase = 1;
         c.events = (s.flags >> kFlagEventShift) & 0xff;
@@ -334,7 +346,7 @@ __global__ void __launch_bounds__(kBlock, MinBlocks<T>::v) ff_kernel(const __gri
 #endif
     if (fin) s.ret += (T)c.reward;
     account<T>(ws, fin, c.done, 0, c.events, s.step, s.ret);
-    if (fin) {
+    if (TB_UNLIKELY(fin)) {
       s.flags &= kFlagDone;  // drop the in-flight mark and the parked event bits
       finish_api<T, KIND>(sc, io, (int64_t)me, s, c.reward, c.done, c.events);
       store_state(base, io.n, (int64_t)me, s);
@@ -563,6 +575,12 @@ template <typename T> static void build_scene(const Params &p, Scene<T> &sc) {
   sc.solver_residual = (T)p.solver_residual; sc.contact_threshold = (T)p.contact_threshold;
   sc.hull_margin = (T)p.hull_margin; sc.box_margin = (T)p.box_margin; sc.gyro = (T)p.gyro_term;
   sc.iters = (int)p.solver_iterations;
+  {
+    T v = (T)p.max_coord_vel;
+    unsigned long long bits = 0;
+    std::memcpy(&bits, &v, sizeof v);
+    sc.vmax_hi = sizeof(T) == 8 ? (unsigned)(bits >> 32) : (unsigned)bits;
+  }
   sc.ball_r = (T)TB_BALL_RADIUS;
   sc.ball_inv_m = (T)(1.0 / TB_BALL_MASS);
   sc.ball_inv_i = (T)(1.0 / (0.4 * TB_BALL_MASS * TB_BALL_RADIUS * TB_BALL_RADIUS));  // sphere inertia recomputed [R]
@@ -586,15 +604,7 @@ template <typename T> static void build_scene(const Params &p, Scene<T> &sc) {
     sc.racket_box[0] = (T)(ay * (1 + 1e-6)); sc.racket_box[1] = (T)(zlo - 1e-6); sc.racket_box[2] = (T)(zhi + 1e-6);
     sc.racket_obb[0] = (T)ay; sc.racket_obb[1] = (T)zlo; sc.racket_obb[2] = (T)zhi;
     double zm = std::fmax(std::fabs(zlo), std::fabs(zhi));
-    double reach_hull = TB_BALL_RADIUS + p.hull_margin + p.contact_threshold, reach_box = TB_BALL_RADIUS + p.box_margin + p.contact_threshold;
-    double top = std::fmax(std::fmax(TB_FLOOR_HZ, TB_NET_HZ), TB_GOAL_HALF_Z);
-    // thresholds of the fast path, each rounded to the safe side so float and double kernels stay conservative
-    sc.ff_z_clear = (T)((top + std::fmax(reach_hull, reach_box)) * (1 + 1e-6));
-    sc.ff_reach_hull = (T)(reach_hull * (1 + 1e-6));
     sc.racket_obb_radius = (T)(std::sqrt(h.racket_half_x * h.racket_half_x + ay * ay + zm * zm) * (1 + 1e-6));
-    sc.ff_low_clear = (T)(((double)sc.racket_obb_radius + p.hull_margin + TB_FLOOR_HZ + p.contact_threshold) * (1 + 1e-6));
-    double rr = (double)sc.racket.bound_radius + reach_hull;
-    sc.ff_reach_racket2 = (T)(rr * rr * (1 + 1e-5));
   }
   build_prism<T, kGoalEdges>(sc.goal, h.goal_v, TB_GOAL_HALF_Z);
 }
@@ -631,7 +641,7 @@ struct tb_ctx {
   uint8_t *d_done = nullptr, *d_events = nullptr, *d_mask = nullptr;
   int64_t launches = 0;
   int *queue = nullptr;                      // fast-forward work queue (env indices), num_envs entries
-  unsigned long long *queue_ctrs = nullptr;  // two (appended, claimed) counter pairs used by alternate steps
+  unsigned long long *queue_ctrs = nullptr;  // two (front, back, claimed) counter triples used by alternate steps
   int parity = 0;
   unsigned ff_grid = 0;                      // persistent grid of ff_kernel
   bool timing = false;                       // tb_set_kernel_timing
@@ -689,9 +699,8 @@ template <typename T> static int ff_grid_size(tb_ctx *c, unsigned *grid) {
 // One env step = step_kernel (+ ff_kernel for SwingRacket) on `stream`.
 static int launch_step(tb_ctx *c, StepIO &io, cudaStream_t stream) {
   io.queue = c->queue;
-  io.queue_ctr = c->queue_ctrs + 2 * c->parity;
-  io.queue_head = io.queue_ctr + 1;
-  io.queue_ctr_next = c->queue_ctrs + 2 * (c->parity ^ 1);
+  io.queue_ctr = c->queue_ctrs + 3 * c->parity;
+  io.queue_ctr_next = c->queue_ctrs + 3 * (c->parity ^ 1);
   c->parity ^= 1;
   const unsigned grid = grid_for(io.n, kBlock);
   const bool swing = c->cfg.env_kind == TB_ENV_SWING;
@@ -783,12 +792,12 @@ int tb_create(const tb_config *cfg, tb_ctx **out) {
   size_t bytes = (size_t)cfg->num_envs * kPacks * 4 * word;
   cudaError_t e = cudaMalloc(&c->state, bytes);
   if (e == cudaSuccess) e = cudaMalloc(&c->stats, TB_NUM_STATS * sizeof(unsigned long long));
-  if (e == cudaSuccess) e = cudaMalloc(&c->queue_ctrs, 4 * sizeof(unsigned long long));
+  if (e == cudaSuccess) e = cudaMalloc(&c->queue_ctrs, 6 * sizeof(unsigned long long));
   if (e == cudaSuccess && cfg->env_kind == TB_ENV_SWING) e = cudaMalloc(&c->queue, (size_t)cfg->num_envs * sizeof(int));
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaMemsetAsync(c->state, 0, bytes, c->own_stream);
   if (e == cudaSuccess) e = cudaMemsetAsync(c->stats, 0, TB_NUM_STATS * sizeof(unsigned long long), c->own_stream);
-  if (e == cudaSuccess) e = cudaMemsetAsync(c->queue_ctrs, 0, 4 * sizeof(unsigned long long), c->own_stream);
+  if (e == cudaSuccess) e = cudaMemsetAsync(c->queue_ctrs, 0, 6 * sizeof(unsigned long long), c->own_stream);
   if (e == cudaSuccess) {
     // identity quaternion, episode = -1 so the first reset starts episode 0
     std::size_t n = (size_t)cfg->num_envs;
