@@ -50,7 +50,7 @@ def parse():
     ap.add_argument("--envs-per-gpu", type=int, default=1 << 20)
     ap.add_argument("--precision", default="f64", choices=["f32", "f64"])
     ap.add_argument("--e2e-steps", type=int, default=26)
-    ap.add_argument("--cpu-sample-envs", type=int, default=16384)
+    ap.add_argument("--cpu-sample-envs", type=int, default=65536)
     ap.add_argument("--stagger", default="auto", choices=["auto", "on", "off"],
                     help="episode phases: off = lock-step (all envs reset together), on = staggered per 128-env group; "
                          "auto = off when --steps is a multiple of the 26-step episode, else on (uniform launches)")
@@ -105,53 +105,59 @@ def measured_peak():
     return 6650.0, "fallback"
 
 
-def cpu_oracle_rate(env, n_envs, steps, threads):
-    """Env-steps/s of the restated CPU oracle (PyBullet is not installable here) on `threads` host threads."""
-    import numpy as np
+class CpuOracleRun:
+    """The restated CPU oracle (PyBullet is not installable here) on `threads` host threads: one env batch, one
+    pre-drawn action tape; step() timings exclude construction and action generation."""
 
-    from oracle import binding as ob
+    def __init__(self, env, n_envs, threads):
+        import numpy as np
 
-    ob.build()
-    o = ob.OracleEnv(env, n_envs, seed=0, threads=threads)
-    o.reset()
-    rng = np.random.default_rng(0)
-    acts = rng.uniform(-1, 1, (steps, n_envs, o.act_dim)).astype(np.float32)
-    t0 = time.perf_counter()
-    for t in range(steps):
-        o.step(acts[t])
-    dt = time.perf_counter() - t0
-    phys = o.physics_steps()
-    o.close()
-    return n_envs * steps / dt, dt, phys
+        from oracle import binding as ob
+
+        ob.build()
+        self.n = n_envs
+        self.o = ob.OracleEnv(env, n_envs, seed=0, threads=threads)
+        self.o.reset()
+        rng = np.random.default_rng(0)
+        self.acts = rng.uniform(-1, 1, (EPISODE_STEPS, n_envs, self.o.act_dim)).astype(np.float32)
+        self.t = 0
+
+    def run(self, steps):
+        """`steps` env steps for every env of the sample; returns (seconds, env steps done)."""
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            self.o.step(self.acts[self.t % EPISODE_STEPS])
+            self.t += 1
+        return time.perf_counter() - t0, self.n * steps
 
 
 # ---------------------------------------------------------------------------------------------- reference arm
 def run_reference(args, rank):
+    """CPU arm: the oracle port on all host cores, same workload (random actions, auto-reset), each bench step =
+    one whole 26-step episode of a bounded sample so the fast-forward step is weighted as in the GPU arm."""
     if rank != 0:
         return
     cores = os.cpu_count() or 1
     n = args.cpu_sample_envs
+    run = CpuOracleRun(args.env, n, cores)
     for _ in range(max(args.warmup, 0)):
-        cpu_oracle_rate(args.env, n, 1, cores)
-    # each "step" = one full 26-step episode of a bounded sample (so the fast-forward step is weighted as in the GPU arm)
-    t0 = time.perf_counter()
-    total = 0
-    phys = 0
+        run.run(EPISODE_STEPS)
+    wall, total = 0.0, 0
     for _ in range(args.steps):
-        rate, dt, ph = cpu_oracle_rate(args.env, n, EPISODE_STEPS, cores)
-        total += n * EPISODE_STEPS
-        phys += ph
-    wall = time.perf_counter() - t0
+        dt, k = run.run(EPISODE_STEPS)
+        wall += dt
+        total += k
     value = total / wall
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * wall / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"{args.env} random actions, CPU sample of {n} envs x {EPISODE_STEPS} steps per bench step",
+        "config": {"workload": f"{args.env} random actions, CPU sample of {n} envs x {EPISODE_STEPS} env steps per bench step",
                    "note": "restated double-precision CPU oracle (oracle/tb_oracle.c) - NOT PyBullet: pybullet, gym and "
                            "stable-baselines3 are absent from this image and cannot be installed offline"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{n} envs x {EPISODE_STEPS} env steps x {args.steps} repeats, {phys} physics substeps"},
+                         "sample": f"{n} envs x {EPISODE_STEPS} env steps x {args.steps} repeats, "
+                                   f"{run.o.physics_steps()} physics substeps incl. warm-up"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -306,16 +312,17 @@ def run_b200(args, rank, world):
         if not args.skip_cpu_baseline:
             cores = os.cpu_count() or 1
             cpu_n = args.cpu_sample_envs
-            cpu_oracle_rate(args.env, cpu_n, 2, cores)
+            run = CpuOracleRun(args.env, cpu_n, cores)
+            run.run(EPISODE_STEPS)
             reps, total, t_cpu = 0, 0, 0.0
-            while t_cpu < 10.0 and reps < 64:
-                _, dt, _ = cpu_oracle_rate(args.env, cpu_n, EPISODE_STEPS, cores)
+            while t_cpu < 12.0 and reps < 200:
+                dt, k = run.run(EPISODE_STEPS)
                 t_cpu += dt
-                total += cpu_n * EPISODE_STEPS
+                total += k
                 reps += 1
             line["cpu_baseline"] = {"value": total / t_cpu, "unit": UNIT, "cores": cores, "kind": "port",
-                                    "sample": f"{cpu_n} envs x {EPISODE_STEPS} env steps x {reps} repeats on {cores} threads; "
-                                              "restated CPU oracle, not PyBullet (absent from the image)"}
+                                    "sample": f"{cpu_n} envs x {EPISODE_STEPS} env steps x {reps} episodes on {cores} threads "
+                                              f"({t_cpu:.1f} s); restated CPU oracle, not PyBullet (absent from the image)"}
         print(json.dumps(line), flush=True)
     batch.close()
     if dist is not None:
