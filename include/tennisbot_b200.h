@@ -73,6 +73,14 @@ extern "C" {
 #define TB_STAT_PHYSICS_STEPS 8
 #define TB_STAT_ENV_STEPS 9
 
+/* how an action drives the racket */
+#define TB_CONTROL_FORCE 0 /* Racket.apply_target_action: world-frame force / torque at the COM (racket.py:92-100);
+                              what both registered gym envs do (swingracket_env.py:76-79, tennisbot_env.py:112-115) */
+#define TB_CONTROL_PID 1   /* Racket.apply_action = set_target_location + apply_pid_force_torque (racket.py:66-89,
+                              103-122): action[0:3] is a target position (hit env: action[0:2] + z = pid_hit_z), three
+                              simple_pid controllers evaluated in-kernel, force = (0,0,pid_bias_z) + outputs.  Reachable in
+                              the reference from playground.py:70-106 and the commented call at tennisbot_env.py:107 */
+
 /* in-kernel action sources for tb_rollout */
 #define TB_ACT_RANDOM 0 /* U(-1,1) = action_space.sample(); Philox stream keyed (env, episode, step) */
 
@@ -110,6 +118,9 @@ int tb_destroy(tb_ctx *ctx); /* p.disconnect (swingracket_env.py:189) */
  * = TennisbotEnv.set_racket_scale / loadURDF(globalScaling) (tennisbot_env.py:213-215, racket.py:39) */
 int tb_set_param(tb_ctx *ctx, const char *name, double value);
 int tb_get_param(tb_ctx *ctx, const char *name, double *value);
+/* TB_CONTROL_*; PID gains / limits are the parameters pid_kp, pid_ki, pid_kd, pid_max_force (Racket.update_pid,
+ * racket.py:170-184), pid_bias_z, pid_hit_z.  Controller memory is per env and cleared by reset. */
+int tb_set_control_mode(tb_ctx *ctx, int mode);
 
 /* ---- reset(): swingracket_env.py:151-186, tennisbot_env.py:217-261.
  * Starts a new episode for envs with d_mask[i] != 0 (all if NULL).  d_obs float32 [N, obs_dim] (may be NULL). */

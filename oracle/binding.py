@@ -47,6 +47,7 @@ def lib():
         L.tbo_destroy.argtypes = [vp]
         L.tbo_destroy.restype = None
         L.tbo_set_threads.argtypes = [vp, i32]
+        L.tbo_set_control_mode.argtypes = [vp, i32]
         L.tbo_set_param.argtypes = [vp, C.c_char_p, dbl]
         L.tbo_get_param.argtypes = [vp, C.c_char_p, C.POINTER(dbl)]
         L.tbo_param_name.restype = C.c_char_p
@@ -130,6 +131,9 @@ class OracleEnv:
 
     def set_threads(self, n):
         _check(lib().tbo_set_threads(self.h, int(n)))
+
+    def set_control_mode(self, mode):
+        _check(lib().tbo_set_control_mode(self.h, {"force": 0, "pid": 1}.get(mode, mode)))
 
     def set_param(self, name, value):
         _check(lib().tbo_set_param(self.h, name.encode(), float(value)))

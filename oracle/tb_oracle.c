@@ -43,13 +43,18 @@ typedef struct {
   double box_margin;           /* same margin, embedded in the box extents [R] */
   double gyro_term;            /* btMultiBody m_useGyroTerm [R] */
   double racket_scale;         /* globalScaling of racket.urdf: tennisbot_env.py:213-215,234 [C] */
+  double pid_kp, pid_ki, pid_kd; /* racket.py:49-51 [C]; Racket.update_pid racket.py:170-184 */
+  double pid_max_force;        /* racket.py:52: output (and integral) limits +-maxForce [C] */
+  double pid_bias_z;           /* racket.py:110: constant z force of apply_pid_force_torque [C] */
+  double pid_hit_z;            /* tennisbot_env.py:106 (commented call): z set-point appended to the 2-D hit action [C] */
 } params_t;
 
 static const char *k_param_names[] = {
     "dt", "gravity_z", "lin_damping", "ang_damping", "max_coord_vel", "rest_ball_racket", "rest_ball_court",
     "rest_ball_goal", "fric_ball_racket", "fric_ball_court", "fric_ball_goal", "contact_erp", "linear_slop",
     "rest_vel_threshold", "solver_iterations", "solver_residual", "contact_threshold", "hull_margin",
-    "box_margin", "gyro_term", "racket_scale"};
+    "box_margin", "gyro_term", "racket_scale", "pid_kp", "pid_ki", "pid_kd", "pid_max_force", "pid_bias_z",
+    "pid_hit_z"};
 #define N_PARAMS ((int)(sizeof k_param_names / sizeof k_param_names[0]))
 
 static void params_default(params_t *p) {
@@ -74,6 +79,12 @@ static void params_default(params_t *p) {
   p->box_margin = TBO_URDF_MARGIN;
   p->gyro_term = 1.0;
   p->racket_scale = 1.0;
+  p->pid_kp = 3.0;
+  p->pid_ki = 0.01;
+  p->pid_kd = 0.1;
+  p->pid_max_force = 10.0;
+  p->pid_bias_z = 4.0;
+  p->pid_hit_z = 1.5;
 }
 
 /* ------------------------------------------------------------------------------------------------ state */
@@ -114,6 +125,8 @@ struct tbo_ctx {
   double racket_inertia[3], racket_com_z;
   double racket_box[3]; /* outline bounding box in the COM frame: max |y|, min z, max z */
   double *state; /* [n][32] */
+  int control_mode; /* 0: direct force/torque (both gym envs), 1: PID position control (racket.py:66-89,103-122) */
+  double *pid;   /* [n][8]: integral xyz, last input xyz, has-last flag, spare; cleared by reset */
   int64_t stats[TBO_NUM_STATS];
   int64_t physics_steps;
 };
@@ -677,11 +690,36 @@ typedef struct {
   probe_t pb;
 } step_out_t;
 
-static void swing_step(const tbo_ctx *c, double *s, const float *a, step_out_t *o) {
+/* Racket.apply_action -> set_target_location + apply_pid_force_torque (racket.py:66-89,103-122): three
+ * simple_pid.PID(kp, ki, kd, output_limits=+-maxForce, sample_time=1/240) on the COM position, called with
+ * dt = 1/240 (so every call updates), force = (0, 0, 4) + outputs, applied at the COM.  simple_pid semantics [R]:
+ * e = sp - x; I = clamp(I + ki e dt); D = -kd (x - x_last)/dt (0 on the first call); out = clamp(kp e + I + D). */
+static void pid_force(const tbo_ctx *c, double *pid, const double *pos, const double *sp, double *F) {
+  const params_t *P = &c->p;
+  const double lim = P->pid_max_force, dt = P->dt;
+  for (int i = 0; i < 3; ++i) {
+    double e = sp[i] - pos[i];
+    double integ = clampd(pid[i] + P->pid_ki * e * dt, -lim, lim);
+    double d_in = pid[6] != 0 ? pos[i] - pid[3 + i] : 0.0;
+    double out = clampd(P->pid_kp * e + integ - P->pid_kd * d_in / dt, -lim, lim);
+    pid[i] = integ;
+    pid[3 + i] = pos[i];
+    F[i] = out;
+  }
+  pid[6] = 1.0;
+  F[2] += P->pid_bias_z;
+}
+
+static void swing_step(const tbo_ctx *c, double *s, double *pid, const float *a, step_out_t *o) {
   /* swingracket_env.py:75-145 */
   const double zero[3] = {0, 0, 0};
   double F[3] = {(double)a[0] * 400, (double)a[1] * 400, (double)a[2] * 400 + 4 * 9.81};
   double Tq[3] = {(double)a[3] * 5, (double)a[4] * 5, (double)a[5] * 5};
+  if (c->control_mode == 1) { /* PID position control: action[0:3] is the target location, no torque */
+    double sp[3] = {(double)a[0], (double)a[1], (double)a[2]};
+    pid_force(c, pid, s + S_RP, sp, F);
+    Tq[0] = Tq[1] = Tq[2] = 0;
+  }
   int bits = physics_step(c, s, F, Tq, zero, 1, &o->pb);
   o->nphys = 1;
   int k = (int)s[S_STEP] + 1;
@@ -710,10 +748,14 @@ static void swing_step(const tbo_ctx *c, double *s, const float *a, step_out_t *
   o->reward = reward; o->done = done; o->events = ev;
 }
 
-static void hit_step(const tbo_ctx *c, double *s, const float *a, step_out_t *o) {
+static void hit_step(const tbo_ctx *c, double *s, double *pid, const float *a, step_out_t *o) {
   /* tennisbot_env.py:104-207; BALL_SHOOT_FRAMES = 5 (:21) */
   const double zero[3] = {0, 0, 0};
   double F[3] = {(double)a[0] * 10, (double)a[1] * 10, 4 * 9.81};
+  if (c->control_mode == 1) { /* the commented racket.apply_action(np.append(action, [1.5, 0, 0, 0])) of :106-107 */
+    double sp[3] = {(double)a[0], (double)a[1], c->p.pid_hit_z};
+    pid_force(c, pid, s + S_RP, sp, F);
+  }
   int k = (int)s[S_STEP];
   double Fb[3] = {0, 0, 0};
   if (k < 5) { Fb[0] = s[S_AUX]; Fb[1] = s[S_AUX + 1]; Fb[2] = s[S_AUX + 2]; }
@@ -750,8 +792,9 @@ static void env_step_one(tbo_ctx *c, int64_t i, const float *act, float *obs, fl
   step_out_t o;
   memset(&o, 0, sizeof o);
   o.pb.margin = INFINITY;
-  if (c->kind == TBO_ENV_SWING) swing_step(c, s, act, &o);
-  else hit_step(c, s, act, &o);
+  double *pid = c->pid + i * 8;
+  if (c->kind == TBO_ENV_SWING) swing_step(c, s, pid, act, &o);
+  else hit_step(c, s, pid, act, &o);
   s[S_RET] += (double)(float)o.reward; /* the return sums the float32 rewards the caller sees */
   double ob[12];
   pack_obs(c, s, ob);
@@ -774,6 +817,7 @@ static void env_step_one(tbo_ctx *c, int64_t i, const float *act, float *obs, fl
       double in[TBO_INIT_WORDS];
       draw_init(c, c->id_offset + i, ep, in);
       start_episode(c, s, in, ep);
+      memset(pid, 0, 8 * sizeof(double)); /* reset() builds a new Racket, hence new PID objects */
       pack_obs(c, s, ob);
     }
   }
@@ -795,7 +839,8 @@ int tbo_create(int kind, int64_t n, int64_t id_offset, uint64_t seed, int auto_r
   params_default(&c->p);
   build_shapes(c);
   c->state = (double *)calloc((size_t)n * TBO_STATE_WORDS, sizeof(double));
-  if (!c->state) { free(c); return fail("tbo_create: out of memory"); }
+  c->pid = (double *)calloc((size_t)n * 8, sizeof(double));
+  if (!c->state || !c->pid) { free(c->state); free(c->pid); free(c); return fail("tbo_create: out of memory"); }
   for (int64_t i = 0; i < n; ++i) { c->state[i * TBO_STATE_WORDS + S_RQ + 3] = 1.0; c->state[i * TBO_STATE_WORDS + S_EPISODE] = -1.0; }
   *out = c;
   return 0;
@@ -803,11 +848,17 @@ int tbo_create(int kind, int64_t n, int64_t id_offset, uint64_t seed, int auto_r
 void tbo_destroy(tbo_ctx *c) {
   if (!c) return;
   free(c->state);
+  free(c->pid);
   free(c);
 }
 int tbo_set_threads(tbo_ctx *c, int nthreads) {
   if (!c || nthreads < 1) return fail("tbo_set_threads: bad argument");
   c->threads = nthreads;
+  return 0;
+}
+int tbo_set_control_mode(tbo_ctx *c, int mode) {
+  if (!c || (mode != 0 && mode != 1)) return fail("tbo_set_control_mode: bad argument");
+  c->control_mode = mode;
   return 0;
 }
 int tbo_num_params(void) { return N_PARAMS; }
@@ -867,6 +918,7 @@ static int reset_impl(tbo_ctx *c, const double *init, const uint8_t *mask, float
     if (init) memcpy(in, init + i * TBO_INIT_WORDS, sizeof in);
     else draw_init(c, c->id_offset + i, ep, in);
     start_episode(c, s, in, ep);
+    memset(c->pid + i * 8, 0, 8 * sizeof(double));
     if (obs) {
       double ob[12];
       pack_obs(c, s, ob);

@@ -48,6 +48,9 @@ void tbo_destroy(tbo_ctx *c);
 int tbo_obs_dim(int env_kind);
 int tbo_act_dim(int env_kind);
 int tbo_set_threads(tbo_ctx *c, int nthreads);
+/* 0 = direct force / torque actions (what both gym envs do), 1 = PID position control: Racket.apply_action
+ * (racket.py:66-89,103-122; reachable from playground.py:70-106 and the commented call at tennisbot_env.py:107) */
+int tbo_set_control_mode(tbo_ctx *c, int mode);
 int tbo_set_param(tbo_ctx *c, const char *name, double value);
 int tbo_get_param(tbo_ctx *c, const char *name, double *value);
 int tbo_num_params(void);

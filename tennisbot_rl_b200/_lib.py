@@ -14,6 +14,7 @@ ENV_SWING, ENV_HIT = 0, 1
 F32, F64 = 0, 1
 STATE_WORDS, INIT_WORDS, NUM_STATS = 32, 8, 10
 ACT_RANDOM = 0
+CONTROL_FORCE, CONTROL_PID = 0, 1
 
 EV_RACKET_BALL, EV_COURT_BALL, EV_GOAL_BALL, EV_TIMEOUT, EV_BALL_PASSED, EV_NET_BALL, EV_RACKET_LOW = 1, 2, 4, 8, 16, 32, 64
 STAT_NAMES = ("episodes", "sum_length", "racket_hits", "goals", "court", "timeouts", "sum_return_q20",
@@ -22,7 +23,7 @@ STAT_NAMES = ("episodes", "sum_length", "racket_hits", "goals", "court", "timeou
 # every symbol include/tennisbot_b200.h declares (checked by tests/test_abi.py)
 EXPORTS = (
     "tb_last_error", "tb_abi_version", "tb_obs_dim", "tb_act_dim", "tb_num_params", "tb_param_name",
-    "tb_scene_constant", "tb_create", "tb_destroy", "tb_set_param", "tb_get_param", "tb_reset", "tb_reset_from",
+    "tb_scene_constant", "tb_create", "tb_destroy", "tb_set_param", "tb_get_param", "tb_set_control_mode", "tb_reset", "tb_reset_from",
     "tb_step", "tb_rollout", "tb_get_state", "tb_set_state", "tb_stats_device_ptr", "tb_read_stats",
     "tb_reset_host", "tb_step_host", "tb_launch_count", "tb_set_kernel_timing", "tb_get_kernel_timing",
 )
@@ -62,6 +63,7 @@ def load():
     L.tb_destroy.argtypes = [vp]
     L.tb_set_param.argtypes = [vp, C.c_char_p, dbl]
     L.tb_get_param.argtypes = [vp, C.c_char_p, C.POINTER(dbl)]
+    L.tb_set_control_mode.argtypes = [vp, i32]
     L.tb_reset.argtypes = [vp, vp, vp, vp]
     L.tb_reset_from.argtypes = [vp, vp, vp, vp, vp]
     L.tb_step.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp]

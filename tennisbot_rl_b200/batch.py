@@ -71,6 +71,11 @@ class TennisBatch:
     def set_param(self, name, value):
         _lib.check(self.lib.tb_set_param(self.h, name.encode(), float(value)))
 
+    def set_control_mode(self, mode):
+        """'force' (both gym envs) or 'pid' (Racket.apply_action: the action is a target position)."""
+        m = {"force": _lib.CONTROL_FORCE, "pid": _lib.CONTROL_PID}.get(mode, mode)
+        _lib.check(self.lib.tb_set_control_mode(self.h, int(m)))
+
     def get_param(self, name):
         v = C.c_double()
         _lib.check(self.lib.tb_get_param(self.h, name.encode(), C.byref(v)))

@@ -94,6 +94,7 @@ template <typename T> struct Scene {
   T erp, slop, rest_vel_threshold, solver_residual, contact_threshold, hull_margin, box_margin, gyro;
   int iters;
   unsigned vmax_hi;  // high 32 bits of max_coord_vel in T's format (clamp_velocities)
+  T pid_kp, pid_ki, pid_kd, pid_lim, pid_bias_z, pid_hit_z;  // TB_CONTROL_PID (racket.py:47-64,103-122)
   T ball_r, ball_inv_m, ball_inv_i, racket_inv_m;
   T racket_i[3], racket_inv_i[3];
   T com_z;
@@ -702,6 +703,24 @@ template <typename T> __device__ __forceinline__ T dist_to_reward(T d) {
   return d < (T)0.5 ? (T)20 : d < 1 ? (T)15 : d < 2 ? (T)10 : d < 3 ? (T)5 : d < 4 ? (T)1 : (T)0;
 }
 
+// TB_CONTROL_PID: three simple_pid.PID controllers on the racket COM position, evaluated with dt = 1/240
+// (racket.py:47-64,103-122).  e = sp - x; I = clamp(I + ki e dt); D = -kd (x - x_last)/dt, 0 on the first call;
+// out = clamp(kp e + I + D); force = (0, 0, bias) + out.  pid = {I xyz, x_last xyz, has_last, -}.
+template <typename T> __device__ __forceinline__ void pid_force(const Scene<T> &sc, T *pid, const T *pos, const T *sp, T *F) {
+  const T lim = sc.pid_lim, dt = sc.dt;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    T e = sp[i] - pos[i];
+    T integ = clampv(pid[i] + sc.pid_ki * e * dt, -lim, lim);
+    T d_in = pid[6] != 0 ? pos[i] - pid[3 + i] : (T)0;
+    F[i] = clampv(sc.pid_kp * e + integ - sc.pid_kd * d_in / dt, -lim, lim);
+    pid[i] = integ;
+    pid[3 + i] = pos[i];
+  }
+  pid[6] = 1;
+  F[2] += sc.pid_bias_z;
+}
+
 // Per-lane progress of one agent-visible step().  SwingRacket's 26th step re-enters the substep many times:
 //   phase 0: the substep driven by the action (swingracket_env.py:76-83)
 //   phase 1: first fast-forward substep, no external force (the step above cleared them) (:105-107)
@@ -714,14 +733,20 @@ struct StepCtl {
 
 // One physics substep of the env step in flight plus the env logic that follows it.  Returns true when the
 // env step is complete (reward / done / events are final).
+// pid: this env's controller memory when the context runs TB_CONTROL_PID, else nullptr.
 template <typename T, int KIND>
-__device__ __forceinline__ bool env_substep(const Scene<T> &sc, St<T> &s, const float *a, StepCtl &c) {
+__device__ __forceinline__ bool env_substep(const Scene<T> &sc, St<T> &s, const float *a, StepCtl &c, T *pid = nullptr) {
   T zero[3] = {0, 0, 0};
   if (KIND == TB_ENV_SWING) {
     T F[3], Tq[3] = {0, 0, 0};
     if (c.phase == 0) {
       F[0] = (T)a[0] * 400; F[1] = (T)a[1] * 400; F[2] = (T)a[2] * 400 + (T)(4 * 9.81);
       Tq[0] = (T)a[3] * 5; Tq[1] = (T)a[4] * 5; Tq[2] = (T)a[5] * 5;
+      if (pid) {
+        T sp[3] = {(T)a[0], (T)a[1], (T)a[2]};
+        pid_force(sc, pid, s.rp, sp, F);
+        Tq[0] = Tq[1] = Tq[2] = 0;
+      }
     } else if (c.phase == 1) {
       F[0] = F[1] = F[2] = 0;
     } else {  // the force the reference queued from the post-step pose of the previous substep = this one's pre-step pose
@@ -746,6 +771,10 @@ __device__ __forceinline__ bool env_substep(const Scene<T> &sc, St<T> &s, const 
     return c.done;
   } else {
     T F[3] = {(T)a[0] * 10, (T)a[1] * 10, (T)(4 * 9.81)};
+    if (pid) {
+      T sp[3] = {(T)a[0], (T)a[1], sc.pid_hit_z};
+      pid_force(sc, pid, s.rp, sp, F);
+    }
     T Fb[3] = {0, 0, 0};
     if (s.step < 5) { Fb[0] = s.aux[0]; Fb[1] = s.aux[1]; Fb[2] = s.aux[2]; }
     int bits = physics_step<T, false>(sc, s, F, zero, Fb, 0);

@@ -84,6 +84,16 @@ template <typename T> __device__ __forceinline__ void store_state(T *base, int64
   st_pack(base, n, 7, i, Pack<T>{s.ret, int_as(T(), s.step), int_as(T(), s.flags), int_as(T(), (int64_t)s.episode)});
 }
 
+// controller memory of TB_CONTROL_PID: two more packs per env in a separate array (allocated when the mode is set)
+template <typename T> __device__ __forceinline__ void load_pid(const T *pb, int64_t n, int64_t i, T *pid) {
+  Pack<T> a = ld_pack(pb, n, 0, i), b = ld_pack(pb, n, 1, i);
+  pid[0] = a.x; pid[1] = a.y; pid[2] = a.z; pid[3] = a.w; pid[4] = b.x; pid[5] = b.y; pid[6] = b.z; pid[7] = b.w;
+}
+template <typename T> __device__ __forceinline__ void store_pid(T *pb, int64_t n, int64_t i, const T *pid) {
+  st_pack(pb, n, 0, i, Pack<T>{pid[0], pid[1], pid[2], pid[3]});
+  st_pack(pb, n, 1, i, Pack<T>{pid[4], pid[5], pid[6], pid[7]});
+}
+
 // ------------------------------------------------------------------------------------------------ kernels
 struct StepIO {
   void *state;
@@ -99,6 +109,7 @@ struct StepIO {
   unsigned long long *queue_ctr;     // [0] front entries, [1] back entries appended by this step's step_kernel,
                                      // [2] entries claimed by ff_kernel lanes
   unsigned long long *queue_ctr_next;  // the triple the NEXT step uses; step_kernel zeroes it
+  void *pid;                         // TB_CONTROL_PID: 2 packs x N of controller memory, else nullptr
 };
 
 template <int KIND> struct Dims {
@@ -254,7 +265,18 @@ __global__ void __launch_bounds__(kBlock) step_kernel(const __grid_constant__ Sc
     load_state(base, io.n, me, s);
     load_action<KIND>(io.actions, me, a);
     c.done = s.flags & kFlagDone;
-    fin = env_substep<T, KIND>(sc, s, a, c);
+    if (TB_UNLIKELY(io.pid != nullptr)) {
+      T pid[8];
+      load_pid(static_cast<const T *>(io.pid), io.n, me, pid);
+      fin = env_substep<T, KIND>(sc, s, a, c, pid);
+      if (fin && c.done && io.auto_reset) {  // reset() builds a new Racket, hence fresh controllers
+#pragma unroll
+        for (int j = 0; j < 8; ++j) pid[j] = 0;
+      }
+      store_pid(static_cast<T *>(io.pid), io.n, me, pid);
+    } else {
+      fin = env_substep<T, KIND>(sc, s, a, c);
+    }
     if (fin) s.ret += (T)c.reward;
   }
   unsigned act_mask = __ballot_sync(full, valid);
@@ -350,6 +372,10 @@ __global__ void __launch_bounds__(kBlock, MinBlocks<T>::v) ff_kernel(const __gri
       s.flags &= kFlagDone;  // drop the in-flight mark and the parked event bits
       finish_api<T, KIND>(sc, io, (int64_t)me, s, c.reward, c.done, c.events);
       store_state(base, io.n, (int64_t)me, s);
+      if (io.pid && c.done && io.auto_reset) {
+        T z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        store_pid(static_cast<T *>(io.pid), io.n, (int64_t)me, z);
+      }
       active = false;
     }
   }
@@ -440,6 +466,10 @@ __global__ void __launch_bounds__(kBlock) reset_kernel(const __grid_constant__ S
   }
   start_episode<T, KIND>(sc, s, in, ep);
   store_state(base, io.n, i, s);
+  if (io.pid) {
+    T z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    store_pid(static_cast<T *>(io.pid), io.n, i, z);
+  }
   if (io.obs) {
     float ob[12];
     pack_obs<T, KIND>(s, ob);
@@ -483,13 +513,15 @@ template <typename T> __global__ void set_state_kernel(T *base, int64_t n, const
 struct Params {  // order matches k_param_names
   double dt, gravity_z, lin_damping, ang_damping, max_coord_vel, rest_ball_racket, rest_ball_court, rest_ball_goal,
       fric_ball_racket, fric_ball_court, fric_ball_goal, contact_erp, linear_slop, rest_vel_threshold,
-      solver_iterations, solver_residual, contact_threshold, hull_margin, box_margin, gyro_term, racket_scale;
+      solver_iterations, solver_residual, contact_threshold, hull_margin, box_margin, gyro_term, racket_scale, pid_kp,
+      pid_ki, pid_kd, pid_max_force, pid_bias_z, pid_hit_z;
 };
 static const char *k_param_names[] = {
     "dt", "gravity_z", "lin_damping", "ang_damping", "max_coord_vel", "rest_ball_racket", "rest_ball_court",
     "rest_ball_goal", "fric_ball_racket", "fric_ball_court", "fric_ball_goal", "contact_erp", "linear_slop",
     "rest_vel_threshold", "solver_iterations", "solver_residual", "contact_threshold", "hull_margin",
-    "box_margin", "gyro_term", "racket_scale"};
+    "box_margin", "gyro_term", "racket_scale", "pid_kp", "pid_ki", "pid_kd", "pid_max_force", "pid_bias_z",
+    "pid_hit_z"};
 constexpr int kNumParams = sizeof(k_param_names) / sizeof(k_param_names[0]);
 static_assert(sizeof(Params) == kNumParams * sizeof(double), "Params / name table mismatch");
 
@@ -515,6 +547,12 @@ static void params_default(Params &p) {
   p.box_margin = TB_URDF_MARGIN;
   p.gyro_term = 1.0;
   p.racket_scale = 1.0;
+  p.pid_kp = 3.0;   // racket.py:49-52
+  p.pid_ki = 0.01;
+  p.pid_kd = 0.1;
+  p.pid_max_force = 10.0;
+  p.pid_bias_z = 4.0;    // racket.py:110
+  p.pid_hit_z = 1.5;     // tennisbot_env.py:106
 }
 
 template <typename T, int NE> static void build_prism(Prism<T, NE> &pr, const double (*v)[2], double half_thick) {
@@ -574,6 +612,8 @@ template <typename T> static void build_scene(const Params &p, Scene<T> &sc) {
   sc.erp = (T)p.contact_erp; sc.slop = (T)p.linear_slop; sc.rest_vel_threshold = (T)p.rest_vel_threshold;
   sc.solver_residual = (T)p.solver_residual; sc.contact_threshold = (T)p.contact_threshold;
   sc.hull_margin = (T)p.hull_margin; sc.box_margin = (T)p.box_margin; sc.gyro = (T)p.gyro_term;
+  sc.pid_kp = (T)p.pid_kp; sc.pid_ki = (T)p.pid_ki; sc.pid_kd = (T)p.pid_kd; sc.pid_lim = (T)p.pid_max_force;
+  sc.pid_bias_z = (T)p.pid_bias_z; sc.pid_hit_z = (T)p.pid_hit_z;
   sc.iters = (int)p.solver_iterations;
   {
     T v = (T)p.max_coord_vel;
@@ -644,6 +684,8 @@ struct tb_ctx {
   unsigned long long *queue_ctrs = nullptr;  // two (front, back, claimed) counter triples used by alternate steps
   int parity = 0;
   unsigned ff_grid = 0;                      // persistent grid of ff_kernel
+  int control_mode = TB_CONTROL_FORCE;
+  void *pid = nullptr;                       // controller memory, allocated by tb_set_control_mode(TB_CONTROL_PID)
   bool timing = false;                       // tb_set_kernel_timing
   cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
   double ms_step = 0, ms_ff = 0;
@@ -671,7 +713,19 @@ static StepIO make_io(tb_ctx *c) {
   std::memset(&io, 0, sizeof io);
   io.state = c->state; io.n = c->cfg.num_envs; io.id_offset = c->cfg.env_id_offset; io.seed = c->cfg.seed;
   io.auto_reset = c->cfg.auto_reset; io.stats = c->stats; io.k_steps = 1;
+  io.pid = c->control_mode == TB_CONTROL_PID ? c->pid : nullptr;
   return io;
+}
+
+static int set_control_mode(tb_ctx *c, int mode) {
+  if (mode != TB_CONTROL_FORCE && mode != TB_CONTROL_PID) return fail("%s", "tb_set_control_mode: unknown mode");
+  if (mode == TB_CONTROL_PID && !c->pid) {
+    size_t bytes = (size_t)c->cfg.num_envs * 8 * (c->cfg.precision == TB_F64 ? 8 : 4);
+    CU(cudaMalloc(&c->pid, bytes));
+    CU(cudaMemset(c->pid, 0, bytes));
+  }
+  c->control_mode = mode;
+  return 0;
 }
 
 #define DISPATCH(KERNEL, grid, block, stream, ...)                                                          \
@@ -833,7 +887,7 @@ int tb_destroy(tb_ctx *c) {
   DeviceGuard g(c->cfg.device);
   if (c->own_stream) { cudaStreamSynchronize(c->own_stream); cudaStreamDestroy(c->own_stream); }
   for (int i = 0; i < 3; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
-  cudaFree(c->state); cudaFree(c->stats); cudaFree(c->queue_ctrs); cudaFree(c->queue);
+  cudaFree(c->state); cudaFree(c->stats); cudaFree(c->queue_ctrs); cudaFree(c->queue); cudaFree(c->pid);
   cudaFree(c->d_actions); cudaFree(c->d_obs); cudaFree(c->d_reward); cudaFree(c->d_term);
   cudaFree(c->d_done); cudaFree(c->d_events); cudaFree(c->d_mask);
   delete c;
@@ -846,6 +900,10 @@ int tb_set_param(tb_ctx *c, const char *name, double value) {
   for (int i = 0; i < kNumParams; ++i)
     if (!std::strcmp(name, k_param_names[i])) { slots[i] = value; rebuild(c); return 0; }
   return fail("tb_set_param: unknown parameter '%s'", name);
+}
+int tb_set_control_mode(tb_ctx *c, int mode) {
+  GUARD(c);
+  return set_control_mode(c, mode);
 }
 int tb_get_param(tb_ctx *c, const char *name, double *value) {
   if (!c || !name || !value) return fail("%s", "tb_get_param: bad argument");
@@ -882,6 +940,7 @@ int tb_step(tb_ctx *c, const float *d_actions, float *d_obs, float *d_reward, ui
 int tb_rollout(tb_ctx *c, int action_mode, int k_steps, float *d_obs, float *d_reward_sum, int32_t *d_done_count, void *stream) {
   GUARD(c);
   if (action_mode != TB_ACT_RANDOM) return fail("%s", "tb_rollout: unknown action mode");
+  if (c->control_mode != TB_CONTROL_FORCE) return fail("%s", "tb_rollout: in-kernel random actions need TB_CONTROL_FORCE");
   if (k_steps < 0) return fail("%s", "tb_rollout: k_steps must be >= 0");
   StepIO io = make_io(c);
   io.k_steps = k_steps; io.obs = d_obs; io.reward_sum = d_reward_sum; io.done_count = d_done_count;

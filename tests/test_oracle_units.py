@@ -233,3 +233,43 @@ def test_param_override_changes_dynamics(oracle_lib):
     assert b[16] == 10.0 and a[16] < 10.0
     with pytest.raises(RuntimeError):
         o.set_param("no_such_parameter", 1.0)
+
+
+class _SimplePID:
+    """simple_pid.PID restated for the test (the package is not installed): proportional on error, derivative on
+    measurement, integral and output clamped to the limits, first call has no derivative."""
+
+    def __init__(self, kp, ki, kd, lim):
+        self.kp, self.ki, self.kd, self.lim = kp, ki, kd, lim
+        self.integral, self.last = 0.0, None
+
+    def __call__(self, setpoint, x, dt):
+        e = setpoint - x
+        self.integral = float(np.clip(self.integral + self.ki * e * dt, -self.lim, self.lim))
+        d = -self.kd * (x - self.last) / dt if self.last is not None else 0.0
+        self.last = x
+        return float(np.clip(self.kp * e + self.integral + d, -self.lim, self.lim))
+
+
+def test_pid_control_mode(oracle_lib):
+    """A9: Racket.apply_action (racket.py:66-89,103-122): force = (0,0,4) + PID(kp=3, ki=.01, kd=.1, +-10 N)(pos)."""
+    o = oracle_lib.OracleEnv("Tennisbot-v0", 1, auto_reset=False)
+    o.set_control_mode("pid")
+    init = np.array([[9.5, 1.0, 0.205, 30.0, -3.0, -9.0, 0.5, 1.2]])
+    o.reset(init=init)
+    pids = [_SimplePID(3.0, 0.01, 0.1, 10.0) for _ in range(3)]
+    dt, m, g = 1 / 240, 4.0, -9.81
+    pos = np.array([9.5, 1.0, 0.705])
+    vel = np.zeros(3)
+    target = np.array([9.8, 0.7, 1.5], np.float32)
+    for k in range(50):
+        f = np.array([pids[i](float(target[i]), pos[i], dt) for i in range(3)]) + [0, 0, 4.0]
+        kdamp = 0.04 * (1 + np.linalg.norm(vel))
+        vel = vel + dt * (f / m + [0, 0, g] - vel * kdamp)
+        pos = pos + dt * vel
+        r = o.step(target[None, :2])
+        np.testing.assert_allclose(r["obs"][0][:3], pos, rtol=0, atol=2e-6)
+        np.testing.assert_allclose(r["obs"][0][3:6], vel, rtol=0, atol=2e-6)
+    # gains are parameters (Racket.update_pid); reset clears the controller memory
+    o.set_param("pid_kp", 10.0)
+    assert o.get_param("pid_kp") == 10.0

@@ -116,3 +116,22 @@ def test_fused_rollout_matches_stepwise(oracle_lib, env):
     assert np.abs(grs - r["reward_sum"]).max() < 1e-3
     np.testing.assert_array_equal(b.read_stats(), o.read_stats())
     assert np.abs(b.get_state().cpu().numpy() - o.get_state()).max() < TOL_F64_STATE
+
+
+@pytest.mark.parametrize("env", ["SwingRacket-v0", "Tennisbot-v0"])
+def test_pid_control_mode_parity(oracle_lib, env):
+    """A9 (TB_CONTROL_PID): actions are target positions, three in-kernel simple_pid controllers; f64 parity with the
+    oracle over a horizon that crosses auto-resets (controller memory is cleared by reset)."""
+    n = 1024
+    b, o = _make(env, n, "f64", 5, oracle_lib)
+    b.set_control_mode("pid")
+    o.set_control_mode("pid")
+    np.testing.assert_array_equal(b.reset().cpu().numpy(), o.reset())
+    rng = np.random.default_rng(3)
+    lo, hi = (np.array([5, -4, 0.5, 0, 0, 0]), np.array([12, 4, 2.0, 0, 0, 0])) if o.act_dim == 6 else (np.array([7, -5]), np.array([13, 5]))
+    steps = 60 if env == "SwingRacket-v0" else 700
+    rep, valid = run_parity(b, o, steps, lambda t, _obs: rng.uniform(lo, hi, (n, o.act_dim)), band=0.0, check_state_every=15)
+    print(rep)
+    assert rep.event_mismatch_hard == 0 and rep.event_mismatch_near == 0
+    assert rep.max_state_err < TOL_F64_STATE and rep.max_obs_err < TOL_F64_OUT
+    np.testing.assert_array_equal(b.read_stats(), o.read_stats())
