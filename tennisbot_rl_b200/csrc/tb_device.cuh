@@ -461,21 +461,27 @@ __device__ __noinline__ int narrow_phase(const Scene<T> &sc, int need, const Nar
   return bits | (nc << 8);
 }
 
-// sin and cos of the half rotation angle of one substep.  |x| = |omega| dt / 2 <= 0.37 because every velocity
-// coordinate is clamped to +-100, so a short Taylor series is exact to the last bit or two and replaces the
-// general-range library routine (the oracle calls libm; the difference is below 1 ulp).
-__device__ __forceinline__ void sincos_small(float x, float *s, float *c) {
-  float x2 = x * x;
-  *s = x * (1.0f + x2 * (-1.0f / 6 + x2 * (1.0f / 120 + x2 * (-1.0f / 5040 + x2 * (1.0f / 362880)))));
+// Half-angle factors of one substep's rotation, as even functions of |omega|: with x = |omega| dt / 2,
+//   sinc(x) = sin(x)/x and cos(x) are power series in x^2 = a2 dt^2 / 4, so neither |omega|, its reciprocal nor a
+// small-angle special case (Bullet switches to a Taylor form below 0.001 rad/s) is ever needed.  |x| <= 0.37
+// because every velocity coordinate is clamped to +-100; the short series covers |omega| < 24 rad/s (x^2 < 2.5e-3)
+// to the last bit, the long one the rest.  The oracle calls libm sin/cos; the difference is below 1 ulp.
+__device__ __forceinline__ void sinc_cos_x2(float x2, float *sinc, float *c) {
+  *sinc = 1.0f + x2 * (-1.0f / 6 + x2 * (1.0f / 120 + x2 * (-1.0f / 5040 + x2 * (1.0f / 362880))));
   *c = 1.0f + x2 * (-0.5f + x2 * (1.0f / 24 + x2 * (-1.0f / 720 + x2 * (1.0f / 40320 + x2 * (-1.0f / 3628800)))));
 }
-__device__ __forceinline__ void sincos_small(double x, double *s, double *c) {
-  double x2 = x * x;
-  *s = x * (1.0 + x2 * (-1.0 / 6 + x2 * (1.0 / 120 + x2 * (-1.0 / 5040 + x2 * (1.0 / 362880 + x2 * (-1.0 / 39916800 +
-       x2 * (1.0 / 6227020800.0 + x2 * (-1.0 / 1307674368000.0 + x2 * (1.0 / 355687428096000.0)))))))));
-  *c = 1.0 + x2 * (-0.5 + x2 * (1.0 / 24 + x2 * (-1.0 / 720 + x2 * (1.0 / 40320 + x2 * (-1.0 / 3628800 +
-       x2 * (1.0 / 479001600.0 + x2 * (-1.0 / 87178291200.0 + x2 * (1.0 / 20922789888000.0 +
-       x2 * (-1.0 / 6402373705728000.0)))))))));
+__device__ __forceinline__ void sinc_cos_x2(double x2, double *sinc, double *c) {
+  if (x2 < 2.5e-3) {
+    *sinc = 1.0 + x2 * (-1.0 / 6 + x2 * (1.0 / 120 + x2 * (-1.0 / 5040 + x2 * (1.0 / 362880 + x2 * (-1.0 / 39916800)))));
+    *c = 1.0 + x2 * (-0.5 + x2 * (1.0 / 24 + x2 * (-1.0 / 720 + x2 * (1.0 / 40320 + x2 * (-1.0 / 3628800 +
+         x2 * (1.0 / 479001600.0))))));
+  } else {
+    *sinc = 1.0 + x2 * (-1.0 / 6 + x2 * (1.0 / 120 + x2 * (-1.0 / 5040 + x2 * (1.0 / 362880 + x2 * (-1.0 / 39916800 +
+            x2 * (1.0 / 6227020800.0 + x2 * (-1.0 / 1307674368000.0 + x2 * (1.0 / 355687428096000.0))))))));
+    *c = 1.0 + x2 * (-0.5 + x2 * (1.0 / 24 + x2 * (-1.0 / 720 + x2 * (1.0 / 40320 + x2 * (-1.0 / 3628800 +
+         x2 * (1.0 / 479001600.0 + x2 * (-1.0 / 87178291200.0 + x2 * (1.0 / 20922789888000.0 +
+         x2 * (-1.0 / 6402373705728000.0)))))))));
+  }
 }
 __device__ __forceinline__ float fast_rsqrt(float x) {
   float y = rsqrtf(x);
@@ -487,30 +493,27 @@ __device__ __forceinline__ double fast_rsqrt(double x) { return ::rsqrt(x); }
 template <typename T> __device__ __forceinline__ void integrate_quat(const Scene<T> &sc, St<T> &s) {
   const T dt = sc.dt;
   if (s.rw[0] != 0 || s.rw[1] != 0 || s.rw[2] != 0) {
-    T a2 = dot3(s.rw, s.rw), k, sn, cw;
-    if (TB_UNLIKELY(a2 < (T)1e-6)) {  // |omega| < 0.001: Taylor form of sin(x)/x, as Bullet does
-      T ang = M<T>::sqrt(a2);
-      k = (T)0.5 * dt - dt * dt * dt * (T)0.020833333333 * a2;
-      sincos_small((T)0.5 * ang * dt, &sn, &cw);
-    } else {
-      T inv_ang = fast_rsqrt(a2), ang = a2 * inv_ang;
-      sincos_small((T)0.5 * ang * dt, &sn, &cw);
-      k = sn * inv_ang;
-    }
+    T a2 = dot3(s.rw, s.rw), sinc, cw;
+    sinc_cos_x2((T)0.25 * dt * dt * a2, &sinc, &cw);
+    T k = (T)0.5 * dt * sinc;  // sin(|omega| dt / 2) / |omega|
     T ax = s.rw[0] * k, ay = s.rw[1] * k, az = s.rw[2] * k;
     const T *q = s.rq;
     T x = cw * q[0] + ax * q[3] + ay * q[2] - az * q[1];
     T y = cw * q[1] - ax * q[2] + ay * q[3] + az * q[0];
     T z = cw * q[2] + ax * q[1] - ay * q[0] + az * q[3];
     T w = cw * q[3] - ax * q[0] - ay * q[1] - az * q[2];
-    T inv = fast_rsqrt(x * x + y * y + z * z + w * w);
+    // the product of two unit quaternions is unit up to rounding: 1/sqrt(1 + e) = 1 - e/2 to ~e^2, so one
+    // multiply-add renormalises; a quaternion that is off by more (injected through tb_set_state) takes the exact path
+    T n2 = x * x + y * y + z * z + w * w;
+    T inv = (T)1.5 - (T)0.5 * n2;
+    if (TB_UNLIKELY(M<T>::abs(n2 - 1) > (T)1e-4)) inv = fast_rsqrt(n2);
     s.rq[0] = x * inv; s.rq[1] = y * inv; s.rq[2] = z * inv; s.rq[3] = w * inv;
   }
 }
 
 // One stepSimulation(): detect at the start-of-step poses, integrate velocities with Bullet's multibody
 // damping, solve contacts, integrate poses.  Returns the TB_EV_* contact bits getContactPoints would report.
-// known_bits: event bits already latched for this env step (lets the sticky RACKET_LOW diagnostic skip its loop).
+// known_bits: event bits already latched for this env step (unused since the floor-flag test became branch-free).
 template <typename T, bool WITH_GOAL>
 __device__ __forceinline__ int physics_step(const Scene<T> &sc, St<T> &s, const T *f_racket, const T *t_racket,
                                             const T *f_ball, int known_bits) {
@@ -518,38 +521,43 @@ __device__ __forceinline__ int physics_step(const Scene<T> &sc, St<T> &s, const 
   ContactSet<T> cs;  // lives in local memory; touched on the rare path only
   int nc = 0, bits = 0;
 
-  // ---- (1) detection: cheap conservative broad-phase rejects in line, every narrow phase in one rare call
+  // ---- (1) detection: conservative broad-phase rejects in line and branch-free, every narrow phase in one rare call
+  T R[9];
+  quat_to_mat(s.rq, R);
   {
     int need = 0;
-    T rel[3] = {s.bp[0] - s.rp[0], s.bp[1] - s.rp[1], s.bp[2] - s.rp[2]};
-    T reach = sc.racket.bound_radius + rb + sc.hull_margin + thr;
-    if (dot3(rel, rel) <= reach * reach) need |= kNeedRacket;
+    {
+      // racket: inside the hull's bounding sphere AND, in the racket frame, inside the plate's slab and the outline's
+      // bounding box (each grown by ball radius + margin + threshold).  A ball that merely lingers near a racket
+      // it missed - the common case, both are in free fall side by side - never leaves the straight line.
+      T rel[3] = {s.bp[0] - s.rp[0], s.bp[1] - s.rp[1], s.bp[2] - s.rp[2]}, pl[3];
+      matT_vec(R, rel, pl);
+      const T reach = rb + sc.hull_margin + thr, rs = sc.racket.bound_radius + reach;
+      bool near_racket = dot3(rel, rel) <= rs * rs && !(M<T>::abs(pl[0]) - sc.racket.half_thick > reach) &&
+                         !(M<T>::abs(pl[1]) - sc.racket_box[0] > reach) && !(pl[2] - sc.racket_box[2] > reach) &&
+                         !(sc.racket_box[1] - pl[2] > reach);
+      need |= near_racket ? kNeedRacket : 0;
+    }
     const T reach_b = rb + sc.box_margin + thr;
-    if (!(M<T>::abs(s.bp[2]) - sc.floor_h[2] > reach_b || M<T>::abs(s.bp[0]) - sc.floor_h[0] > reach_b ||
-          M<T>::abs(s.bp[1]) - sc.floor_h[1] > reach_b))
-      need |= kNeedFloor;
-    if (!(M<T>::abs(s.bp[0]) - sc.net_h[0] > reach_b || M<T>::abs(s.bp[2]) - sc.net_h[2] > reach_b ||
-          M<T>::abs(s.bp[1]) - sc.net_h[1] > reach_b))
-      need |= kNeedNet;
+    need |= !(M<T>::abs(s.bp[2]) - sc.floor_h[2] > reach_b || M<T>::abs(s.bp[0]) - sc.floor_h[0] > reach_b ||
+              M<T>::abs(s.bp[1]) - sc.floor_h[1] > reach_b) ? kNeedFloor : 0;
+    need |= !(M<T>::abs(s.bp[0]) - sc.net_h[0] > reach_b || M<T>::abs(s.bp[2]) - sc.net_h[2] > reach_b ||
+              M<T>::abs(s.bp[1]) - sc.net_h[1] > reach_b) ? kNeedNet : 0;
     if (WITH_GOAL) {
-      T reach_g = rb + sc.hull_margin + thr;
-      if (M<T>::abs(s.bp[2]) - sc.goal_hz <= reach_g) {
-        T gx = s.bp[0] - s.goal[0], gy = s.bp[1] - s.goal[1], rxy = sc.goal_r + reach_g;
-        if (gx * gx + gy * gy <= rxy * rxy) need |= kNeedGoal;
-      }
+      const T reach_g = rb + sc.hull_margin + thr, rxy = sc.goal_r + reach_g;
+      T gx = s.bp[0] - s.goal[0], gy = s.bp[1] - s.goal[1];
+      need |= (M<T>::abs(s.bp[2]) - sc.goal_hz <= reach_g && gx * gx + gy * gy <= rxy * rxy) ? kNeedGoal : 0;
     }
     // Racket vs floor is not modelled (the racket falls through the court once the episode's control phase is
     // over); TB_EV_RACKET_LOW marks the steps from which its pose is outside the parity horizon: the lowest
     // corner of the hull's oriented bounding box (outline box x plate thickness, margin included) is at or below
     // the floor's contact threshold while the COM is over the court.
-    if (!(known_bits & TB_EV_RACKET_LOW) && s.rp[2] - sc.racket_obb_radius - sc.hull_margin <= sc.floor_h[2] + thr) {
-      const T *q = s.rq;
-      T r6 = 2 * (q[0] * q[2] - q[1] * q[3]), r7 = 2 * (q[1] * q[2] + q[0] * q[3]), r8 = 1 - 2 * (q[0] * q[0] + q[1] * q[1]);
-      T zlo = r8 * sc.racket_obb[1], zhi = r8 * sc.racket_obb[2];
-      T low = s.rp[2] - M<T>::abs(r6) * sc.racket.half_thick - M<T>::abs(r7) * sc.racket_obb[0] + (zlo < zhi ? zlo : zhi) -
+    {
+      T zlo = R[8] * sc.racket_obb[1], zhi = R[8] * sc.racket_obb[2];
+      T low = s.rp[2] - M<T>::abs(R[6]) * sc.racket.half_thick - M<T>::abs(R[7]) * sc.racket_obb[0] + (zlo < zhi ? zlo : zhi) -
               sc.hull_margin;
-      if (low <= sc.floor_h[2] + thr && M<T>::abs(s.rp[0]) <= sc.floor_h[0] + 1 && M<T>::abs(s.rp[1]) <= sc.floor_h[1] + 1)
-        bits |= TB_EV_RACKET_LOW;
+      bits |= (low <= sc.floor_h[2] + thr && M<T>::abs(s.rp[0]) <= sc.floor_h[0] + 1 && M<T>::abs(s.rp[1]) <= sc.floor_h[1] + 1)
+                  ? TB_EV_RACKET_LOW : 0;
     }
     if (TB_UNLIKELY(need)) {
       NarrowIn<T> in;
@@ -579,7 +587,6 @@ __device__ __forceinline__ int physics_step(const Scene<T> &sc, St<T> &s, const 
       for (int i = 0; i < 3; ++i) s.bw[i] = s.bw[i] + dt * (-s.bw[i] * kw);
     }
   }
-  T R[9];
   const bool rotating = s.rw[0] != 0 || s.rw[1] != 0 || s.rw[2] != 0 || t_racket[0] != 0 || t_racket[1] != 0 ||
                         t_racket[2] != 0;
   {
@@ -589,7 +596,6 @@ __device__ __forceinline__ int physics_step(const Scene<T> &sc, St<T> &s, const 
       T g = i == 2 ? sc.gravity_z : (T)0;
       s.rv[i] = s.rv[i] + dt * (f_racket[i] * sc.racket_inv_m + g - s.rv[i] * kv);
     }
-    if (rotating) quat_to_mat(s.rq, R);
     if (rotating) {  // the hit env's racket never rotates: no torque is ever applied to it
       T wl[3], tl[3], iw[3], gy[3], al[3], aw[3];
       matT_vec(R, s.rw, wl);
