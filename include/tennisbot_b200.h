@@ -130,7 +130,8 @@ int tb_reset(tb_ctx *ctx, const uint8_t *d_mask, float *d_obs, void *stream);
 int tb_reset_from(tb_ctx *ctx, const double *d_init, const uint8_t *d_mask, float *d_obs, void *stream);
 
 /* ---- step(): swingracket_env.py:75-145, tennisbot_env.py:104-207 (+ p.stepSimulation, p.getContactPoints,
- * Racket.apply_target_action racket.py:92-100, Ball.apply_force objects.py:67-72).  One fused kernel launch.
+ * Racket.apply_target_action racket.py:92-100, Ball.apply_force objects.py:67-72).  Two launches on `stream`:
+ * step_kernel (every env, one substep) and, for SwingRacket, ff_kernel (the queued fast-forward flights).
  * d_actions float32 [N, act_dim]; d_obs float32 [N, obs_dim]; d_reward float32 [N]; d_done uint8 [N];
  * d_terminal_obs float32 [N, obs_dim] written for done envs only (may be NULL); d_events uint8 [N] (may be NULL). */
 int tb_step(tb_ctx *ctx, const float *d_actions, float *d_obs, float *d_reward, uint8_t *d_done,

@@ -1,4 +1,4 @@
-"""TennisBatch: N lock-step envs on one B200, stepped by the fused CUDA kernel behind the C ABI.
+"""TennisBatch: N lock-step envs on one B200, stepped by the CUDA kernels behind the C ABI.
 
 PyTorch is used for device memory and streams only; all arithmetic of the env step happens in
 libtennisbot_b200.so (csrc/tb_kernels.cu).  Replaces, for a batch, what one reference env object does with
@@ -93,7 +93,7 @@ class TennisBatch:
         return self.obs
 
     def step(self, actions, obs=None, reward=None, done=None, terminal_obs=None, events=None):
-        """One env step for all N envs: ONE kernel launch. actions: float32 CUDA tensor [N, act_dim].
+        """One env step for all N envs (step_kernel + ff_kernel on the current stream). actions: float32 CUDA tensor [N, act_dim].
         Returns (obs, reward, done, terminal_obs, events) device tensors (the caller's, or reused internal ones)."""
         if actions.dtype != torch.float32 or not actions.is_cuda or not actions.is_contiguous():
             actions = actions.to(device=self.device, dtype=torch.float32).contiguous()

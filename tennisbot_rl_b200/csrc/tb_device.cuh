@@ -513,10 +513,9 @@ template <typename T> __device__ __forceinline__ void integrate_quat(const Scene
 
 // One stepSimulation(): detect at the start-of-step poses, integrate velocities with Bullet's multibody
 // damping, solve contacts, integrate poses.  Returns the TB_EV_* contact bits getContactPoints would report.
-// known_bits: event bits already latched for this env step (unused since the floor-flag test became branch-free).
 template <typename T, bool WITH_GOAL>
 __device__ __forceinline__ int physics_step(const Scene<T> &sc, St<T> &s, const T *f_racket, const T *t_racket,
-                                            const T *f_ball, int known_bits) {
+                                            const T *f_ball) {
   const T dt = sc.dt, thr = sc.contact_threshold, rb = sc.ball_r;
   ContactSet<T> cs;  // lives in local memory; touched on the rare path only
   int nc = 0, bits = 0;
@@ -760,7 +759,7 @@ __device__ __forceinline__ bool env_substep(const Scene<T> &sc, St<T> &s, const 
       F[1] = -2 * (s.rp[1] - s.aux[1]);
       F[2] = -2 * (s.rp[2] - s.aux[2] - 4);
     }
-    int bits = physics_step<T, true>(sc, s, F, Tq, zero, c.events);
+    int bits = physics_step<T, true>(sc, s, F, Tq, zero);
     int k = ++s.step;
     c.events |= bits;
     if (c.phase == 0) {
@@ -783,7 +782,7 @@ __device__ __forceinline__ bool env_substep(const Scene<T> &sc, St<T> &s, const 
     }
     T Fb[3] = {0, 0, 0};
     if (s.step < 5) { Fb[0] = s.aux[0]; Fb[1] = s.aux[1]; Fb[2] = s.aux[2]; }
-    int bits = physics_step<T, false>(sc, s, F, zero, Fb, 0);
+    int bits = physics_step<T, false>(sc, s, F, zero, Fb);
     int k = ++s.step;
     c.events = bits;
     if (k < 5) { c.done = false; return true; }  // returns False regardless of self.done (tennisbot_env.py:138-139)

@@ -220,9 +220,10 @@ __device__ __forceinline__ void account(WarpStats &ws, bool fin, bool done, int 
 }
 
 // Completion of an env step for one lane: terminal observation, auto-reset, outputs.  The caller stores the state.
+// ob_out != nullptr: hand the observation row back instead of storing it (step_kernel stores whole tiles coalesced).
 template <typename T, int KIND>
 __device__ __forceinline__ void finish_api(const Scene<T> &sc, const StepIO &io, int64_t me, St<T> &s, float reward,
-                                           bool done, int events) {
+                                           bool done, int events, float *ob_out = nullptr) {
   float ob[12];
   pack_obs<T, KIND>(s, ob);
   if (done) {
@@ -237,33 +238,67 @@ __device__ __forceinline__ void finish_api(const Scene<T> &sc, const StepIO &io,
       s.flags |= kFlagDone;
     }
   }
-  store_obs<KIND>(io.obs, me, ob);
+  if (ob_out) {
+#pragma unroll
+    for (int j = 0; j < Dims<KIND>::obs; ++j) ob_out[j] = ob[j];
+  } else {
+    store_obs<KIND>(io.obs, me, ob);
+  }
   io.reward[me] = reward;
   io.done[me] = (uint8_t)done;
   if (io.events) io.events[me] = (uint8_t)events;
 }
 
-template <typename T, int KIND>
-__global__ void __launch_bounds__(kBlock) step_kernel(const __grid_constant__ Scene<T> sc, const __grid_constant__ StepIO io) {
+#ifndef TB_STEP_MINB32
+#define TB_STEP_MINB32 3
+#endif
+#ifndef TB_STEP_MINB64
+#define TB_STEP_MINB64 3
+#endif
+template <typename T> struct StepMinBlocks { static constexpr int v = TB_STEP_MINB32; };
+template <> struct StepMinBlocks<double> { static constexpr int v = TB_STEP_MINB64; };
+
+// STAGE: move the action / observation rows through warp-private shared-memory tiles (see below); chosen by the host
+// when the caller's buffers are pinned host memory, off for buffers in HBM where it only costs registers.
+template <typename T, int KIND, bool STAGE>
+__global__ void __launch_bounds__(kBlock, StepMinBlocks<T>::v) step_kernel(const __grid_constant__ Scene<T> sc, const __grid_constant__ StepIO io) {
   __shared__ unsigned long long sacc[kBlock / 32][TB_NUM_STATS];
   __shared__ int s_cnt[2 * (kBlock / 32)];
   __shared__ unsigned long long s_base[2];
+  // Each warp's 32 action rows come in and its 32 observation rows go out as one contiguous tile through shared
+  // memory (warp-private, __syncwarp only): [N, act] / [N, obs] float32 rows are 24 / 8 / 48 bytes, which per-thread
+  // accesses would turn into strided partial sectors - harmless in HBM behind L2, costly when the caller's buffers
+  // are pinned host memory and every sector is a PCIe transaction (tb_step_host's zero-copy path).
+  constexpr int AD = Dims<KIND>::act, OD = Dims<KIND>::obs;
+  __shared__ __align__(16) float s_tiles[STAGE ? kBlock / 32 : 1][STAGE ? 32 * OD : 4];
   const unsigned full = 0xffffffffu;
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  float *s_tile = s_tiles[STAGE ? wib : 0];
   WarpStats ws;
   ws.init(sacc[wib], lane);
   if (blockIdx.x == 0 && threadIdx.x == 0) { io.queue_ctr_next[0] = 0; io.queue_ctr_next[1] = 0; io.queue_ctr_next[2] = 0; }
 
-  const int64_t me = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+  const int64_t tile0 = (int64_t)blockIdx.x * kBlock + wib * 32, me = tile0 + lane;
   const bool valid = me < io.n;
+  const int rows = io.n - tile0 >= 32 ? 32 : (io.n > tile0 ? (int)(io.n - tile0) : 0);
   T *base = static_cast<T *>(io.state);
   St<T> s;
   StepCtl c = {0, 0, 0, 0.0f, false};
   bool fin = false;
+  float a[8];
+  if (STAGE) {
+    const float *src = io.actions + tile0 * AD;
+    const int nf = rows * AD, nv = nf >> 2;
+    for (int i = lane; i < nv; i += 32) reinterpret_cast<float4 *>(s_tile)[i] = reinterpret_cast<const float4 *>(src)[i];
+    for (int i = (nv << 2) + lane; i < nf; i += 32) s_tile[i] = src[i];
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < AD; ++j) a[j] = valid ? s_tile[lane * AD + j] : 0.0f;
+    __syncwarp();
+  }
   if (valid) {
-    float a[8];
     load_state(base, io.n, me, s);
-    load_action<KIND>(io.actions, me, a);
+    if (!STAGE) load_action<KIND>(io.actions, me, a);
     c.done = s.flags & kFlagDone;
     if (TB_UNLIKELY(io.pid != nullptr)) {
       T pid[8];
@@ -282,7 +317,17 @@ __global__ void __launch_bounds__(kBlock) step_kernel(const __grid_constant__ Sc
   unsigned act_mask = __ballot_sync(full, valid);
   if (lane == 0) ws.acc[TB_STAT_PHYSICS_STEPS] += __popc(act_mask);
   account<T>(ws, fin, c.done, c.hit, c.events, s.step, s.ret);
-  if (valid && fin) finish_api<T, KIND>(sc, io, me, s, c.reward, c.done, c.events);
+  // every env of the warp's tile completed its step (always, except in a launch that feeds the fast-forward): the
+  // rows go out through the tile; otherwise finished envs store their own row and ff_kernel writes the others later
+  const bool whole_tile = STAGE && __all_sync(full, fin || !valid);
+  if (valid && fin) finish_api<T, KIND>(sc, io, me, s, c.reward, c.done, c.events, whole_tile ? s_tile + lane * OD : nullptr);
+  if (whole_tile) {
+    __syncwarp();
+    float *dst = io.obs + tile0 * OD;
+    const int nf = rows * OD, nv = nf >> 2;
+    for (int i = lane; i < nv; i += 32) reinterpret_cast<float4 *>(dst)[i] = reinterpret_cast<const float4 *>(s_tile)[i];
+    for (int i = (nv << 2) + lane; i < nf; i += 32) dst[i] = s_tile[i];
+  }
 
   // envs entering the fast-forward: queue them for ff_kernel (only SwingRacket ever does).  Longest-job-first:
   // a ball the racket has hit flies for up to 775 more substeps and is queued from the FRONT, a ball still in free
@@ -686,6 +731,7 @@ struct tb_ctx {
   unsigned ff_grid = 0;                      // persistent grid of ff_kernel
   int control_mode = TB_CONTROL_FORCE;
   void *pid = nullptr;                       // controller memory, allocated by tb_set_control_mode(TB_CONTROL_PID)
+  bool zero_copy = std::getenv("TB_HOST_STAGING") == nullptr;  // tb_step_host: address pinned host buffers from the kernels
   bool timing = false;                       // tb_set_kernel_timing
   cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
   double ms_step = 0, ms_ff = 0;
@@ -751,7 +797,7 @@ template <typename T> static int ff_grid_size(tb_ctx *c, unsigned *grid) {
   return 0;
 }
 // One env step = step_kernel (+ ff_kernel for SwingRacket) on `stream`.
-static int launch_step(tb_ctx *c, StepIO &io, cudaStream_t stream) {
+static int launch_step(tb_ctx *c, StepIO &io, cudaStream_t stream, bool stage = false) {
   io.queue = c->queue;
   io.queue_ctr = c->queue_ctrs + 3 * c->parity;
   io.queue_ctr_next = c->queue_ctrs + 3 * (c->parity ^ 1);
@@ -759,13 +805,19 @@ static int launch_step(tb_ctx *c, StepIO &io, cudaStream_t stream) {
   const unsigned grid = grid_for(io.n, kBlock);
   const bool swing = c->cfg.env_kind == TB_ENV_SWING;
   if (c->timing) CU(cudaEventRecord(c->ev[0], stream));
+#define TB_LAUNCH_STEP(T, K, SC)                                                        \
+  do {                                                                                 \
+    if (stage) step_kernel<T, K, true><<<grid, kBlock, 0, stream>>>(SC, io);           \
+    else step_kernel<T, K, false><<<grid, kBlock, 0, stream>>>(SC, io);                \
+  } while (0)
   if (c->cfg.precision == TB_F64) {
-    if (swing) step_kernel<double, TB_ENV_SWING><<<grid, kBlock, 0, stream>>>(c->sc64, io);
-    else step_kernel<double, TB_ENV_HIT><<<grid, kBlock, 0, stream>>>(c->sc64, io);
+    if (swing) TB_LAUNCH_STEP(double, TB_ENV_SWING, c->sc64);
+    else TB_LAUNCH_STEP(double, TB_ENV_HIT, c->sc64);
   } else {
-    if (swing) step_kernel<float, TB_ENV_SWING><<<grid, kBlock, 0, stream>>>(c->sc32, io);
-    else step_kernel<float, TB_ENV_HIT><<<grid, kBlock, 0, stream>>>(c->sc32, io);
+    if (swing) TB_LAUNCH_STEP(float, TB_ENV_SWING, c->sc32);
+    else TB_LAUNCH_STEP(float, TB_ENV_HIT, c->sc32);
   }
+#undef TB_LAUNCH_STEP
   c->launches++;
   CU(cudaGetLastError());
   if (c->timing) CU(cudaEventRecord(c->ev[1], stream));
@@ -927,14 +979,18 @@ int tb_reset_from(tb_ctx *c, const double *d_init, const uint8_t *d_mask, float 
   return reset_impl(c, d_init, d_mask, d_obs, stream);
 }
 
-int tb_step(tb_ctx *c, const float *d_actions, float *d_obs, float *d_reward, uint8_t *d_done, float *d_terminal_obs,
-            uint8_t *d_events, void *stream) {
+static int step_impl(tb_ctx *c, const float *d_actions, float *d_obs, float *d_reward, uint8_t *d_done,
+                     float *d_terminal_obs, uint8_t *d_events, void *stream, bool stage) {
   GUARD(c);
   if (!d_actions || !d_obs || !d_reward || !d_done) return fail("%s", "tb_step: actions, obs, reward and done are required");
   StepIO io = make_io(c);
   io.actions = d_actions; io.obs = d_obs; io.reward = d_reward; io.done = d_done; io.term_obs = d_terminal_obs;
   io.events = d_events;
-  return launch_step(c, io, (cudaStream_t)stream);
+  return launch_step(c, io, (cudaStream_t)stream, stage);
+}
+int tb_step(tb_ctx *c, const float *d_actions, float *d_obs, float *d_reward, uint8_t *d_done, float *d_terminal_obs,
+            uint8_t *d_events, void *stream) {
+  return step_impl(c, d_actions, d_obs, d_reward, d_done, d_terminal_obs, d_events, stream, false);
 }
 
 int tb_rollout(tb_ctx *c, int action_mode, int k_steps, float *d_obs, float *d_reward_sum, int32_t *d_done_count, void *stream) {
@@ -1010,13 +1066,36 @@ int tb_reset_host(tb_ctx *c, const uint8_t *h_mask, float *h_obs) {
   return 0;
 }
 
+// Device alias of a host buffer the kernels can address directly (pinned + mapped memory under unified virtual
+// addressing: cudaHostAlloc / torch pin_memory), or nullptr for pageable memory.
+static void *mapped_alias(const void *h) {
+  if (!h) return nullptr;
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, h) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  return at.type == cudaMemoryTypeHost ? at.devicePointer : nullptr;
+}
+
 int tb_step_host(tb_ctx *c, const float *h_actions, float *h_obs, float *h_reward, uint8_t *h_done, float *h_terminal_obs,
                  uint8_t *h_events) {
   GUARD(c);
   if (!h_actions || !h_obs || !h_reward || !h_done) return fail("%s", "tb_step_host: actions, obs, reward and done are required");
-  if (ensure_staging(c)) return 1;
   size_t n = (size_t)c->cfg.num_envs, od = (size_t)tb_obs_dim(c->cfg.env_kind), ad = (size_t)tb_act_dim(c->cfg.env_kind);
   cudaStream_t s = c->own_stream;
+  if (c->zero_copy) {
+    // Pinned buffers: the kernels read the actions from and write the results to host memory themselves.  The
+    // two PCIe directions then run concurrently and overlap with the compute, instead of H2D -> kernels -> D2H.
+    const float *za = (const float *)mapped_alias(h_actions);
+    float *zo = (float *)mapped_alias(h_obs), *zr = (float *)mapped_alias(h_reward);
+    uint8_t *zd = (uint8_t *)mapped_alias(h_done);
+    float *zt = (float *)mapped_alias(h_terminal_obs);
+    uint8_t *ze = (uint8_t *)mapped_alias(h_events);
+    if (za && zo && zr && zd && (zt || !h_terminal_obs) && (ze || !h_events)) {
+      if (step_impl(c, za, zo, zr, zd, zt, ze, s, true)) return 1;
+      CU(cudaStreamSynchronize(s));
+      return 0;
+    }
+  }
+  if (ensure_staging(c)) return 1;
   CU(cudaMemcpyAsync(c->d_actions, h_actions, n * ad * sizeof(float), cudaMemcpyHostToDevice, s));
   if (tb_step(c, c->d_actions, c->d_obs, c->d_reward, c->d_done, h_terminal_obs ? c->d_term : nullptr,
               h_events ? c->d_events : nullptr, s))
