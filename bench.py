@@ -10,7 +10,7 @@ A "step" is one pass of the hot path over the batch: one agent-visible env step 
 per-GPU slice: 1 048 576 SwingRacket-v0 envs per GPU, uniform random actions, initial states from the env's own
 reset ranges.  Every SwingRacket episode is exactly 26 agent steps (25 one-substep control steps + the fast-forward
 step), so the timed region must cover whole episodes to weight the two kinds of step correctly:
-  --steps a multiple of 26 (default 104): lock-step episodes (all envs reset together, as a VecEnv starts), the
+  --steps a multiple of 26 (default 1040 = 40 episodes, ~0.4 s): lock-step episodes (all envs reset together, as a VecEnv starts), the
       timed region starts on an episode boundary and spans K/26 whole episodes;
   any other --steps: episode phases are staggered per 128-env group (group g starts g mod 26 steps late) so that
       every launch carries the same 25:1 mix and any K is representative (slower: each launch then waits for its own
@@ -43,7 +43,7 @@ GROUP = 128
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=104)
+    ap.add_argument("--steps", type=int, default=1040)
     ap.add_argument("--warmup", type=int, default=26)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--env", default="SwingRacket-v0", choices=["SwingRacket-v0", "Tennisbot-v0"])
@@ -59,40 +59,50 @@ def parse():
 
 
 # ---------------------------------------------------------------------------------------------- helpers
-class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons while the timed region runs (B200_PROFILING.md's clocks line)."""
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons while the timed region runs (B200_PROFILING.md's clocks line), one
+    long-running `nvidia-smi -lms 50` whose rows between start() and stop() are kept."""
 
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,power.draw")
 
     def __init__(self, index):
-        super().__init__(daemon=True)
-        self.index, self.rows, self._stop_evt = index, [], threading.Event()
+        self.rows, self.proc, self.thread = [], None, None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            return
+        self.keep = False
+        self.thread = threading.Thread(target=self._pump, daemon=True)
+        self.thread.start()
 
-    def run(self):
-        while not self._stop_evt.is_set():
-            try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                parts = [p.strip() for p in out.strip().split(",")]
-                if len(parts) >= 6:
+    def _pump(self):
+        for line in self.proc.stdout:
+            if self.keep:
+                parts = [p.strip() for p in line.strip().split(",")]
+                if len(parts) >= 7:
                     self.rows.append(parts)
-            except Exception:
-                pass
-            self._stop_evt.wait(0.2)
+
+    def start(self):
+        time.sleep(0.15)  # let nvidia-smi reach its sampling loop
+        self.keep = True
 
     def stop(self):
-        self._stop_evt.set()
-        self.join(timeout=6)
+        self.keep = False
+        if self.proc is not None:
+            self.proc.terminate()
         sm = sorted(int(r[0]) for r in self.rows if r[0].isdigit())
         reasons = set()
         for r in self.rows:
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[2:6]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
+        watts = [float(r[6]) for r in self.rows if r[6].replace(".", "", 1).isdigit()]
         return {"sm_mhz": sm[len(sm) // 2] if sm else None,
                 "sm_max_mhz": int(self.rows[0][1]) if self.rows and self.rows[0][1].isdigit() else None,
-                "reasons": sorted(reasons), "samples": len(self.rows)}
+                "reasons": sorted(reasons), "samples": len(self.rows), "power_w_max": max(watts) if watts else None}
 
 
 def measured_peak():
@@ -301,7 +311,7 @@ def run_b200(args, rank, world):
                              "ff_kernel": {"ms_per_launch": ms_b / max(nk, 1), "bound": "alu/latency (fast-forward substeps; see profiles/)",
                                            "share_of_step_time": ms_b / max(ms_a + ms_b, 1e-9)}}},
             "e2e": {"value": total_envs * args.e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h, "steps": args.e2e_steps, "api": "TennisBatch.step_host -> tb_step_host (pinned host buffers)"},
+                    "d2h_bytes_per_step": d2h, "steps": args.e2e_steps, "api": "TennisBatch.step_host -> tb_step_host: pinned host buffers in and out; the kernels read the actions from and write obs/reward/done to host memory over PCIe themselves (both directions concurrent with the compute)"},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "episode_stats": {"episodes": int(st[0]), "mean_length": float(st[1]) / max(int(st[0]), 1),

@@ -135,3 +135,50 @@ def test_pid_control_mode_parity(oracle_lib, env):
     assert rep.event_mismatch_hard == 0 and rep.event_mismatch_near == 0
     assert rep.max_state_err < TOL_F64_STATE and rep.max_obs_err < TOL_F64_OUT
     np.testing.assert_array_equal(b.read_stats(), o.read_stats())
+
+
+@pytest.mark.parametrize("n", [1, 31, 33, 127, 129, 1000])
+@pytest.mark.parametrize("env", ["SwingRacket-v0", "Tennisbot-v0"])
+def test_ragged_batch_sizes(oracle_lib, env, n):
+    """Batch sizes that do not fill a warp / a CTA / the staging tiles: same bars as the full-size f64 test, through
+    both the device-pointer entry point and the host-buffer one (zero-copy tiles with partial rows)."""
+    b, o = _make(env, n, "f64", 2, oracle_lib)
+    np.testing.assert_array_equal(b.reset().cpu().numpy(), o.reset())
+    rng = np.random.default_rng(n)
+    steps = 30 if env == "SwingRacket-v0" else 40
+    rep, valid = run_parity(b, o, steps, lambda t, _obs: rng.uniform(-1, 1, (n, o.act_dim)), band=0.0, check_state_every=10)
+    assert rep.event_mismatch_hard == 0 and rep.max_state_err < TOL_F64_STATE and rep.max_obs_err < TOL_F64_OUT
+    for t in range(30):  # host-buffer path, crossing the swing env's fast-forward step again
+        a = rng.uniform(-1, 1, (n, o.act_dim)).astype(np.float32)
+        hb = b.step_host(a)
+        ref = o.step(a)
+        np.testing.assert_array_equal(hb["done"], ref["done"])
+        np.testing.assert_array_equal(hb["events"], ref["events"])
+        np.testing.assert_allclose(hb["obs"], ref["obs"], atol=TOL_F64_OUT)
+        np.testing.assert_allclose(hb["reward"], ref["reward"], atol=TOL_F64_OUT)
+        d = ref["done"] != 0
+        np.testing.assert_allclose(hb["terminal_obs"][d], ref["terminal_obs"][d], atol=TOL_F64_OUT)
+    np.testing.assert_array_equal(b.read_stats(), o.read_stats())
+
+
+def test_host_staging_fallback_matches(oracle_lib):
+    """tb_step_host with PAGEABLE numpy buffers takes the staged-copy path; results equal the zero-copy path's."""
+    import ctypes as C
+
+    from tennisbot_rl_b200 import _lib
+
+    n = 300
+    b, o = _make("SwingRacket-v0", n, "f64", 8, oracle_lib)
+    b.reset()
+    o.reset()
+    rng = np.random.default_rng(4)
+    obs, rew, done = np.zeros((n, 6), np.float32), np.zeros(n, np.float32), np.zeros(n, np.uint8)
+    vp = C.c_void_p
+    for t in range(30):
+        a = rng.uniform(-1, 1, (n, 6)).astype(np.float32)
+        _lib.check(b.lib.tb_step_host(b.h, a.ctypes.data_as(vp), obs.ctypes.data_as(vp), rew.ctypes.data_as(vp),
+                                      done.ctypes.data_as(vp), None, None))
+        ref = o.step(a)
+        np.testing.assert_array_equal(done, ref["done"])
+        np.testing.assert_allclose(obs, ref["obs"], atol=TOL_F64_OUT)
+        np.testing.assert_allclose(rew, ref["reward"], atol=TOL_F64_OUT)
