@@ -39,7 +39,13 @@ template <> struct M<float> {
 };
 template <> struct M<double> {
   static __device__ __forceinline__ double sqrt(double x) { return ::sqrt(x); }
-  static __device__ __forceinline__ double sqrt_fast(double x) { return ::sqrt(x); }
+  // Speed norms that only feed the damping factor k (1 + |v|) need ~1e-10, not the last bit: float rsqrt estimate
+  // (2^-22) + one Newton step in double = 1e-13 relative, half the instructions of the IEEE square root.
+  static __device__ __forceinline__ double sqrt_fast(double x) {
+    double y = (double)rsqrtf((float)x);
+    y = y * (1.5 - 0.5 * x * y * y);
+    return x > 1e-30 ? x * y : 0.0;
+  }
   static __device__ __forceinline__ double rsqrt(double x) { return 1.0 / ::sqrt(x); }
   static __device__ __forceinline__ double abs(double x) { return fabs(x); }
   static __device__ __forceinline__ void sincos(double x, double *s, double *c) { ::sincos(x, s, c); }
