@@ -10,11 +10,12 @@ A "step" is one pass of the hot path over the batch: one agent-visible env step 
 per-GPU slice: 1 048 576 SwingRacket-v0 envs per GPU, uniform random actions, initial states from the env's own
 reset ranges.  Every SwingRacket episode is exactly 26 agent steps (25 one-substep control steps + the fast-forward
 step), so the timed region must cover whole episodes to weight the two kinds of step correctly:
-  --steps a multiple of 26 (default 1040 = 40 episodes, ~0.4 s): lock-step episodes (all envs reset together, as a VecEnv starts), the
-      timed region starts on an episode boundary and spans K/26 whole episodes;
-  any other --steps: episode phases are staggered per 128-env group (group g starts g mod 26 steps late) so that
-      every launch carries the same 25:1 mix and any K is representative (slower: each launch then waits for its own
-      800-substep time-out flights).
+Episodes run in lock step (all envs reset together, as a VecEnv starts).  With --steps a multiple of 26 (default
+1040 = 40 episodes, ~0.4 s) the timed region spans K/26 whole episodes.  For any other K the region is placed so
+that it ENDS right after a fast-forward step and therefore contains ceil(K/26) of them: the expensive step is then
+weighted at least as heavily as in whole episodes and the number can only come out pessimistic.  `--stagger on`
+instead offsets the episode phases per 128-env group (g mod 26) so that every launch carries the same 25:1 mix
+(slower: each launch then waits for its own 800-substep time-out flights).
 """
 import argparse
 import json
@@ -51,9 +52,8 @@ def parse():
     ap.add_argument("--precision", default="f64", choices=["f32", "f64"])
     ap.add_argument("--e2e-steps", type=int, default=26)
     ap.add_argument("--cpu-sample-envs", type=int, default=65536)
-    ap.add_argument("--stagger", default="auto", choices=["auto", "on", "off"],
-                    help="episode phases: off = lock-step (all envs reset together), on = staggered per 128-env group; "
-                         "auto = off when --steps is a multiple of the 26-step episode, else on (uniform launches)")
+    ap.add_argument("--stagger", default="off", choices=["on", "off"],
+                    help="episode phases: off = lock-step (all envs reset together), on = staggered per 128-env group")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     return ap.parse_args()
 
@@ -103,6 +103,17 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2] if sm else None,
                 "sm_max_mhz": int(self.rows[0][1]) if self.rows and self.rows[0][1].isdigit() else None,
                 "reasons": sorted(reasons), "samples": len(self.rows), "power_w_max": max(watts) if watts else None}
+
+
+def measured_traffic(env, precision, n):
+    """DRAM bytes per env step (both kernels) from the committed ncu capture of the same workload, else None."""
+    p = ROOT / "profiles" / "r1_traffic.json"
+    if env == "SwingRacket-v0" and precision == "f64" and n == 1 << 20 and p.exists():
+        try:
+            return float(json.loads(p.read_text())["dram_bytes_per_env_step_launch_pair"])
+        except Exception:
+            pass
+    return None
 
 
 def measured_peak():
@@ -214,12 +225,13 @@ def run_b200(args, rank, world):
     # action buffers: a ring of pre-drawn U(-1,1) batches resident in HBM (synthetic actions = action_space.sample())
     ring = [torch.empty((n, batch.act_dim), dtype=torch.float32, device=dev).uniform_(-1, 1) for _ in range(4)]
     pre_launch = 0
-    stagger = args.stagger == "on" or (args.stagger == "auto" and args.steps % EPISODE_STEPS != 0 and args.env == "SwingRacket-v0")
+    stagger = args.stagger == "on" and args.env == "SwingRacket-v0"
     if not stagger:
         batch.reset()
     else:
         pre_launch = stagger_phases(batch, torch)
-    align = 0 if stagger or args.env != "SwingRacket-v0" else (-args.warmup) % EPISODE_STEPS
+    # lock-step: start the timed region at episode phase (-K mod 26) so that it ends right after a fast-forward step
+    align = 0 if stagger or args.env != "SwingRacket-v0" else (-args.steps - args.warmup) % EPISODE_STEPS
     for w in range(args.warmup + align):  # `align` extra untimed steps put the timed region on an episode boundary
         batch.step(ring[w % len(ring)])
     if dist is not None:
@@ -297,12 +309,14 @@ def run_b200(args, rank, world):
             "config": {"workload": f"{args.env} batched {n} envs per GPU (config 5 slice), uniform random actions, "
                                    f"reset ranges of the env, auto-reset",
                        "envs_per_gpu": n, "total_envs": total_envs,
-                       "phase_stagger": f"per {GROUP}-env group, g mod {EPISODE_STEPS}" if stagger else "none (lock-step episodes, timed region = whole episodes)",
+                       "phase_stagger": f"per {GROUP}-env group, g mod {EPISODE_STEPS}" if stagger else
+                       f"none: lock-step episodes, timed region holds {-(-args.steps // EPISODE_STEPS)} fast-forward steps in {args.steps} steps",
                        "alignment_steps": align,
                        "l2_policy": "working set per launch %.0f MB > 126 MB L2 (inputs larger than L2)" % (n * algo / 1e6),
                        "parallelism": f"env-sharded x{world}, no data-path collective; int64[10] stats all-reduce per {EPISODE_STEPS} steps"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_env_step": algo,
+                         "traffic": measured_traffic(args.env, args.precision, n), "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": n * algo, "algorithmic_bytes_per_env_step": algo,
                          "scope": "whole env step = step_kernel + ff_kernel, algorithmic bytes of the step / mean step time",
                          "kernels": {
                              "step_kernel": {"ms_per_launch": ms_a / max(nk, 1), "achieved_gbs": n * algo / (ms_a / max(nk, 1) * 1e-3) / 1e9,
