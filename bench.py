@@ -234,8 +234,9 @@ def run_b200(args, rank, world):
     align = 0 if stagger or args.env != "SwingRacket-v0" else (-args.steps - args.warmup) % EPISODE_STEPS
     for w in range(args.warmup + align):  # `align` extra untimed steps put the timed region on an episode boundary
         batch.step(ring[w % len(ring)])
+    reduced = stats.clone()  # the all-reduce works on a snapshot: the live vector keeps accumulating in the kernels
     if dist is not None:
-        dist.all_reduce(stats)  # warm the NCCL communicator
+        dist.all_reduce(reduced)  # warm the NCCL communicator
     batch.read_stats(clear=True)
     l0 = batch.launch_count()
 
@@ -248,7 +249,8 @@ def run_b200(args, rank, world):
     for k in range(args.steps):
         batch.step(ring[k % len(ring)])
         if dist is not None and (k + 1) % EPISODE_STEPS == 0:
-            dist.all_reduce(stats)  # per-iteration reduction of the episode statistics (10 x int64)
+            reduced.copy_(stats)
+            dist.all_reduce(reduced)  # per-iteration reduction of the episode statistics (10 x int64)
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
@@ -259,11 +261,9 @@ def run_b200(args, rank, world):
         t = torch.tensor([ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
-        st_local = torch.from_numpy(batch.read_stats()).to(dev)
-        # steps after the last in-loop all-reduce hold un-reduced increments; a fresh sum is exact either way
-        stats.copy_(st_local)
-        dist.all_reduce(stats)
-        st = stats.cpu().numpy()
+        reduced.copy_(stats)
+        dist.all_reduce(reduced)
+        st = reduced.cpu().numpy()
 
     # ---- per-kernel device times over one more episode (events inside the library, stream synchronised per step:
     #      outside the timed region by construction)

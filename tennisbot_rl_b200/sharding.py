@@ -17,7 +17,9 @@ def shard_range(total_envs, rank, world):
 
 
 def all_reduce_stats(stats, group=None):
-    """Sum the per-rank statistics vectors in place. `stats`: int64 tensor (CUDA under NCCL, CPU under gloo)."""
+    """Sum the per-rank statistics vectors in place. `stats`: int64 tensor (CUDA under NCCL, CPU under gloo).
+    Pass a SNAPSHOT (`batch.stats_tensor().clone()`): the live vector keeps accumulating inside the kernels, and
+    reducing it in place would fold the other ranks' counts into this rank's accumulator."""
     import torch.distributed as dist
 
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
