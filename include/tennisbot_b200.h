@@ -159,6 +159,12 @@ int tb_step_host(tb_ctx *ctx, const float *h_actions, float *h_obs, float *h_rew
 /* number of kernels this context has launched (bench.py's gpu_launches) */
 int tb_launch_count(tb_ctx *ctx, int64_t *launches);
 
+/* Diagnostics of the most recent SwingRacket fast-forward (tb_step's second kernel): out[0] = rounds, out[1] = envs that
+ * took the generic full-substep path at least once, out[2 + 2r], out[3 + 2r] = nanoseconds spent in round r's full and
+ * fast phases (r < 6), out[14] = nanoseconds of the finishing pass, out[15] = non-zero if a grid barrier gave up.
+ * Synchronises the context's last stream work.  h_out: 16 x int64. */
+int tb_ff_diagnostics(tb_ctx *ctx, int64_t *h_out);
+
 /* Per-kernel device timing for roofline reports.  While enabled, every tb_step brackets its two kernels with CUDA
  * events on the launch stream and synchronises the stream to accumulate their durations (so do not enable it
  * inside a throughput measurement).  tb_get_kernel_timing returns the accumulated milliseconds of step_kernel and

@@ -25,7 +25,7 @@ EXPORTS = (
     "tb_last_error", "tb_abi_version", "tb_obs_dim", "tb_act_dim", "tb_num_params", "tb_param_name",
     "tb_scene_constant", "tb_create", "tb_destroy", "tb_set_param", "tb_get_param", "tb_set_control_mode", "tb_reset", "tb_reset_from",
     "tb_step", "tb_rollout", "tb_get_state", "tb_set_state", "tb_stats_device_ptr", "tb_read_stats",
-    "tb_reset_host", "tb_step_host", "tb_launch_count", "tb_set_kernel_timing", "tb_get_kernel_timing",
+    "tb_reset_host", "tb_step_host", "tb_launch_count", "tb_ff_diagnostics", "tb_set_kernel_timing", "tb_get_kernel_timing",
 )
 
 
@@ -75,6 +75,7 @@ def load():
     L.tb_reset_host.argtypes = [vp, vp, vp]
     L.tb_step_host.argtypes = [vp, vp, vp, vp, vp, vp, vp]
     L.tb_launch_count.argtypes = [vp, C.POINTER(i64)]
+    L.tb_ff_diagnostics.argtypes = [vp, C.POINTER(i64)]
     L.tb_set_kernel_timing.argtypes = [vp, i32]
     L.tb_get_kernel_timing.argtypes = [vp, C.POINTER(dbl), C.POINTER(dbl), C.POINTER(i64)]
     _lib = L

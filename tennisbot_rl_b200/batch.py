@@ -145,6 +145,14 @@ class TennisBatch:
         _lib.check(self.lib.tb_launch_count(self.h, C.byref(v)))
         return v.value
 
+    def ff_diagnostics(self):
+        """int64[16] record of the most recent fast-forward launch (see tb_ff_diagnostics)."""
+        import numpy as np
+
+        out = np.zeros(16, np.int64)
+        _lib.check(self.lib.tb_ff_diagnostics(self.h, out.ctypes.data_as(C.POINTER(C.c_int64))))
+        return out
+
     def set_kernel_timing(self, enabled):
         _lib.check(self.lib.tb_set_kernel_timing(self.h, int(bool(enabled))))
 

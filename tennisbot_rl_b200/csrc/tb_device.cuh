@@ -32,6 +32,7 @@ template <> struct M<float> {
     asm("sqrt.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
   }
+  static __device__ __forceinline__ float norm_damp(float x2) { return sqrt_fast(x2); }
   static __device__ __forceinline__ float rsqrt(float x) { return 1.0f / sqrtf(x); }
   static __device__ __forceinline__ float abs(float x) { return fabsf(x); }
   static __device__ __forceinline__ void sincos(float x, float *s, float *c) { sincosf(x, s, c); }
@@ -45,6 +46,15 @@ template <> struct M<double> {
     double y = (double)rsqrtf((float)x);
     y = y * (1.5 - 0.5 * x * y * y);
     return x > 1e-30 ? x * y : 0.0;
+  }
+  // the same without the zero test: the float estimate is taken of max(x, 1e-37), so x = 0 gives 0 and |v| below
+  // 3e-19 is off by at most its own size (it enters only as 1 + |v|)
+  static __device__ __forceinline__ double norm_damp(double x2) {
+    float e;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fmaxf((float)x2, 1e-37f)));
+    double y = (double)e;
+    y = y * (1.5 - 0.5 * x2 * y * y);
+    return x2 * y;
   }
   static __device__ __forceinline__ double rsqrt(double x) { return 1.0 / ::sqrt(x); }
   static __device__ __forceinline__ double abs(double x) { return fabs(x); }
@@ -109,6 +119,26 @@ template <typename T> struct Scene {
   T racket_box[3];  // outline bounding box in the COM frame: max |y|, min z, max z (grown by 1e-6: reject only)
   T racket_obb[3];  // the same box, exact: TB_EV_RACKET_LOW
   T racket_obb_radius;  // distance of its farthest corner from the COM (pre-check of the same test)
+  // derived constants of the fast-forward substep (ff_substep), formed on the host in double
+  T ff_hack[3];    // dt / m_racket * (-50, -2, -2): the force law of swingracket_env.py:135-141 as velocity per metre
+  T ff_gyro[3];    // dt * gyro * (I_k - I_j) / I_i: Euler's equations in the principal (= body) frame
+  T ff_dtg;        // dt * gravity_z
+  T ff_kl, ff_ka;  // dt * lin_damping, dt * ang_damping
+  T ff_qx2;        // dt^2 / 4
+  T ff_slab;       // |face-normal coordinate| of the ball beyond which the racket is out of reach (grown: reject only)
+  T ff_low_z;      // racket COM height above which TB_EV_RACKET_LOW cannot fire
+  T ff_ball_z;     // ball height above which floor, net and goal are all out of reach
+  unsigned vmax2_hi;  // high word of max_coord_vel^2 in T's format (limit test on |omega|^2)
+  // ff_fast's "this substep needs the full treatment" predicates (all grown: they may only park a lane for nothing)
+  T ffp_racket_r2;             // (hull bounding radius + reach)^2
+  T ffp_floor[3], ffp_net[3];  // half extents + reach
+  T ffp_goal_z, ffp_goal_r2;   // goal half height + reach, (goal radius + reach)^2
+  T ffp_a2;                    // |omega|^2 above which the short half-angle series or the velocity limit is in doubt
+  T ffp_v2;                    // squared speed above which a coordinate could reach the velocity limit within a substep
+  T ffp_face[3];               // the floor's top face without its margin rim: x, y half extents and the core's top
+  T ffp_low, ffp_court[2];     // TB_EV_RACKET_LOW: floor top + contact threshold; court half extents + 1
+  T ffp_box[3];                // racket outline bounding box + reach (max |y|, min z, max z), grown
+  T ffl_inv_dt, ffl_erp_dt, ffl_m, ffl_jinv_t;  // landing hook: 1/dt, erp/dt, ball mass, 1/(1/m + r^2/I)
   Prism<T, kRacketEdges> racket;
   Prism<T, kGoalEdges> goal;
 };
@@ -165,26 +195,35 @@ template <typename T> __device__ __forceinline__ void matT_vec(const T *R, const
 // Distance from (t; u,v) to a convex prism core: polygon in (u,v), extruded +-half_thick along t.
 // n = unit normal core -> point as (nt,nu,nv); q = closest core point.  Inside the core the minimum
 // translation axis (face vs outline) stands in for Bullet's EPA.
+// Two passes over the outline: which side of every edge line the point is on (cheap; the signed distance to any
+// edge line is a lower bound of the distance to the polygon, so beyond `far` the pass's maximum is returned as is,
+// n and q unset), and - only for a point outside the outline but within `far` - the closest point on its edges.
 template <typename T, int NE>
-__device__ __noinline__ T prism_distance(const Prism<T, NE> &pr, T t, T u, T v, T *n, T *q) {
-  T best_d2 = M<T>::inf(), bq0 = 0, bq1 = 0, max_side = -M<T>::inf();
+__device__ __noinline__ T prism_distance(const Prism<T, NE> &pr, T t, T u, T v, T far, T *n, T *q) {
+  T max_side = -M<T>::inf();
   int max_edge = 0;
-#pragma unroll 1
+#pragma unroll 2
   for (int i = 0; i < NE; ++i) {
     const Edge<T> &e = pr.e[i];
-    T ru = u - e.ax, rv = v - e.ay;
-    T side = ru * e.nx + rv * e.ny;
+    T side = (u - e.ax) * e.nx + (v - e.ay) * e.ny;
     if (side > max_side) { max_side = side; max_edge = i; }
-    T s = (ru * e.ex + rv * e.ey) * e.inv_len2;
-    s = s < 0 ? (T)0 : (s > 1 ? (T)1 : s);
-    T q0 = e.ax + s * e.ex, q1 = e.ay + s * e.ey;
-    T d0 = u - q0, d1 = v - q1;
-    T d2 = d0 * d0 + d1 * d1;
-    if (d2 < best_d2) { best_d2 = d2; bq0 = q0; bq1 = q1; }
   }
+  if (max_side > far) return max_side;
   T et = M<T>::abs(t) - pr.half_thick;
   T st = t < 0 ? (T)-1 : (T)1;
   if (max_side > 0) {
+    T best_d2 = M<T>::inf(), bq0 = 0, bq1 = 0;
+#pragma unroll 1
+    for (int i = 0; i < NE; ++i) {
+      const Edge<T> &e = pr.e[i];
+      T ru = u - e.ax, rv = v - e.ay;
+      T s = (ru * e.ex + rv * e.ey) * e.inv_len2;
+      s = s < 0 ? (T)0 : (s > 1 ? (T)1 : s);
+      T q0 = e.ax + s * e.ex, q1 = e.ay + s * e.ey;
+      T d0 = u - q0, d1 = v - q1;
+      T d2 = d0 * d0 + d1 * d1;
+      if (d2 < best_d2) { best_d2 = d2; bq0 = q0; bq1 = q1; }
+    }
     T du = u - bq0, dv = v - bq1;
     if (et > 0) {
       T dist = M<T>::sqrt(et * et + best_d2);
@@ -422,7 +461,7 @@ __device__ __noinline__ int narrow_phase(const Scene<T> &sc, int need, const Nar
     if (!(M<T>::abs(pl[0]) - sc.racket.half_thick > reach || M<T>::abs(pl[1]) - sc.racket_box[0] > reach ||
           pl[2] - sc.racket_box[2] > reach || sc.racket_box[1] - pl[2] > reach)) {
       T nl[3], ql[3];
-      T dc = prism_distance<T, kRacketEdges>(sc.racket, pl[0], pl[1], pl[2], nl, ql);
+      T dc = prism_distance<T, kRacketEdges>(sc.racket, pl[0], pl[1], pl[2], reach * (T)1.0001, nl, ql);
       T d = dc - (sc.ball_r + sc.hull_margin);
       if (d <= thr) {
         Contact<T> &k = cs->c[nc++];
@@ -453,7 +492,8 @@ __device__ __noinline__ int narrow_phase(const Scene<T> &sc, int need, const Nar
   }
   if (WITH_GOAL && (need & kNeedGoal)) {
     T nl[3], ql[3];
-    T dc = prism_distance<T, kGoalEdges>(sc.goal, in->bp[2], in->bp[0] - in->goal[0], in->bp[1] - in->goal[1], nl, ql);
+    T dc = prism_distance<T, kGoalEdges>(sc.goal, in->bp[2], in->bp[0] - in->goal[0], in->bp[1] - in->goal[1],
+                                         (sc.ball_r + sc.hull_margin + thr) * (T)1.0001, nl, ql);
     T d = dc - (sc.ball_r + sc.hull_margin);
     if (d <= thr) {
       Contact<T> &k = cs->c[nc++];
@@ -488,6 +528,13 @@ __device__ __forceinline__ void sinc_cos_x2(double x2, double *sinc, double *c) 
          x2 * (1.0 / 479001600.0 + x2 * (-1.0 / 87178291200.0 + x2 * (1.0 / 20922789888000.0 +
          x2 * (-1.0 / 6402373705728000.0)))))))));
   }
+}
+// the short branch alone (x^2 < 2.5e-3, i.e. |omega| < 24 rad/s)
+__device__ __forceinline__ void sinc_cos_short(float x2, float *sinc, float *c) { sinc_cos_x2(x2, sinc, c); }
+__device__ __forceinline__ void sinc_cos_short(double x2, double *sinc, double *c) {
+  // first dropped terms at x2 = 2.5e-3: 2.4e-21 and 2.0e-25
+  *sinc = 1.0 + x2 * (-1.0 / 6 + x2 * (1.0 / 120 + x2 * (-1.0 / 5040 + x2 * (1.0 / 362880))));
+  *c = 1.0 + x2 * (-0.5 + x2 * (1.0 / 24 + x2 * (-1.0 / 720 + x2 * (1.0 / 40320 + x2 * (-1.0 / 3628800)))));
 }
 __device__ __forceinline__ float fast_rsqrt(float x) {
   float y = rsqrtf(x);
@@ -740,6 +787,7 @@ struct StepCtl {
   int phase, events, hit;
   float reward;
   bool done;
+  int last;  // contact bits of the most recent substep alone (ff_substep)
 };
 
 // One physics substep of the env step in flight plus the env logic that follows it.  Returns true when the
@@ -802,6 +850,382 @@ __device__ __forceinline__ bool env_substep(const Scene<T> &sc, St<T> &s, const 
     c.reward = (float)reward;
     return true;
   }
+}
+
+// ------------------------------------------------------------------------------------------------ fast-forward
+// SwingRacket's 26th step (swingracket_env.py:105-141) repeats the same torque-free substep up to 775 times, so it
+// has its own restatement of physics_step + the env logic, equal to env_substep's phases 1 and 2 in exact arithmetic
+// and to ~1e-16 per substep in floating point, at half the double-precision work:
+//   * the racket's angular velocity is carried in the BODY frame (s.rw holds R^T omega between ff_enter and ff_leave).
+//     With no torque, omega_body <- omega_body + dt * alpha_body(omega_body) is closed: the pose update rotates
+//     about omega itself, which leaves R^T omega unchanged; and exp(omega dt) q = q exp(omega_body dt).  No rotation
+//     matrix is needed for the dynamics at all.  The principal axes are the body axes, so the gyroscopic term is
+//     three products with host-side constants;
+//   * damping enters as one factor per body, v <- v (1 - dt k (1 + |v|)) + dt g, the force law as a velocity
+//     increment per metre;
+//   * detection evaluates one coordinate each first: the ball's face-normal coordinate in the racket frame (one
+//     column of R), its height against floor / net / goal, the racket's COM height against TB_EV_RACKET_LOW.  All
+//     three rejects are conservative; whatever passes runs the same exact tests as physics_step.
+template <typename T> struct FfRare {
+  T rq[4], bv[3], bw[3], rv[3], wl[3];  // in/out: pose + velocities after force integration (omega in the body frame)
+};
+__device__ __forceinline__ bool nonzero3(const float *a) {
+  return ((__float_as_uint(a[0]) | __float_as_uint(a[1]) | __float_as_uint(a[2])) & 0x7fffffffu) != 0;
+}
+__device__ __forceinline__ bool nonzero3(const double *a) {
+  unsigned hi = (unsigned)(__double2hiint(a[0]) | __double2hiint(a[1]) | __double2hiint(a[2])) & 0x7fffffffu;
+  unsigned lo = (unsigned)(__double2loint(a[0]) | __double2loint(a[1]) | __double2loint(a[2]));
+  return (hi | lo) != 0;
+}
+// Rare continuation of a substep: contact solve and / or the exact +-max_coord_vel clamp, both of which act on the
+// world-frame angular velocity.  Out of line; data crosses through FfRare only.
+template <typename T>
+__device__ __noinline__ void ff_rare(const Scene<T> &sc, const ContactSet<T> *cs, int nc, FfRare<T> *io) {
+  T R[9], w[3];
+  quat_to_mat(io->rq, R);
+  mat_vec(R, io->wl, w);
+  const T vmax = sc.max_coord_vel;
+  T bv[3] = {io->bv[0], io->bv[1], io->bv[2]}, bw[3] = {io->bw[0], io->bw[1], io->bw[2]};
+  T rv[3] = {io->rv[0], io->rv[1], io->rv[2]};
+  clamp_velocities(bv, bw, rv, w, vmax, sc.vmax_hi);
+  if (nc > 0) {
+    SolveIO<T> so;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { so.bv[i] = bv[i]; so.bw[i] = bw[i]; so.rv[i] = rv[i]; so.rw[i] = w[i]; }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) so.rq[i] = io->rq[i];
+    solve_contacts(sc, cs, nc, &so);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { bv[i] += so.dvb[i]; bw[i] += so.dwb[i]; rv[i] += so.dva[i]; w[i] += so.dwa[i]; }
+    clamp_velocities(bv, bw, rv, w, vmax, sc.vmax_hi);
+  }
+  T wl[3];
+  matT_vec(R, w, wl);
+#pragma unroll
+  for (int i = 0; i < 3; ++i) { io->bv[i] = bv[i]; io->bw[i] = bw[i]; io->rv[i] = rv[i]; io->wl[i] = wl[i]; }
+}
+
+// world <-> body frame of the racket's angular velocity, once per env on either side of the fast-forward
+template <typename T> __device__ __forceinline__ void ff_enter(St<T> &s) {
+  T R[9], wl[3];
+  quat_to_mat(s.rq, R);
+  matT_vec(R, s.rw, wl);
+  s.rw[0] = wl[0]; s.rw[1] = wl[1]; s.rw[2] = wl[2];
+}
+template <typename T> __device__ __forceinline__ void ff_leave(St<T> &s) {
+  T R[9], w[3];
+  quat_to_mat(s.rq, R);
+  mat_vec(R, s.rw, w);
+  s.rw[0] = w[0]; s.rw[1] = w[1]; s.rw[2] = w[2];
+}
+
+// One fast-forward substep + the env logic that follows it (swingracket_env.py:105-141).  c.phase is 1 on the first
+// substep (no external force: the control step cleared it) and 2 afterwards.  Returns true when the env step is over.
+template <typename T> __device__ __forceinline__ bool ff_substep(const Scene<T> &sc, St<T> &s, StepCtl &c) {
+  const T dt = sc.dt, thr = sc.contact_threshold, rb = sc.ball_r;
+  ContactSet<T> cs;  // local memory; rare path only
+  int nc = 0, bits = 0;
+
+  // ---- (1) detection at the start-of-step poses
+  {
+    int need = 0;
+    const T x = s.rq[0], y = s.rq[1], z = s.rq[2], w = s.rq[3];
+    const T r6 = 2 * (x * z - y * w);
+    T rel[3] = {s.bp[0] - s.rp[0], s.bp[1] - s.rp[1], s.bp[2] - s.rp[2]};
+    T pl0 = (1 - 2 * (y * y + z * z)) * rel[0] + 2 * (x * y + z * w) * rel[1] + r6 * rel[2];
+    if (TB_UNLIKELY(!(M<T>::abs(pl0) > sc.ff_slab))) {  // inside the plate's slab: the remaining racket rejects
+      T R[9], pl[3];
+      quat_to_mat(s.rq, R);
+      matT_vec(R, rel, pl);
+      const T reach = rb + sc.hull_margin + thr, rs = sc.racket.bound_radius + reach;
+      bool near_racket = dot3(rel, rel) <= rs * rs && !(M<T>::abs(pl[0]) - sc.racket.half_thick > reach) &&
+                         !(M<T>::abs(pl[1]) - sc.racket_box[0] > reach) && !(pl[2] - sc.racket_box[2] > reach) &&
+                         !(sc.racket_box[1] - pl[2] > reach);
+      need |= near_racket ? kNeedRacket : 0;
+    }
+    if (TB_UNLIKELY(!(s.bp[2] > sc.ff_ball_z))) {  // low enough to reach the floor, the net's top or the goal's
+      const T reach_b = rb + sc.box_margin + thr;
+      need |= !(M<T>::abs(s.bp[2]) - sc.floor_h[2] > reach_b || M<T>::abs(s.bp[0]) - sc.floor_h[0] > reach_b ||
+                M<T>::abs(s.bp[1]) - sc.floor_h[1] > reach_b) ? kNeedFloor : 0;
+      need |= !(M<T>::abs(s.bp[0]) - sc.net_h[0] > reach_b || M<T>::abs(s.bp[2]) - sc.net_h[2] > reach_b ||
+                M<T>::abs(s.bp[1]) - sc.net_h[1] > reach_b) ? kNeedNet : 0;
+      const T reach_g = rb + sc.hull_margin + thr, rxy = sc.goal_r + reach_g;
+      T gx = s.bp[0] - s.goal[0], gy = s.bp[1] - s.goal[1];
+      need |= (M<T>::abs(s.bp[2]) - sc.goal_hz <= reach_g && gx * gx + gy * gy <= rxy * rxy) ? kNeedGoal : 0;
+    }
+    if (!(s.rp[2] > sc.ff_low_z)) {  // TB_EV_RACKET_LOW, exact test as in physics_step
+      T r7 = 2 * (y * z + x * w), r8 = 1 - 2 * (x * x + y * y);
+      T zlo = r8 * sc.racket_obb[1], zhi = r8 * sc.racket_obb[2];
+      T low = s.rp[2] - M<T>::abs(r6) * sc.racket.half_thick - M<T>::abs(r7) * sc.racket_obb[0] + (zlo < zhi ? zlo : zhi) -
+              sc.hull_margin;
+      bits |= (low <= sc.floor_h[2] + thr && M<T>::abs(s.rp[0]) <= sc.floor_h[0] + 1 && M<T>::abs(s.rp[1]) <= sc.floor_h[1] + 1)
+                  ? TB_EV_RACKET_LOW : 0;
+    }
+    if (TB_UNLIKELY(need)) {
+      NarrowIn<T> in;
+#pragma unroll
+      for (int i = 0; i < 3; ++i) { in.rp[i] = s.rp[i]; in.bp[i] = s.bp[i]; }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) in.rq[i] = s.rq[i];
+      in.goal[0] = s.goal[0]; in.goal[1] = s.goal[1];
+      int r = narrow_phase<T, true>(sc, need, &in, &cs);
+      bits |= r & 0xff;
+      nc = r >> 8;
+    }
+  }
+
+  // ---- (2) velocities
+  {
+    T fb = 1 - sc.ff_kl * (1 + M<T>::norm_damp(dot3(s.bv, s.bv)));
+    s.bv[0] *= fb; s.bv[1] *= fb; s.bv[2] = s.bv[2] * fb + sc.ff_dtg;
+    if (nonzero3(s.bw)) {  // the ball spins only after a frictional contact
+      T fs = 1 - sc.ff_ka * (1 + M<T>::norm_damp(dot3(s.bw, s.bw)));
+      s.bw[0] *= fs; s.bw[1] *= fs; s.bw[2] *= fs;
+    }
+    T fr = 1 - sc.ff_kl * (1 + M<T>::norm_damp(dot3(s.rv, s.rv)));
+    T h0 = 0, h1 = 0, h2 = sc.ff_dtg;
+    if (c.phase == 2) {  // the force the reference queued from the pose the previous substep ended with (:135-141)
+      h0 = sc.ff_hack[0] * (s.rp[0] - s.aux[0]);  // s.aux = spawn + (0, 0, 4) here, see ff_full
+      h1 = sc.ff_hack[1] * (s.rp[1] - s.aux[1]);
+      h2 = sc.ff_hack[2] * (s.rp[2] - s.aux[2]) + sc.ff_dtg;
+    }
+    s.rv[0] = s.rv[0] * fr + h0; s.rv[1] = s.rv[1] * fr + h1; s.rv[2] = s.rv[2] * fr + h2;
+    T fw = 1 - sc.ff_ka * (1 + M<T>::norm_damp(dot3(s.rw, s.rw)));
+    T p12 = s.rw[1] * s.rw[2], p20 = s.rw[2] * s.rw[0], p01 = s.rw[0] * s.rw[1];
+    s.rw[0] = s.rw[0] * fw - sc.ff_gyro[0] * p12;
+    s.rw[1] = s.rw[1] * fw - sc.ff_gyro[1] * p20;
+    s.rw[2] = s.rw[2] * fw - sc.ff_gyro[2] * p01;
+  }
+  T a2 = dot3(s.rw, s.rw);
+  {
+    bool over = near_limit(a2, sc.vmax2_hi);  // some world coordinate of omega may have reached the limit
+#pragma unroll
+    for (int i = 0; i < 3; ++i) over = over | near_limit(s.bv[i], sc.vmax_hi) | near_limit(s.bw[i], sc.vmax_hi) | near_limit(s.rv[i], sc.vmax_hi);
+    // ---- (3) contact solve, exact clamps
+    if (TB_UNLIKELY(over || nc > 0)) {
+      FfRare<T> io;
+#pragma unroll
+      for (int i = 0; i < 3; ++i) { io.bv[i] = s.bv[i]; io.bw[i] = s.bw[i]; io.rv[i] = s.rv[i]; io.wl[i] = s.rw[i]; }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) io.rq[i] = s.rq[i];
+      ff_rare(sc, &cs, nc, &io);
+#pragma unroll
+      for (int i = 0; i < 3; ++i) { s.bv[i] = io.bv[i]; s.bw[i] = io.bw[i]; s.rv[i] = io.rv[i]; s.rw[i] = io.wl[i]; }
+      a2 = dot3(s.rw, s.rw);
+    }
+  }
+
+  // ---- (4) poses: x += dt v ; q <- q exp(omega_body dt), renormalised to first order (see integrate_quat)
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    s.bp[i] += dt * s.bv[i];
+    s.rp[i] += dt * s.rv[i];
+  }
+  {
+    T sinc, cw;
+    sinc_cos_x2(sc.ff_qx2 * a2, &sinc, &cw);
+    T k = (T)0.5 * dt * sinc;
+    T ax = s.rw[0] * k, ay = s.rw[1] * k, az = s.rw[2] * k;
+    const T q0 = s.rq[0], q1 = s.rq[1], q2 = s.rq[2], q3 = s.rq[3];
+    T x = cw * q0 + ax * q3 + az * q1 - ay * q2;
+    T y = cw * q1 + ay * q3 + ax * q2 - az * q0;
+    T z = cw * q2 + az * q3 + ay * q0 - ax * q1;
+    T w = cw * q3 - ax * q0 - ay * q1 - az * q2;
+    T n2 = x * x + y * y + z * z + w * w;
+    T inv = (T)1.5 - (T)0.5 * n2;
+    if (TB_UNLIKELY(M<T>::abs(n2 - 1) > (T)1e-4)) inv = fast_rsqrt(n2);
+    s.rq[0] = x * inv; s.rq[1] = y * inv; s.rq[2] = z * inv; s.rq[3] = w * inv;
+  }
+
+  // ---- env logic (swingracket_env.py:109-133)
+  int k = ++s.step;
+  c.events |= bits;
+  c.last = bits;
+  c.phase = 2;
+  T reward = 0;
+  if (bits & TB_EV_COURT_BALL) { c.done = true; reward += moved_dist_to_goal(s); }
+  if (bits & TB_EV_GOAL_BALL) { reward += moved_dist_to_goal(s); reward += 50; c.done = true; }
+  if (k > 800) { c.done = true; c.events |= TB_EV_TIMEOUT; }
+  if (c.done) c.reward = (float)reward;
+  return c.done;
+}
+
+// ------------------------------------------------------------------------------------------------ fast lane
+// What a lane of ff_kernel keeps in registers between substeps: omega in the body frame, tgt = spawn + (0,0,4), and
+// the squared speeds nb, nr, nw of ball, racket and omega - the classification of a state needs them and the next
+// substep's damping factors reuse them.
+template <typename T> struct FfLane {
+  T rp[3], rq[4], rv[3], wl[3], bp[3], bv[3], bw[3], tgt[3], goal[2], nb, nr, nw;
+  int step, events;
+};
+// How the substep that starts from a state has to be taken:
+constexpr int kFfFree = 0;  // ff_fast, no contact possible
+constexpr int kFfLand = 1;  // ff_fast with the floor-face contact hook: the ball is within reach of the court's top face only
+constexpr int kFfFull = 2;  // ff_full: racket slab, net, goal or a floor edge within reach, the 800-step time-out, a speed
+                            // near the +-max_coord_vel clamp or |omega| beyond the short half-angle series
+constexpr int kFfDone = 3;  // (returned by the step functions) the env step is over
+// Conservative (a lane may be sent to ff_full for nothing, never the other way), and decided by the env's own state
+// only, so which path integrates a given substep never depends on the other lanes of the warp.
+// nb, nr, nw: squared speeds of ball, racket and racket spin.
+template <typename T>
+__device__ __forceinline__ int ff_classify_core(const Scene<T> &sc, const T *rp, const T *rq, const T *bp, const T *goal, T nb, T nr,
+                                                T nw, int step) {
+  const T x = rq[0], y = rq[1], z = rq[2], w = rq[3];
+  T rel[3] = {bp[0] - rp[0], bp[1] - rp[1], bp[2] - rp[2]};
+  T pl0 = (1 - 2 * (y * y + z * z)) * rel[0] + 2 * (x * y + z * w) * rel[1] + 2 * (x * z - y * w) * rel[2];
+  // bitwise on purpose: one straight line of compares, no short-circuit branches
+  bool racket = !(M<T>::abs(pl0) > sc.ff_slab) & !(dot3(rel, rel) > sc.ffp_racket_r2);
+  if (TB_UNLIKELY(racket)) {  // inside the plate's slab and the hull's bounding sphere: the outline's bounding box decides
+    T pl1 = 2 * (x * y - z * w) * rel[0] + (1 - 2 * (x * x + z * z)) * rel[1] + 2 * (y * z + x * w) * rel[2];
+    T pl2 = 2 * (x * z + y * w) * rel[0] + 2 * (y * z - x * w) * rel[1] + (1 - 2 * (x * x + y * y)) * rel[2];
+    racket = !(M<T>::abs(pl1) > sc.ffp_box[0]) & !(pl2 > sc.ffp_box[2]) & !(pl2 < sc.ffp_box[1]);
+  }
+  const T ax = M<T>::abs(bp[0]), ay = M<T>::abs(bp[1]), az = M<T>::abs(bp[2]);
+  T gx = bp[0] - goal[0], gy = bp[1] - goal[1];
+  bool full = racket | (!(ax > sc.ffp_net[0]) & !(az > sc.ffp_net[2]) & !(ay > sc.ffp_net[1])) |
+              (!(az > sc.ffp_goal_z) & !(gx * gx + gy * gy > sc.ffp_goal_r2)) |
+              !(nb < sc.ffp_v2) | !(nr < sc.ffp_v2) | !(nw < sc.ffp_a2) | (step >= 800);
+  bool floor = !(az > sc.ffp_floor[2]) & !(ax > sc.ffp_floor[0]) & !(ay > sc.ffp_floor[1]);
+  bool face = (bp[2] > sc.ffp_face[2]) & (ax < sc.ffp_face[0]) & (ay < sc.ffp_face[1]);
+  return (full | (floor & !face)) ? kFfFull : (floor ? kFfLand : kFfFree);
+}
+template <typename T> __device__ __forceinline__ int ff_classify(const Scene<T> &sc, FfLane<T> &L) {
+  L.nb = dot3(L.bv, L.bv); L.nr = dot3(L.rv, L.rv); L.nw = dot3(L.wl, L.wl);
+  return ff_classify_core(sc, L.rp, L.rq, L.bp, L.goal, L.nb, L.nr, L.nw, L.step);
+}
+// the same for a state record (omega in the world frame: same norm)
+template <typename T> __device__ __forceinline__ int ff_classify_state(const Scene<T> &sc, const St<T> &s) {
+  return ff_classify_core(sc, s.rp, s.rq, s.bp, s.goal, dot3(s.bv, s.bv), dot3(s.rv, s.rv), dot3(s.rw, s.rw), s.step);
+}
+
+// The substep without a narrow phase: ff_substep with phase 2, no clamp, the short series and at most the one contact
+// a free-falling ball ends almost every flight with - the court's top face (kind == kFfLand).  There the contact
+// normal is +z, the tangents btPlaneSpace1 gives are -y and +x, and the three rows of a single sphere contact
+// against a static body are orthogonal in the mass metric (r x n = 0), so projected Gauss-Seidel converges in its
+// first sweep: normal impulse = max(0, rhs), friction pair = rhs scaled into the cone.  solve_contacts' second
+// sweep would change that by rounding only.  Only valid from a state ff_classify() did not send to ff_full.
+// Returns ff_classify() of the state it leaves, or kFfDone after a landing (TB_EV_COURT_BALL set in L.events).
+template <typename T> __device__ __forceinline__ int ff_fast(const Scene<T> &sc, FfLane<T> &L, int kind) {
+  const T dt = sc.dt;
+  {  // TB_EV_RACKET_LOW at the start-of-step pose, exact test as in physics_step
+    const T x = L.rq[0], y = L.rq[1], z = L.rq[2], w = L.rq[3];
+    T r6 = 2 * (x * z - y * w), r7 = 2 * (y * z + x * w), r8 = 1 - 2 * (x * x + y * y);
+    T zlo = r8 * sc.racket_obb[1], zhi = r8 * sc.racket_obb[2];
+    T low = L.rp[2] - M<T>::abs(r6) * sc.racket.half_thick - M<T>::abs(r7) * sc.racket_obb[0] + (zlo < zhi ? zlo : zhi) - sc.hull_margin;
+    bool is_low = (low <= sc.ffp_low) & (M<T>::abs(L.rp[0]) <= sc.ffp_court[0]) & (M<T>::abs(L.rp[1]) <= sc.ffp_court[1]);
+    L.events |= is_low ? TB_EV_RACKET_LOW : 0;
+  }
+  // signed distance of the ball to the court's top face at the start-of-step pose (box_distance's face case)
+  const T d_floor = (L.bp[2] - (sc.floor_h[2] - sc.box_margin)) - (sc.ball_r + sc.box_margin);
+  T fb = 1 - sc.ff_kl * (1 + M<T>::norm_damp(L.nb));
+  L.bv[0] *= fb; L.bv[1] *= fb; L.bv[2] = L.bv[2] * fb + sc.ff_dtg;
+  {  // unconditional: a warp almost always holds a ball that spins, and 0 * f stays 0 for the others
+    T fs = 1 - sc.ff_ka * (1 + M<T>::norm_damp(dot3(L.bw, L.bw)));
+    L.bw[0] *= fs; L.bw[1] *= fs; L.bw[2] *= fs;
+  }
+  T fr = 1 - sc.ff_kl * (1 + M<T>::norm_damp(L.nr));
+  L.rv[0] = L.rv[0] * fr + sc.ff_hack[0] * (L.rp[0] - L.tgt[0]);
+  L.rv[1] = L.rv[1] * fr + sc.ff_hack[1] * (L.rp[1] - L.tgt[1]);
+  L.rv[2] = L.rv[2] * fr + (sc.ff_hack[2] * (L.rp[2] - L.tgt[2]) + sc.ff_dtg);
+  T fw = 1 - sc.ff_ka * (1 + M<T>::norm_damp(L.nw));
+  T p12 = L.wl[1] * L.wl[2], p20 = L.wl[2] * L.wl[0], p01 = L.wl[0] * L.wl[1];
+  L.wl[0] = L.wl[0] * fw - sc.ff_gyro[0] * p12;
+  L.wl[1] = L.wl[1] * fw - sc.ff_gyro[1] * p20;
+  L.wl[2] = L.wl[2] * fw - sc.ff_gyro[2] * p01;
+  bool landed = false;
+  if (TB_UNLIKELY(kind == kFfLand && d_floor <= sc.contact_threshold)) {
+    landed = true;
+    L.events |= TB_EV_COURT_BALL;
+    const T rb = sc.ball_r, inv_m = sc.ball_inv_m, inv_i = sc.ball_inv_i;
+    // normal row: u = (0,0,1), r x u = 0.  Divisions by constants are products with host-side reciprocals (the
+    // block sits in the substep loop's instruction footprint).
+    T rel = L.bv[2];
+    T e = M<T>::abs(rel) < sc.rest_vel_threshold ? (T)0 : -sc.rest_court * rel;
+    if (e < 0) e = 0;
+    T pen = d_floor + sc.slop, vel_err = e - rel, pos_err = 0;
+    if (pen > 0) vel_err -= pen * sc.ffl_inv_dt;
+    else pos_err = -pen * sc.ffl_erp_dt;
+    T lam_n = (pos_err + vel_err) * sc.ffl_m;
+    if (lam_n > 0) {
+      L.bv[2] += lam_n * inv_m;
+      // friction pair: u1 = (0,-1,0), r x u1 = (-rb,0,0); u2 = (1,0,0), r x u2 = (0,-rb,0)
+      T s1 = (L.bv[1] + rb * L.bw[0]) * sc.ffl_jinv_t, s2 = -(L.bv[0] - rb * L.bw[1]) * sc.ffl_jinv_t;
+      T lim = sc.mu_court * lam_n, m2 = s1 * s1 + s2 * s2;
+      if (m2 > lim * lim) {
+        T y = (T)rsqrtf((float)m2);  // float estimate + two Newton steps: ~1e-15 relative
+        y = y * ((T)1.5 - (T)0.5 * m2 * y * y);
+        y = y * ((T)1.5 - (T)0.5 * m2 * y * y);
+        T sf = lim * y;
+        s1 *= sf; s2 *= sf;
+      }
+      L.bv[1] -= s1 * inv_m; L.bw[0] -= rb * s1 * inv_i;
+      L.bv[0] += s2 * inv_m; L.bw[1] -= rb * s2 * inv_i;
+      const T vmax = sc.max_coord_vel;  // the clamp physics_step applies after a solve
+#pragma unroll
+      for (int i = 0; i < 3; ++i) { L.bv[i] = clampv(L.bv[i], -vmax, vmax); L.bw[i] = clampv(L.bw[i], -vmax, vmax); }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    L.bp[i] += dt * L.bv[i];
+    L.rp[i] += dt * L.rv[i];
+  }
+  {
+    T sinc, cw;
+    sinc_cos_short(sc.ff_qx2 * dot3(L.wl, L.wl), &sinc, &cw);
+    T k = (T)0.5 * dt * sinc;
+    T ax = L.wl[0] * k, ay = L.wl[1] * k, az = L.wl[2] * k;
+    const T q0 = L.rq[0], q1 = L.rq[1], q2 = L.rq[2], q3 = L.rq[3];
+    T x = cw * q0 + ax * q3 + az * q1 - ay * q2;
+    T y = cw * q1 + ay * q3 + ax * q2 - az * q0;
+    T z = cw * q2 + az * q3 + ay * q0 - ax * q1;
+    T w = cw * q3 - ax * q0 - ay * q1 - az * q2;
+    T inv = (T)1.5 - (T)0.5 * (x * x + y * y + z * z + w * w);
+    L.rq[0] = x * inv; L.rq[1] = y * inv; L.rq[2] = z * inv; L.rq[3] = w * inv;
+  }
+  ++L.step;
+  int next = ff_classify(sc, L);
+  return landed ? kFfDone : next;
+}
+
+// The full substep (first substep of a flight that starts in contact, racket / net / goal / floor-edge contact,
+// time-out, ...): ff_substep on a copy of the lane.  Out of line, data crosses through *Lp only.  Returns what comes
+// next (kFfFree .. kFfDone); the env step's accumulated event bits are left in Lp->events, the contact bits of this
+// substep alone in *last (the reward of the env step depends on those only, swingracket_env.py:111-126).
+template <typename T>
+__device__ __noinline__ int ff_full(const Scene<T> &sc, FfLane<T> *Lp, int phase, int *last) {
+  St<T> s;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    s.rp[i] = Lp->rp[i]; s.rv[i] = Lp->rv[i]; s.rw[i] = Lp->wl[i]; s.bp[i] = Lp->bp[i]; s.bv[i] = Lp->bv[i];
+    s.bw[i] = Lp->bw[i]; s.aux[i] = Lp->tgt[i];
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) s.rq[i] = Lp->rq[i];
+  s.goal[0] = Lp->goal[0]; s.goal[1] = Lp->goal[1];
+  s.d0 = 1; s.ret = 0; s.step = Lp->step; s.flags = 0; s.episode = 0;  // the reward is formed by ff_reward later
+  StepCtl c = {phase, Lp->events, 0, 0.0f, false, 0};
+  bool fin = ff_substep<T>(sc, s, c);
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    Lp->rp[i] = s.rp[i]; Lp->rv[i] = s.rv[i]; Lp->wl[i] = s.rw[i]; Lp->bp[i] = s.bp[i]; Lp->bv[i] = s.bv[i];
+    Lp->bw[i] = s.bw[i];
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) Lp->rq[i] = s.rq[i];
+  Lp->step = s.step; Lp->events = c.events;
+  *last = c.last;
+  int next = ff_classify(sc, *Lp);
+  return fin ? kFfDone : next;
+}
+
+// Reward of the env step a fast-forward ended with, from the contact bits of its last substep (swingracket_env.py:111-126;
+// same order of operations as ff_substep).
+template <typename T> __device__ __forceinline__ float ff_reward(const St<T> &s, int last) {
+  T reward = 0;
+  if (last & TB_EV_COURT_BALL) reward += moved_dist_to_goal(s);
+  if (last & TB_EV_GOAL_BALL) { reward += moved_dist_to_goal(s); reward += 50; }
+  return (float)reward;
 }
 
 }  // namespace tb

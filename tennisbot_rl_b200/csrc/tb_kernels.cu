@@ -10,6 +10,7 @@
 #include <cuda_runtime.h>
 
 #include <cmath>
+#include <cstddef>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -30,10 +31,6 @@ constexpr int kBlock = 128;     // threads per CTA of the step kernel
 // CTAs per SM the register budget is held to: 4 x 128 threads -> 128 regs/thread (f32), 3 -> 168 (f64); measured best on B200
 template <typename T> struct MinBlocks { static constexpr int v = TB_MINB32; };
 template <> struct MinBlocks<double> { static constexpr int v = TB_MINB64; };
-#ifndef TB_REFILL_MIN
-#define TB_REFILL_MIN 8
-#endif
-constexpr int kRefillMin = TB_REFILL_MIN;   // idle lanes that trigger a refill before the periodic one
 
 // ------------------------------------------------------------------------------------------------ pack I/O
 template <typename T> struct Pack { T x, y, z, w; };
@@ -106,9 +103,10 @@ struct StepIO {
   int32_t *done_count;
   unsigned long long *stats;
   int *queue;                        // env indices waiting for ff_kernel: long flights from the front, short from the back
-  unsigned long long *queue_ctr;     // [0] front entries, [1] back entries appended by this step's step_kernel,
-                                     // [2] entries claimed by ff_kernel lanes
-  unsigned long long *queue_ctr_next;  // the triple the NEXT step uses; step_kernel zeroes it
+  int *queue_b, *queue_full;         // ff_kernel's own queues: fast queue of odd rounds, envs waiting for a full substep
+  unsigned long long *queue_ctr;     // kCtrWords counters (kC* below): [0] front, [1] back entries appended by this
+                                     // step's step_kernel, the rest ff_kernel's
+  unsigned long long *queue_ctr_next;  // the set the NEXT step uses; step_kernel zeroes it
   void *pid;                         // TB_CONTROL_PID: 2 packs x N of controller memory, else nullptr
 };
 
@@ -164,6 +162,19 @@ template <int KIND> __device__ __forceinline__ void random_action(uint64_t seed,
 //
 // Episode statistics are warp-uniform popc()/redux sums kept in shared memory, one atomic per counter per warp.
 constexpr int kFlagDone = 1, kFlagInFlight = 2, kFlagEventShift = 8;
+// marks ff_kernel's phases hand an env on with (all cleared again before the env step completes):
+constexpr int kFlagLanded = 4;      // the env step is over; outputs / statistics / auto-reset pending
+constexpr int kFlagFirst = 8;       // the flight's first substep (no external force) has not been taken yet
+constexpr int kFlagLastShift = 16;  // contact bits of the flight's last substep
+// counter words of one step's set
+constexpr int kCtrWords = 32;  // 16 counters + 16 diagnostic words (kD*)
+constexpr int kCFront = 0, kCBack = 1, kCBarrier = 2, kCError = 3;
+constexpr int kDRounds = 16, kDFullEnvs = 17, kDPhase = 18, kDFinish = 30;  // tb_ff_diagnostics
+// per ff round parity p: entries of the fast queue, claimed of it, entries of the full queue, claimed of it
+__host__ __device__ constexpr int kCFast(int p) { return 4 + 4 * p; }
+__host__ __device__ constexpr int kCFastClaim(int p) { return 5 + 4 * p; }
+__host__ __device__ constexpr int kCFull(int p) { return 6 + 4 * p; }
+__host__ __device__ constexpr int kCFullClaim(int p) { return 7 + 4 * p; }
 
 struct WarpStats {
   unsigned long long *acc;  // this warp's row of the CTA's shared accumulators
@@ -263,8 +274,8 @@ template <> struct StepMinBlocks<double> { static constexpr int v = TB_STEP_MINB
 template <typename T, int KIND, bool STAGE>
 __global__ void __launch_bounds__(kBlock, StepMinBlocks<T>::v) step_kernel(const __grid_constant__ Scene<T> sc, const __grid_constant__ StepIO io) {
   __shared__ unsigned long long sacc[kBlock / 32][TB_NUM_STATS];
-  __shared__ int s_cnt[2 * (kBlock / 32)];
-  __shared__ unsigned long long s_base[2];
+  __shared__ int s_cnt[3 * (kBlock / 32)];
+  __shared__ unsigned long long s_base[3];
   // Each warp's 32 action rows come in and its 32 observation rows go out as one contiguous tile through shared
   // memory (warp-private, __syncwarp only): [N, act] / [N, obs] float32 rows are 24 / 8 / 48 bytes, which per-thread
   // accesses would turn into strided partial sectors - harmless in HBM behind L2, costly when the caller's buffers
@@ -276,7 +287,7 @@ __global__ void __launch_bounds__(kBlock, StepMinBlocks<T>::v) step_kernel(const
   float *s_tile = s_tiles[STAGE ? wib : 0];
   WarpStats ws;
   ws.init(sacc[wib], lane);
-  if (blockIdx.x == 0 && threadIdx.x == 0) { io.queue_ctr_next[0] = 0; io.queue_ctr_next[1] = 0; io.queue_ctr_next[2] = 0; }
+  if (blockIdx.x == 0 && threadIdx.x < kCtrWords) io.queue_ctr_next[threadIdx.x] = 0;
 
   const int64_t tile0 = (int64_t)blockIdx.x * kBlock + wib * 32, me = tile0 + lane;
   const bool valid = me < io.n;
@@ -332,97 +343,379 @@ __global__ void __launch_bounds__(kBlock, StepMinBlocks<T>::v) step_kernel(const
   // envs entering the fast-forward: queue them for ff_kernel (only SwingRacket ever does).  Longest-job-first:
   // a ball the racket has hit flies for up to 775 more substeps and is queued from the FRONT, a ball still in free
   // fall lands after ~100 and is queued from the BACK, so the long flights start first and the short ones fill
-  // the tail of ff_kernel.
+  // the tail of ff_kernel.  An env whose first fast-forward substep needs the full treatment (ball within reach of
+  // the racket, mostly: a hit in progress) goes to the full queue, which ff_kernel serves before anything else.
   bool queued = valid && !fin;
   if (KIND == TB_ENV_SWING) {
-    bool is_long = queued && dot3(s.bv, s.bv) > (T)9;
-    unsigned lmask = __ballot_sync(full, is_long), smask = __ballot_sync(full, queued && !is_long);
-    if (lane == 0) { s_cnt[wib] = __popc(lmask); s_cnt[kBlock / 32 + wib] = __popc(smask); }
+    constexpr int W = kBlock / 32;
+    int cls = queued ? (ff_classify_state(sc, s) == kFfFull ? 2 : (dot3(s.bv, s.bv) > (T)9 ? 0 : 1)) : 3;
+    unsigned m0 = __ballot_sync(full, cls == 0), m1 = __ballot_sync(full, cls == 1), m2 = __ballot_sync(full, cls == 2);
+    if (lane == 0) { s_cnt[wib] = __popc(m0); s_cnt[W + wib] = __popc(m1); s_cnt[2 * W + wib] = __popc(m2); }
     __syncthreads();
-    if (threadIdx.x == 0) {
-      int tl = 0, ts = 0;
+    if (threadIdx.x < 3) {
+      int k = threadIdx.x, tot = 0;
 #pragma unroll
-      for (int w = 0; w < kBlock / 32; ++w) {
-        int a = s_cnt[w], b = s_cnt[kBlock / 32 + w];
-        s_cnt[w] = tl; s_cnt[kBlock / 32 + w] = ts;
-        tl += a; ts += b;
+      for (int w = 0; w < W; ++w) {
+        int a = s_cnt[k * W + w];
+        s_cnt[k * W + w] = tot;
+        tot += a;
       }
-      s_base[0] = tl ? atomicAdd(io.queue_ctr, (unsigned long long)tl) : 0ULL;
-      s_base[1] = ts ? atomicAdd(io.queue_ctr + 1, (unsigned long long)ts) : 0ULL;
+      unsigned long long *ctr = io.queue_ctr + (k == 0 ? kCFront : k == 1 ? kCBack : kCFull(0));
+      s_base[k] = tot ? atomicAdd(ctr, (unsigned long long)tot) : 0ULL;
     }
     __syncthreads();
     if (queued) {
       const unsigned lt = (1u << lane) - 1u;
-      if (is_long) io.queue[s_base[0] + s_cnt[wib] + __popc(lmask & lt)] = (int)me;
-      else io.queue[io.n - 1 - (int64_t)(s_base[1] + s_cnt[kBlock / 32 + wib] + __popc(smask & lt))] = (int)me;
-      s.flags = (s.flags & ~(0xff << kFlagEventShift)) | kFlagInFlight | (c.events << kFlagEventShift);
+      if (cls == 0) io.queue[s_base[0] + s_cnt[wib] + __popc(m0 & lt)] = (int)me;
+      else if (cls == 1) io.queue[io.n - 1 - (int64_t)(s_base[1] + s_cnt[W + wib] + __popc(m1 & lt))] = (int)me;
+      else io.queue_full[s_base[2] + s_cnt[2 * W + wib] + __popc(m2 & lt)] = (int)me;
+      s.flags = (s.flags & ~(0xff << kFlagEventShift)) | kFlagInFlight | kFlagFirst | (c.events << kFlagEventShift);
     }
   }
   if (valid) store_state(base, io.n, me, s);
   ws.flush(io.stats);
 }
 
-// Fast-forward continuation (SwingRacket only).
+// Fast-forward continuation (SwingRacket only): one persistent launch (a CTA per resident slot) that runs in PHASES
+// separated by grid-wide barriers, so that at any time every warp of an SM executes the same small piece of code:
+//
+//   A  fast   every LANE is a small state machine: claim an env from the round's fast queue, keep its state in registers
+//             and take ff_fast substeps (a straight line, the court landing included) until the flight ends or a
+//             substep needs the full treatment; then hand the env on through HBM (landed mark, or the full queue)
+//             and claim the next one.  Leaving / claiming is done for several lanes of a warp at once.  A lane in an
+//             800-substep flight delays nobody; the longest flights are queued first.
+//   B  full   one lane per queued env: generic substeps (ff_full: narrow phase, contact solve, time-out) until the
+//             env step ends or ff_fast applies again; those go to the next round's fast queue.
+//   ... A, B repeat until no env is left in flight (rounds beyond kFfMaxRounds finish in B) ...
+//   C  finish every env that landed: reward, statistics, outputs, auto-reset, one coalesced pass like step_kernel.
+//
+// Mixed into one loop, each landing / claim / contact stalled 31 other lanes and streamed ~40 KB of rare code
+// through the instruction caches the substep loop lives in (measured: 2.2x slower).
+#ifndef TB_FF_SERVE_MIN
+#define TB_FF_SERVE_MIN 8
+#endif
+#ifndef TB_FF_SERVE_WAIT
+#define TB_FF_SERVE_WAIT 12
+#endif
+constexpr int kServeMin = TB_FF_SERVE_MIN, kServeWait = TB_FF_SERVE_WAIT;
+constexpr int kIdle = 4;  // lane states 0..3 = kFfFree, kFfLand (running), kFfFull, kFfDone (leaving)
+constexpr int kFfMaxRounds = 3;  // the last round's phase B runs its envs to the end of their flights
+
+__device__ __forceinline__ unsigned long long ld_ctr(const unsigned long long *p) { return __ldcg(p); }
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+
+// All CTAs of the (co-resident) grid meet.  Returns false if the barrier could not complete (another CTA gave up or a
+// time-out: the launch then ends without finishing its envs instead of hanging the device).
+__device__ __forceinline__ bool grid_barrier(unsigned long long *ctr, unsigned &epoch) {
+  __shared__ int s_ok;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned long long target = (unsigned long long)(++epoch) * gridDim.x;
+    atomicAdd(ctr + kCBarrier, 1ULL);
+    int ok = 1;
+    long long t0 = clock64();
+    while (ld_ctr(ctr + kCBarrier) < target) {
+      __nanosleep(200);
+      if (ld_ctr(ctr + kCError) || clock64() - t0 > (1LL << 33)) {  // ~4 s
+        atomicExch(ctr + kCError, 1ULL);
+        ok = 0;
+        break;
+      }
+    }
+    __threadfence();
+    s_ok = ok;
+  }
+  __syncthreads();
+  return s_ok != 0;
+}
+
+// warp-aggregated append of `me` (for lanes with pred) to a queue
+__device__ __forceinline__ void queue_push(int *q, unsigned long long *count, bool pred, int me, int lane) {
+  const unsigned full = 0xffffffffu;
+  unsigned m = __ballot_sync(full, pred);
+  if (!m) return;
+  int leader = __ffs(m) - 1;
+  unsigned long long base = 0;
+  if (lane == leader) base = atomicAdd(count, (unsigned long long)__popc(m));
+  base = __shfl_sync(full, base, leader);
+  if (pred) q[base + __popc(m & ((1u << lane) - 1u))] = me;
+}
+
+// state loads that bypass L1: another SM may have rewritten the env since this SM last saw it (same launch)
+__device__ __forceinline__ Pack<float> ldcg_pack(const float *base, int64_t n, int p, int64_t i) {
+  float4 v = __ldcg(reinterpret_cast<const float4 *>(base + ((int64_t)p * n + i) * 4));
+  return {v.x, v.y, v.z, v.w};
+}
+__device__ __forceinline__ Pack<double> ldcg_pack(const double *base, int64_t n, int p, int64_t i) {
+  const double2 *q = reinterpret_cast<const double2 *>(base + ((int64_t)p * n + i) * 4);
+  double2 a = __ldcg(q), b = __ldcg(q + 1);
+  return {a.x, a.y, b.x, b.y};
+}
+// an env's flight state HBM -> lane (omega to the body frame); returns the flags word
+template <typename T> __device__ __forceinline__ int ff_load(const T *base, int64_t n, int64_t me, FfLane<T> &L) {
+  Pack<T> p0 = ldcg_pack(base, n, 0, me), p1 = ldcg_pack(base, n, 1, me), p2 = ldcg_pack(base, n, 2, me), p3 = ldcg_pack(base, n, 3, me),
+          p4 = ldcg_pack(base, n, 4, me), p5 = ldcg_pack(base, n, 5, me), p6 = ldcg_pack(base, n, 6, me), p7 = ldcg_pack(base, n, 7, me);
+  St<T> s;
+  s.rq[0] = p1.x; s.rq[1] = p1.y; s.rq[2] = p1.z; s.rq[3] = p1.w;
+  s.rw[0] = p3.x; s.rw[1] = p3.y; s.rw[2] = p3.z;
+  ff_enter(s);
+  L.rp[0] = p0.x; L.rp[1] = p0.y; L.rp[2] = p0.z; L.bp[0] = p0.w;
+  L.rq[0] = p1.x; L.rq[1] = p1.y; L.rq[2] = p1.z; L.rq[3] = p1.w;
+  L.rv[0] = p2.x; L.rv[1] = p2.y; L.rv[2] = p2.z; L.bp[1] = p2.w;
+  L.wl[0] = s.rw[0]; L.wl[1] = s.rw[1]; L.wl[2] = s.rw[2]; L.bp[2] = p3.w;
+  L.bv[0] = p4.x; L.bv[1] = p4.y; L.bv[2] = p4.z; L.bw[0] = p4.w;
+  L.bw[1] = p5.x; L.bw[2] = p5.y;
+  L.tgt[0] = p5.z; L.tgt[1] = p5.w; L.tgt[2] = p6.x + 4;  // swingracket_env.py:135-141
+  L.goal[0] = p6.y; L.goal[1] = p6.z;
+  L.step = (int)as_int(p7.y);
+  int flags = (int)as_int(p7.z);
+  L.events = (flags >> kFlagEventShift) & 0xff;
+  return flags;
+}
+// lane -> HBM: the packs a flight changes (0..4, the spin half of 5) and step / flags of pack 7
+template <typename T> __device__ __forceinline__ void ff_store(T *base, int64_t n, int64_t me, const FfLane<T> &L, int flags) {
+  St<T> s;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) s.rq[i] = L.rq[i];
+  s.rw[0] = L.wl[0]; s.rw[1] = L.wl[1]; s.rw[2] = L.wl[2];
+  ff_leave(s);
+  st_pack(base, n, 0, me, Pack<T>{L.rp[0], L.rp[1], L.rp[2], L.bp[0]});
+  st_pack(base, n, 1, me, Pack<T>{L.rq[0], L.rq[1], L.rq[2], L.rq[3]});
+  st_pack(base, n, 2, me, Pack<T>{L.rv[0], L.rv[1], L.rv[2], L.bp[1]});
+  st_pack(base, n, 3, me, Pack<T>{s.rw[0], s.rw[1], s.rw[2], L.bp[2]});
+  st_pack(base, n, 4, me, Pack<T>{L.bv[0], L.bv[1], L.bv[2], L.bw[0]});
+  T *p5 = base + ((int64_t)5 * n + me) * 4, *p7 = base + ((int64_t)7 * n + me) * 4;
+  p5[0] = L.bw[1]; p5[1] = L.bw[2];
+  p7[1] = int_as(T(), L.step); p7[2] = int_as(T(), flags);
+}
+
+// Phase A for one warp.  The round's fast queue: the n0 entries step_kernel queued (front / back layout, qfront of them
+// at the front; round 0 only) followed by the entries phase B just appended to lateq; nfast in all, claimed through
+// *claim.  Envs that need a full substep are appended to fullq.
+template <typename T>
+__device__ __forceinline__ void ff_phase_fast(const Scene<T> &sc, const StepIO &io, long long n0, long long qfront, const int *lateq,
+                                              long long nfast, unsigned long long *claim, int *fullq,
+                                              unsigned long long *nfull, int lane, int &nsub) {
+  const unsigned full = 0xffffffffu;
+  T *base = static_cast<T *>(io.state);
+  FfLane<T> L;
+  {  // defined values for lanes that never get an env (ff_fast is never run on them)
+    T *z = reinterpret_cast<T *>(&L);
+#pragma unroll
+    for (int i = 0; i < (int)(offsetof(FfLane<T>, step) / sizeof(T)); ++i) z[i] = 0;
+    L.step = 0; L.events = 0;
+  }
+  int me = 0, st = kIdle, waited = 0, step0 = 0;
+  bool exhausted = false, first = false, first_pending = false;
+  for (;;) {
+    // ---- substeps until enough lanes want to leave / claim (no call, no rare code in this loop)
+    unsigned run_m, wait_m;
+#pragma unroll 1
+    for (;;) {
+      if (st <= kFfLand) st = ff_fast<T>(sc, L, st);
+      if (TB_UNLIKELY(first_pending)) {  // warp-uniform: some lanes just took a flight's first substep, see below
+        if (first) {
+          const T *p5 = base + ((int64_t)5 * io.n + me) * 4, *p6 = base + ((int64_t)6 * io.n + me) * 4;
+          L.tgt[0] = __ldcg(p5 + 2); L.tgt[1] = __ldcg(p5 + 3); L.tgt[2] = __ldcg(p6) + 4;
+          first = false;
+        }
+        first_pending = false;
+      }
+      run_m = __ballot_sync(full, st <= kFfLand);
+      wait_m = exhausted ? __ballot_sync(full, st == kFfFull || st == kFfDone) : ~run_m;
+      waited = wait_m ? waited + 1 : 0;
+      if (!run_m || __popc(wait_m) >= kServeMin || waited >= kServeWait) break;
+    }
+    if (!(run_m | wait_m)) break;
+    waited = 0;
+    // ---- lanes whose flight left ff_fast: state back to HBM, landed mark or the full queue
+    if (st == kFfFull || st == kFfDone) {
+      nsub += L.step - step0;
+      int flags = kFlagInFlight | (L.events << kFlagEventShift);
+      if (st == kFfDone) flags |= kFlagLanded | (TB_EV_COURT_BALL << kFlagLastShift);  // ff_fast ends on the court's top face only
+      ff_store(base, io.n, (int64_t)me, L, flags);
+    }
+    queue_push(fullq, nfull, st == kFfFull, me, lane);
+    if (st == kFfFull || st == kFfDone) st = kIdle;
+    // ---- idle lanes claim queue entries (one atomic per warp)
+    unsigned idle = __ballot_sync(full, st == kIdle);
+    if (idle && !exhausted) {
+      int want = __popc(idle);
+      long long at = 0;
+      if (lane == 0) at = (long long)atomicAdd(claim, (unsigned long long)want);
+      at = __shfl_sync(full, at, 0);
+      if (at + want >= nfast) exhausted = true;
+      long long idx = at + __popc(idle & ((1u << lane) - 1u));
+      bool got = st == kIdle && idx < nfast;
+      bool to_full = false;
+      if (got) {
+        me = idx < qfront ? __ldcg(io.queue + idx) : idx < n0 ? __ldcg(io.queue + (io.n - 1 - (idx - qfront))) : __ldcg(lateq + (idx - n0));
+        int flags = ff_load(base, io.n, (int64_t)me, L);
+        step0 = L.step;
+        st = ff_classify(sc, L);
+        if (st == kFfFull) {  // starts within reach of something: untouched, straight to the full queue
+          to_full = true;
+        } else if (flags & kFlagFirst) {
+          // the flight's first substep carries no force (swingracket_env.py:105-107): with the target on the racket
+          // itself the force law gives exactly zero; the real target comes back after that substep (first_pending)
+          L.tgt[0] = L.rp[0]; L.tgt[1] = L.rp[1]; L.tgt[2] = L.rp[2];
+          first = true;
+        }
+      }
+      queue_push(fullq, nfull, to_full, me, lane);
+      if (to_full) st = kIdle;
+      first_pending = __any_sync(full, first);
+    }
+  }
+}
+
+// Phase B for one warp: 32 queued envs at a time, one per lane, generic substeps until ff_fast applies again (or, with
+// to_end, until the env step is over).
+template <typename T>
+__device__ __noinline__ void ff_phase_full(const Scene<T> &sc, const StepIO &io, const int *fullq, long long nfull,
+                                           unsigned long long *claim, int *nextq, unsigned long long *nnext, bool to_end,
+                                           int lane, int *nsub) {
+  const unsigned full = 0xffffffffu;
+  T *base = static_cast<T *>(io.state);
+  for (;;) {
+    long long at = 0;
+    if (lane == 0) at = (long long)atomicAdd(claim, 32ULL);
+    at = __shfl_sync(full, at, 0);
+    if (at >= nfull) break;
+    const bool have = at + lane < nfull;
+    int me = 0, r = kFfDone;
+    if (have) {
+      me = __ldcg(fullq + at + lane);
+      FfLane<T> L;
+      int flags = ff_load(base, io.n, (int64_t)me, L);
+      int phase = (flags & kFlagFirst) ? 1 : 2, last = 0;
+      const int step0 = L.step;
+      r = ff_classify(sc, L);  // fills the lane's squared speeds; an env is only queued here when this says kFfFull
+      do {
+        if (r == kFfFull) {
+          r = ff_full<T>(sc, &L, phase, &last);
+        } else {  // to_end only: the flight goes on in this lane
+          if (phase == 1) {  // the force-free first substep (see ff_phase_fast)
+            const T t0 = L.tgt[0], t1 = L.tgt[1], t2 = L.tgt[2];
+            L.tgt[0] = L.rp[0]; L.tgt[1] = L.rp[1]; L.tgt[2] = L.rp[2];
+            r = ff_fast<T>(sc, L, r);
+            L.tgt[0] = t0; L.tgt[1] = t1; L.tgt[2] = t2;
+          } else {
+            r = ff_fast<T>(sc, L, r);
+          }
+          last = TB_EV_COURT_BALL;  // if this was the last one: ff_fast ends on the court's top face only
+        }
+        phase = 2;
+      } while (r == kFfFull || (to_end && r != kFfDone));
+      *nsub += L.step - step0;
+      flags = kFlagInFlight | (L.events << kFlagEventShift);
+      if (r == kFfDone) flags |= kFlagLanded | (last << kFlagLastShift);
+      ff_store(base, io.n, (int64_t)me, L, flags);
+    }
+    queue_push(nextq, nnext, have && r != kFfDone, me, lane);
+  }
+}
+
+// Phase C for one warp-tile of 32 consecutive envs: complete the env step of those that landed.
+template <typename T>
+__device__ __noinline__ void ff_phase_finish(const Scene<T> &sc, const StepIO &io, int64_t tile0, WarpStats *wsp) {
+  constexpr int KIND = TB_ENV_SWING;
+  T *base = static_cast<T *>(io.state);
+  const int64_t me = tile0 + wsp->lane;
+  bool fin = false;
+  St<T> s;
+  s.step = 0; s.ret = 0;
+  int events = 0;
+  float reward = 0.0f;
+  if (me < io.n) {
+    Pack<T> p7 = ldcg_pack(base, io.n, 7, me);
+    int flags = (int)as_int(p7.z);
+    if (flags & kFlagLanded) {
+      fin = true;
+      Pack<T> p0 = ldcg_pack(base, io.n, 0, me), p1 = ldcg_pack(base, io.n, 1, me), p2 = ldcg_pack(base, io.n, 2, me),
+              p3 = ldcg_pack(base, io.n, 3, me), p4 = ldcg_pack(base, io.n, 4, me), p5 = ldcg_pack(base, io.n, 5, me),
+              p6 = ldcg_pack(base, io.n, 6, me);
+      s.rp[0] = p0.x; s.rp[1] = p0.y; s.rp[2] = p0.z; s.bp[0] = p0.w;
+      s.rq[0] = p1.x; s.rq[1] = p1.y; s.rq[2] = p1.z; s.rq[3] = p1.w;
+      s.rv[0] = p2.x; s.rv[1] = p2.y; s.rv[2] = p2.z; s.bp[1] = p2.w;
+      s.rw[0] = p3.x; s.rw[1] = p3.y; s.rw[2] = p3.z; s.bp[2] = p3.w;
+      s.bv[0] = p4.x; s.bv[1] = p4.y; s.bv[2] = p4.z; s.bw[0] = p4.w;
+      s.bw[1] = p5.x; s.bw[2] = p5.y; s.aux[0] = p5.z; s.aux[1] = p5.w;
+      s.aux[2] = p6.x; s.goal[0] = p6.y; s.goal[1] = p6.z; s.d0 = p6.w;
+      s.step = (int)as_int(p7.y);
+      s.episode = (uint32_t)as_int(p7.w);
+      events = (flags >> kFlagEventShift) & 0xff;
+      reward = ff_reward(s, (flags >> kFlagLastShift) & 0xff);
+      s.ret = p7.x + (T)reward;
+      s.flags = flags & kFlagDone;  // drop every in-flight mark
+    }
+  }
+  account<T>(*wsp, fin, true, 0, events, s.step, s.ret);
+  if (fin) {
+    finish_api<T, KIND>(sc, io, me, s, reward, true, events);
+    store_state(base, io.n, me, s);
+    if (io.pid && io.auto_reset) {
+      T z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      store_pid(static_cast<T *>(io.pid), io.n, me, z);
+    }
+  }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(kBlock, MinBlocks<T>::v) ff_kernel(const __grid_constant__ Scene<T> sc, const __grid_constant__ StepIO io) {
-  constexpr int KIND = TB_ENV_SWING;
   __shared__ unsigned long long sacc[kBlock / 32][TB_NUM_STATS];
-  const unsigned full = 0xffffffffu;
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  const long long qfront = (long long)io.queue_ctr[0];  // queued envs (written by step_kernel, same stream)
-  const long long qn = qfront + (long long)io.queue_ctr[1];
-  if (qn == 0) return;
+  unsigned long long *ctr = io.queue_ctr;
+  const long long qfront = (long long)ctr[kCFront];  // queued envs (written by step_kernel, same stream)
+  const long long qn0 = qfront + (long long)ctr[kCBack];
+  if (qn0 + (long long)ctr[kCFull(0)] == 0) return;
   WarpStats ws;
   ws.init(sacc[wib], lane);
-
-  T *base = static_cast<T *>(io.state);
-  St<T> s;
-  StepCtl c = {1, 0, 0, 0.0f, false};
-  int me = 0;
-  bool active = false, exhausted = false;
-
-#pragma unroll 1
-  for (unsigned iter = 0;; ++iter) {
-    // ---- idle lanes claim queue entries (one atomic per refill event per warp)
-    unsigned idle = __ballot_sync(full, !active);
-    if (TB_UNLIKELY(idle && !exhausted && (idle == full || __popc(idle) >= kRefillMin || (iter & 15u) == 0))) {
-      int want = __popc(idle);
-      long long first = 0;
-      if (lane == 0) first = (long long)atomicAdd(io.queue_ctr + 2, (unsigned long long)want);
-      first = __shfl_sync(full, first, 0);
-      if (first + want >= qn) exhausted = true;
-      long long idx = first + __popc(idle & ((1u << lane) - 1u));
-      if (!active && idx < qn) {
-        me = io.queue[idx < qfront ? idx : io.n - 1 - (idx - qfront)];
-        load_state(base, io.n, (int64_t)me, s);
-        c.phase = 1;
-        c.events = (s.flags >> kFlagEventShift) & 0xff;
-        c.hit = 0; c.reward = 0.0f; c.done = false;
-        active = true;
-      }
+  unsigned epoch = 0;
+  int nsub = 0;  // substeps this lane integrated
+  bool ok = true;
+  const bool diag = blockIdx.x == 0 && threadIdx.x == 0;  // phase times as this CTA sees them (barrier to barrier)
+  unsigned long long t_mark = diag ? global_ns() : 0;
+  // round r: phase B serves the full queue (round 0: what step_kernel put there), its survivors join the round's fast
+  // queue; phase A runs the flights; whatever needs a full substep again waits for round r + 1
+  for (int round = 0; ok; ++round) {
+    const int p = round & 1;
+    // the other parity's counters were last read before the barrier that ended the previous round
+    if (round > 0 && blockIdx.x == 0 && threadIdx.x == 0) {
+      ctr[kCFast(p ^ 1)] = 0; ctr[kCFastClaim(p ^ 1)] = 0; ctr[kCFull(p ^ 1)] = 0; ctr[kCFullClaim(p ^ 1)] = 0;
     }
-    unsigned act_mask = __ballot_sync(full, active);
-    if (!act_mask) break;
-
-    // ---- one physics substep for every active lane
-    bool fin = false;
-    if (active) fin = env_substep<T, KIND>(sc, s, nullptr, c);
-    if (lane == 0) ws.acc[TB_STAT_PHYSICS_STEPS] += __popc(act_mask);
-#ifdef TB_DEBUG_ITERS  // experiment only: warp iterations x 32 in the env-steps slot, to read lane utilisation
-    if (lane == 0) ws.acc[TB_STAT_ENV_STEPS] += 32;
-#endif
-    if (fin) s.ret += (T)c.reward;
-    account<T>(ws, fin, c.done, 0, c.events, s.step, s.ret);
-    if (TB_UNLIKELY(fin)) {
-      s.flags &= kFlagDone;  // drop the in-flight mark and the parked event bits
-      finish_api<T, KIND>(sc, io, (int64_t)me, s, c.reward, c.done, c.events);
-      store_state(base, io.n, (int64_t)me, s);
-      if (io.pid && c.done && io.auto_reset) {
-        T z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-        store_pid(static_cast<T *>(io.pid), io.n, (int64_t)me, z);
-      }
-      active = false;
+    const long long nfull = (long long)ld_ctr(ctr + kCFull(p));
+    const bool to_end = round + 1 >= kFfMaxRounds;
+    if (nfull) ff_phase_full<T>(sc, io, io.queue_full, nfull, ctr + kCFullClaim(p), io.queue_b, ctr + kCFast(p), to_end, lane, &nsub);
+    if (!(ok = grid_barrier(ctr, epoch))) break;
+    if (diag) {
+      unsigned long long t = global_ns();
+      if (round < 6) ctr[kDPhase + 2 * round] = t - t_mark;
+      t_mark = t;
+      ctr[kDFullEnvs] += (unsigned long long)nfull;
+      ctr[kDRounds] = (unsigned long long)(round + 1);
     }
+    const long long n0 = round == 0 ? qn0 : 0, nfast = n0 + (long long)ld_ctr(ctr + kCFast(p));
+    if (nfast) ff_phase_fast<T>(sc, io, n0, round == 0 ? qfront : 0, io.queue_b, nfast, ctr + kCFastClaim(p), io.queue_full, ctr + kCFull(p ^ 1), lane, nsub);
+    if (!(ok = grid_barrier(ctr, epoch))) break;
+    if (diag) {
+      unsigned long long t = global_ns();
+      if (round < 6) ctr[kDPhase + 2 * round + 1] = t - t_mark;
+      t_mark = t;
+    }
+    if (ld_ctr(ctr + kCFull(p ^ 1)) == 0) break;
+  }
+  if (ok) {
+    nsub = __reduce_add_sync(0xffffffffu, nsub);
+    if (lane == 0) ws.acc[TB_STAT_PHYSICS_STEPS] += nsub;
+    const int64_t stride = (int64_t)gridDim.x * kBlock;
+    for (int64_t tile0 = (int64_t)blockIdx.x * kBlock + wib * 32; tile0 < io.n; tile0 += stride) ff_phase_finish<T>(sc, io, tile0, &ws);
+    if (diag) ctr[kDFinish] = global_ns() - t_mark;
   }
   ws.flush(io.stats);
 }
@@ -692,6 +985,51 @@ template <typename T> static void build_scene(const Params &p, Scene<T> &sc) {
     sc.racket_obb_radius = (T)(std::sqrt(h.racket_half_x * h.racket_half_x + ay * ay + zm * zm) * (1 + 1e-6));
   }
   build_prism<T, kGoalEdges>(sc.goal, h.goal_v, TB_GOAL_HALF_Z);
+  {
+    // fast-forward substep constants (ff_substep).  The three rejects are grown a little: they may only send a
+    // substep into the exact tests for nothing, never past them.
+    const double hack[3] = {-50.0, -2.0, -2.0};  // swingracket_env.py:135-141
+    const double *I = h.racket_inertia;
+    for (int i = 0; i < 3; ++i) {
+      sc.ff_hack[i] = (T)(p.dt * hack[i] / TB_RACKET_MASS);
+      sc.ff_gyro[i] = (T)(p.dt * p.gyro_term * (I[(i + 2) % 3] - I[(i + 1) % 3]) / I[i]);
+    }
+    sc.ff_dtg = (T)(p.dt * p.gravity_z);
+    sc.ff_kl = (T)(p.dt * p.lin_damping);
+    sc.ff_ka = (T)(p.dt * p.ang_damping);
+    sc.ff_qx2 = (T)(0.25 * p.dt * p.dt);
+    const double reach_r = TB_BALL_RADIUS + p.hull_margin + p.contact_threshold;
+    const double reach_b = TB_BALL_RADIUS + p.box_margin + p.contact_threshold;
+    const double grow = sizeof(T) == 8 ? 1e-9 : 1e-4;
+    sc.ff_slab = (T)(h.racket_half_x + reach_r + grow);
+    sc.ff_low_z = (T)(TB_FLOOR_HZ + p.contact_threshold + p.hull_margin + (double)sc.racket_obb_radius * (1 + 1e-6) + grow);
+    sc.ff_ball_z = (T)(std::fmax(std::fmax(TB_FLOOR_HZ, TB_NET_HZ), TB_GOAL_HALF_Z) + std::fmax(reach_r, reach_b) + grow);
+    auto hi_word = [](T v) {
+      unsigned long long bits = 0;
+      std::memcpy(&bits, &v, sizeof v);
+      return sizeof(T) == 8 ? (unsigned)(bits >> 32) : (unsigned)bits;
+    };
+    sc.vmax2_hi = hi_word((T)(p.max_coord_vel * p.max_coord_vel));
+    const double rr = (double)sc.racket.bound_radius + reach_r + grow, gr = TB_GOAL_RADIUS + reach_r + grow;
+    sc.ffp_racket_r2 = (T)(rr * rr * (1 + 1e-6));
+    sc.ffp_floor[0] = (T)(TB_FLOOR_HX + reach_b + grow); sc.ffp_floor[1] = (T)(TB_FLOOR_HY + reach_b + grow);
+    sc.ffp_floor[2] = (T)(TB_FLOOR_HZ + reach_b + grow);
+    sc.ffp_net[0] = (T)(TB_NET_HX + reach_b + grow); sc.ffp_net[1] = (T)(TB_NET_HY + reach_b + grow);
+    sc.ffp_net[2] = (T)(TB_NET_HZ + reach_b + grow);
+    sc.ffp_goal_z = (T)(TB_GOAL_HALF_Z + reach_r + grow);
+    sc.ffp_goal_r2 = (T)(gr * gr * (1 + 1e-6));
+    const double v9 = 0.9 * p.max_coord_vel;
+    sc.ffp_a2 = (T)std::fmin(0.99 * 2.5e-3 / (0.25 * p.dt * p.dt), v9 * v9);
+    sc.ffp_v2 = (T)(v9 * v9);
+    sc.ffp_low = sc.floor_h[2] + sc.contact_threshold;  // formed in T like physics_step does
+    sc.ffp_box[0] = (T)((double)sc.racket_box[0] + reach_r + grow); sc.ffp_box[1] = (T)((double)sc.racket_box[1] - reach_r - grow);
+    sc.ffp_box[2] = (T)((double)sc.racket_box[2] + reach_r + grow);
+    sc.ffl_inv_dt = (T)(1.0 / p.dt); sc.ffl_erp_dt = (T)(p.contact_erp / p.dt); sc.ffl_m = (T)TB_BALL_MASS;
+    sc.ffl_jinv_t = (T)(1.0 / (1.0 / TB_BALL_MASS + TB_BALL_RADIUS * TB_BALL_RADIUS / (0.4 * TB_BALL_MASS * TB_BALL_RADIUS * TB_BALL_RADIUS)));
+    sc.ffp_court[0] = sc.floor_h[0] + 1; sc.ffp_court[1] = sc.floor_h[1] + 1;
+    sc.ffp_face[0] = (T)(TB_FLOOR_HX - p.box_margin - grow); sc.ffp_face[1] = (T)(TB_FLOOR_HY - p.box_margin - grow);
+    sc.ffp_face[2] = (T)(TB_FLOOR_HZ - p.box_margin + grow);
+  }
 }
 
 }  // namespace tb
@@ -726,7 +1064,8 @@ struct tb_ctx {
   uint8_t *d_done = nullptr, *d_events = nullptr, *d_mask = nullptr;
   int64_t launches = 0;
   int *queue = nullptr;                      // fast-forward work queue (env indices), num_envs entries
-  unsigned long long *queue_ctrs = nullptr;  // two (front, back, claimed) counter triples used by alternate steps
+  int *queue_b = nullptr, *queue_full = nullptr;
+  unsigned long long *queue_ctrs = nullptr;  // two counter sets (kCtrWords each) used by alternate steps
   int parity = 0;
   unsigned ff_grid = 0;                      // persistent grid of ff_kernel
   int control_mode = TB_CONTROL_FORCE;
@@ -798,9 +1137,9 @@ template <typename T> static int ff_grid_size(tb_ctx *c, unsigned *grid) {
 }
 // One env step = step_kernel (+ ff_kernel for SwingRacket) on `stream`.
 static int launch_step(tb_ctx *c, StepIO &io, cudaStream_t stream, bool stage = false) {
-  io.queue = c->queue;
-  io.queue_ctr = c->queue_ctrs + 3 * c->parity;
-  io.queue_ctr_next = c->queue_ctrs + 3 * (c->parity ^ 1);
+  io.queue = c->queue; io.queue_b = c->queue_b; io.queue_full = c->queue_full;
+  io.queue_ctr = c->queue_ctrs + kCtrWords * c->parity;
+  io.queue_ctr_next = c->queue_ctrs + kCtrWords * (c->parity ^ 1);
   c->parity ^= 1;
   const unsigned grid = grid_for(io.n, kBlock);
   const bool swing = c->cfg.env_kind == TB_ENV_SWING;
@@ -898,12 +1237,14 @@ int tb_create(const tb_config *cfg, tb_ctx **out) {
   size_t bytes = (size_t)cfg->num_envs * kPacks * 4 * word;
   cudaError_t e = cudaMalloc(&c->state, bytes);
   if (e == cudaSuccess) e = cudaMalloc(&c->stats, TB_NUM_STATS * sizeof(unsigned long long));
-  if (e == cudaSuccess) e = cudaMalloc(&c->queue_ctrs, 6 * sizeof(unsigned long long));
+  if (e == cudaSuccess) e = cudaMalloc(&c->queue_ctrs, 2 * kCtrWords * sizeof(unsigned long long));
   if (e == cudaSuccess && cfg->env_kind == TB_ENV_SWING) e = cudaMalloc(&c->queue, (size_t)cfg->num_envs * sizeof(int));
+  if (e == cudaSuccess && cfg->env_kind == TB_ENV_SWING) e = cudaMalloc(&c->queue_b, (size_t)cfg->num_envs * sizeof(int));
+  if (e == cudaSuccess && cfg->env_kind == TB_ENV_SWING) e = cudaMalloc(&c->queue_full, (size_t)cfg->num_envs * sizeof(int));
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaMemsetAsync(c->state, 0, bytes, c->own_stream);
   if (e == cudaSuccess) e = cudaMemsetAsync(c->stats, 0, TB_NUM_STATS * sizeof(unsigned long long), c->own_stream);
-  if (e == cudaSuccess) e = cudaMemsetAsync(c->queue_ctrs, 0, 6 * sizeof(unsigned long long), c->own_stream);
+  if (e == cudaSuccess) e = cudaMemsetAsync(c->queue_ctrs, 0, 2 * kCtrWords * sizeof(unsigned long long), c->own_stream);
   if (e == cudaSuccess) {
     // identity quaternion, episode = -1 so the first reset starts episode 0
     std::size_t n = (size_t)cfg->num_envs;
@@ -939,7 +1280,7 @@ int tb_destroy(tb_ctx *c) {
   DeviceGuard g(c->cfg.device);
   if (c->own_stream) { cudaStreamSynchronize(c->own_stream); cudaStreamDestroy(c->own_stream); }
   for (int i = 0; i < 3; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
-  cudaFree(c->state); cudaFree(c->stats); cudaFree(c->queue_ctrs); cudaFree(c->queue); cudaFree(c->pid);
+  cudaFree(c->state); cudaFree(c->stats); cudaFree(c->queue_ctrs); cudaFree(c->queue); cudaFree(c->queue_b); cudaFree(c->queue_full); cudaFree(c->pid);
   cudaFree(c->d_actions); cudaFree(c->d_obs); cudaFree(c->d_reward); cudaFree(c->d_term);
   cudaFree(c->d_done); cudaFree(c->d_events); cudaFree(c->d_mask);
   delete c;
@@ -1120,6 +1461,21 @@ int tb_get_kernel_timing(tb_ctx *c, double *ms_step_kernel, double *ms_ff_kernel
   if (!c || !ms_step_kernel || !ms_ff_kernel || !steps) return fail("%s", "tb_get_kernel_timing: bad argument");
   *ms_step_kernel = c->ms_step; *ms_ff_kernel = c->ms_ff; *steps = c->timed_steps;
   c->ms_step = c->ms_ff = 0; c->timed_steps = 0;
+  return 0;
+}
+
+int tb_ff_diagnostics(tb_ctx *c, int64_t *h_out) {
+  GUARD(c);
+  if (!h_out) return fail("%s", "tb_ff_diagnostics: h_out is NULL");
+  CU(cudaDeviceSynchronize());
+  unsigned long long h[2 * kCtrWords];
+  CU(cudaMemcpy(h, c->queue_ctrs, sizeof h, cudaMemcpyDeviceToHost));
+  // the set of the most recent step that entered the fast-forward: the one whose round count is non-zero and whose
+  // twin was zeroed since (both non-zero cannot happen: every step_kernel zeroes the next step's set)
+  const unsigned long long *s = h[kDRounds] ? h : h + kCtrWords;
+  for (int i = 0; i < 14; ++i) h_out[i] = (int64_t)s[kDRounds + i];
+  h_out[14] = (int64_t)s[kDFinish];
+  h_out[15] = (int64_t)s[kCError];
   return 0;
 }
 

@@ -9,8 +9,8 @@ env = sys.argv[3] if len(sys.argv) > 3 else "SwingRacket-v0"
 steps = int(sys.argv[4]) if len(sys.argv) > 4 else 27
 b = TennisBatch(env, n, precision=prec, seed=0)
 b.reset()
-a = torch.empty((n, b.act_dim), device="cuda").uniform_(-1, 1)
+acts = [torch.empty((n, b.act_dim), device="cuda").uniform_(-1, 1) for _ in range(4)]  # the ring bench.py steps through
 for t in range(steps):
-    b.step(a)
+    b.step(acts[t % 4])
 torch.cuda.synchronize()
 print(b.read_stats())

@@ -1,0 +1,21 @@
+"""Per-step device times of step_kernel and ff_kernel over one lock-step SwingRacket episode (events inside the library).
+usage: time_kernels.py precision n_envs"""
+import sys
+import torch
+sys.path.insert(0, ".")
+from tennisbot_rl_b200.batch import TennisBatch
+prec = sys.argv[1]; n = int(sys.argv[2])
+b = TennisBatch("SwingRacket-v0", n, precision=prec, seed=0)
+b.reset()
+acts = [torch.empty((n, b.act_dim), device="cuda").uniform_(-1, 1) for _ in range(4)]
+for t in range(26): b.step(acts[t % 4])
+torch.cuda.synchronize()
+b.set_kernel_timing(True)
+rows = []
+for t in range(26):
+    b.step(acts[t % 4])
+    rows.append(b.kernel_timing())
+for t, r in enumerate(rows):
+    if t % 26 >= 23 or t % 26 == 0: print(t, "step_kernel %.4f ms ff_kernel %.4f ms" % (r[0], r[1]))
+d = b.ff_diagnostics()
+print("ff diagnostics: rounds %d, envs through the full path %d, phase ns %s, finish ns %d, barrier error %d" % (d[0], d[1], d[2:14].tolist(), d[14], d[15]))
