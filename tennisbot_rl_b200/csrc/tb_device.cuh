@@ -138,6 +138,7 @@ template <typename T> struct Scene {
   T ffp_face[3];               // the floor's top face without its margin rim: x, y half extents and the core's top
   T ffp_low, ffp_court[2];     // TB_EV_RACKET_LOW: floor top + contact threshold; court half extents + 1
   T ffp_box[3];                // racket outline bounding box + reach (max |y|, min z, max z), grown
+  T ffp_rim;                   // reach beyond the racket outline, grown
   T ffl_inv_dt, ffl_erp_dt, ffl_m, ffl_jinv_t;  // landing hook: 1/dt, erp/dt, ball mass, 1/(1/m + r^2/I)
   Prism<T, kRacketEdges> racket;
   Prism<T, kGoalEdges> goal;
@@ -1079,6 +1080,18 @@ __device__ __forceinline__ int ff_classify_core(const Scene<T> &sc, const T *rp,
     T pl1 = 2 * (x * y - z * w) * rel[0] + (1 - 2 * (x * x + z * z)) * rel[1] + 2 * (y * z + x * w) * rel[2];
     T pl2 = 2 * (x * z + y * w) * rel[0] + 2 * (y * z - x * w) * rel[1] + (1 - 2 * (x * x + y * y)) * rel[2];
     racket = !(M<T>::abs(pl1) > sc.ffp_box[0]) & !(pl2 > sc.ffp_box[2]) & !(pl2 < sc.ffp_box[1]);
+    if (racket) {
+      // ... and the outline itself: the signed distance to any edge line is a lower bound of the distance to the hull.
+      // A ball that lingers beside a racket it missed (both in free fall) stays out of the full path this way.
+      T max_side = -M<T>::inf();
+#pragma unroll 2
+      for (int i = 0; i < kRacketEdges; ++i) {
+        const Edge<T> &e = sc.racket.e[i];
+        T side = (pl1 - e.ax) * e.nx + (pl2 - e.ay) * e.ny;
+        max_side = side > max_side ? side : max_side;
+      }
+      racket = !(max_side > sc.ffp_rim);
+    }
   }
   const T ax = M<T>::abs(bp[0]), ay = M<T>::abs(bp[1]), az = M<T>::abs(bp[2]);
   T gx = bp[0] - goal[0], gy = bp[1] - goal[1];

@@ -103,7 +103,11 @@ struct StepIO {
   int32_t *done_count;
   unsigned long long *stats;
   int *queue;                        // env indices waiting for ff_kernel: long flights from the front, short from the back
-  int *queue_b, *queue_full;         // ff_kernel's own queues: fast queue of odd rounds, envs waiting for a full substep
+  int *queue_full;                   // envs whose FIRST fast-forward substep needs the full treatment (step_kernel fills it)
+  unsigned long long *dq_full, *dq_late;  // ff_kernel's dynamic queues (slots tagged with `epoch`): envs parked for a full
+                                     // substep; envs whose flight goes on after one.  dq_cap slots each
+  long long dq_cap;
+  unsigned epoch;                    // step counter of the context, never 0: tag of this launch's queue slots
   unsigned long long *queue_ctr;     // kCtrWords counters (kC* below): [0] front, [1] back entries appended by this
                                      // step's step_kernel, the rest ff_kernel's
   unsigned long long *queue_ctr_next;  // the set the NEXT step uses; step_kernel zeroes it
@@ -166,15 +170,17 @@ constexpr int kFlagDone = 1, kFlagInFlight = 2, kFlagEventShift = 8;
 constexpr int kFlagLanded = 4;      // the env step is over; outputs / statistics / auto-reset pending
 constexpr int kFlagFirst = 8;       // the flight's first substep (no external force) has not been taken yet
 constexpr int kFlagLastShift = 16;  // contact bits of the flight's last substep
+constexpr int kFlagVisitShift = 4;  // 2 bits: visits to the full path during this flight
 // counter words of one step's set
-constexpr int kCtrWords = 32;  // 16 counters + 16 diagnostic words (kD*)
-constexpr int kCFront = 0, kCBack = 1, kCBarrier = 2, kCError = 3;
-constexpr int kDRounds = 16, kDFullEnvs = 17, kDPhase = 18, kDFinish = 30;  // tb_ff_diagnostics
-// per ff round parity p: entries of the fast queue, claimed of it, entries of the full queue, claimed of it
-__host__ __device__ constexpr int kCFast(int p) { return 4 + 4 * p; }
-__host__ __device__ constexpr int kCFastClaim(int p) { return 5 + 4 * p; }
-__host__ __device__ constexpr int kCFull(int p) { return 6 + 4 * p; }
-__host__ __device__ constexpr int kCFullClaim(int p) { return 7 + 4 * p; }
+constexpr int kCtrWords = 512;  // (words 128.. : TB_FF_DIAG time series)  // four 128-byte lines: what is polled never shares a line with what is claimed from
+constexpr int kCFront = 0, kCBack = 1, kCError = 3;
+constexpr int kDRounds = 48, kDFullEnvs = 49, kDPhase = 50, kDFinish = 62;  // tb_ff_diagnostics
+constexpr int kCFull0 = 4;        // entries of queue_full (appended by step_kernel)
+constexpr int kCClaim0 = 5;       // claimed entries of queue (ff_kernel's flight lanes)
+constexpr int kCFullClaim0 = 6;   // claimed entries of queue_full (ff_kernel's servers)
+constexpr int kCFullTail = 16, kCFullHead = 17;  // dq_full: reserved by producers / claimed by servers
+constexpr int kCLateTail = 32, kCLateHead = 33;  // dq_late: reserved by servers / claimed by flight lanes
+constexpr int kCLanded = 64;      // envs whose env step is over (own line: everybody polls it at the end)
 
 struct WarpStats {
   unsigned long long *acc;  // this warp's row of the CTA's shared accumulators
@@ -287,7 +293,8 @@ __global__ void __launch_bounds__(kBlock, StepMinBlocks<T>::v) step_kernel(const
   float *s_tile = s_tiles[STAGE ? wib : 0];
   WarpStats ws;
   ws.init(sacc[wib], lane);
-  if (blockIdx.x == 0 && threadIdx.x < kCtrWords) io.queue_ctr_next[threadIdx.x] = 0;
+  if (blockIdx.x == 0)
+    for (int i = threadIdx.x; i < kCtrWords; i += kBlock) io.queue_ctr_next[i] = 0;
 
   const int64_t tile0 = (int64_t)blockIdx.x * kBlock + wib * 32, me = tile0 + lane;
   const bool valid = me < io.n;
@@ -360,7 +367,7 @@ __global__ void __launch_bounds__(kBlock, StepMinBlocks<T>::v) step_kernel(const
         s_cnt[k * W + w] = tot;
         tot += a;
       }
-      unsigned long long *ctr = io.queue_ctr + (k == 0 ? kCFront : k == 1 ? kCBack : kCFull(0));
+      unsigned long long *ctr = io.queue_ctr + (k == 0 ? kCFront : k == 1 ? kCBack : kCFull0);
       s_base[k] = tot ? atomicAdd(ctr, (unsigned long long)tot) : 0ULL;
     }
     __syncthreads();
@@ -376,74 +383,88 @@ __global__ void __launch_bounds__(kBlock, StepMinBlocks<T>::v) step_kernel(const
   ws.flush(io.stats);
 }
 
-// Fast-forward continuation (SwingRacket only): one persistent launch (a CTA per resident slot) that runs in PHASES
-// separated by grid-wide barriers, so that at any time every warp of an SM executes the same small piece of code:
+// Fast-forward continuation (SwingRacket only): one persistent launch (a CTA per resident slot) whose warps have roles:
 //
-//   A  fast   every LANE is a small state machine: claim an env from the round's fast queue, keep its state in registers
-//             and take ff_fast substeps (a straight line, the court landing included) until the flight ends or a
-//             substep needs the full treatment; then hand the env on through HBM (landed mark, or the full queue)
-//             and claim the next one.  Leaving / claiming is done for several lanes of a warp at once.  A lane in an
-//             800-substep flight delays nobody; the longest flights are queued first.
-//   B  full   one lane per queued env: generic substeps (ff_full: narrow phase, contact solve, time-out) until the
-//             env step ends or ff_fast applies again; those go to the next round's fast queue.
-//   ... A, B repeat until no env is left in flight (rounds beyond kFfMaxRounds finish in B) ...
-//   C  finish every env that landed: reward, statistics, outputs, auto-reset, one coalesced pass like step_kernel.
+//   flight warps  every LANE is a small state machine: claim an env, keep its flight state in registers and take ff_fast
+//                 substeps (a straight line, the court landing included) until the flight ends or a substep needs the full
+//                 treatment; then hand the env on through HBM (landed mark, or the dynamic full queue) and claim the next
+//                 one - from step_kernel's queue (longest flights first) and, once that is empty, from the late queue.
+//                 Leaving / claiming is done for several lanes of a warp at once.  A lane in an 800-substep flight
+//                 delays nobody, and no rare code ever enters these warps' instruction stream.
+//   server warps  (one in kServerStride CTAs' last warp) poll the full queues: generic substeps (ff_full: narrow phase,
+//                 contact solve, time-out) for one env per lane until ff_fast applies again; the env then goes to the
+//                 late queue, or is marked landed.  Contact chains (a ball rolling on the racket face takes dozens
+//                 of full substeps) therefore run concurrently with the bulk of the flights, and the long flight that
+//                 follows a late hit starts at once.
+//   everybody     when all envs have landed: the finishing pass - reward, statistics, outputs, auto-reset for every
+//                 env, coalesced like step_kernel.
 //
-// Mixed into one loop, each landing / claim / contact stalled 31 other lanes and streamed ~40 KB of rare code
-// through the instruction caches the substep loop lives in (measured: 2.2x slower).
+// History (measured on B200, 1 Mi envs, f64): everything in one loop per lane 6.8 ms (every landing / claim /
+// contact stalled 31 other lanes and streamed ~40 KB of rare code through the instruction caches of the substep
+// loop); the same work in barrier-separated phases 4.6 - 5.0 ms (every round of "contact, then fly on" paid the latency
+// of its longest chain and longest flight); roles: see profiles/.
 #ifndef TB_FF_SERVE_MIN
 #define TB_FF_SERVE_MIN 8
 #endif
 #ifndef TB_FF_SERVE_WAIT
 #define TB_FF_SERVE_WAIT 12
 #endif
-constexpr int kServeMin = TB_FF_SERVE_MIN, kServeWait = TB_FF_SERVE_WAIT;
-constexpr int kIdle = 4;  // lane states 0..3 = kFfFree, kFfLand (running), kFfFull, kFfDone (leaving)
-constexpr int kFfMaxRounds = 3;  // the last round's phase B runs its envs to the end of their flights
+#ifndef TB_FF_SERVER_STRIDE
+#define TB_FF_SERVER_STRIDE 2
+#endif
+#ifndef TB_FF_SERVER_LANES
+#define TB_FF_SERVER_LANES 32
+#endif
+constexpr int kServeMin = TB_FF_SERVE_MIN, kServeWait = TB_FF_SERVE_WAIT, kServerStride = TB_FF_SERVER_STRIDE, kServerLanes = TB_FF_SERVER_LANES;
+constexpr int kIdle = 4, kWait = 5, kRetired = 6;  // lane states 0..3 = kFfFree, kFfLand (running), kFfFull, kFfDone (leaving);
+                                                   // no env; no env, holds a late-queue ticket; no env, never will
+constexpr int kFfMaxVisits = 3;  // an env that comes to the servers this often finishes its flight there
+constexpr long long kSpinLimit = 1LL << 33;  // clock cycles (~4 s) any wait may take before the launch gives up
 
-__device__ __forceinline__ unsigned long long ld_ctr(const unsigned long long *p) { return __ldcg(p); }
+__device__ __forceinline__ unsigned long long ld_ctr(const unsigned long long *p) { return *reinterpret_cast<const volatile unsigned long long *>(p); }
 __device__ __forceinline__ unsigned long long global_ns() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
   return t;
 }
 
-// All CTAs of the (co-resident) grid meet.  Returns false if the barrier could not complete (another CTA gave up or a
-// time-out: the launch then ends without finishing its envs instead of hanging the device).
-__device__ __forceinline__ bool grid_barrier(unsigned long long *ctr, unsigned &epoch) {
-  __shared__ int s_ok;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    __threadfence();
-    const unsigned long long target = (unsigned long long)(++epoch) * gridDim.x;
-    atomicAdd(ctr + kCBarrier, 1ULL);
-    int ok = 1;
-    long long t0 = clock64();
-    while (ld_ctr(ctr + kCBarrier) < target) {
-      __nanosleep(200);
-      if (ld_ctr(ctr + kCError) || clock64() - t0 > (1LL << 33)) {  // ~4 s
-        atomicExch(ctr + kCError, 1ULL);
-        ok = 0;
-        break;
-      }
-    }
-    __threadfence();
-    s_ok = ok;
-  }
-  __syncthreads();
-  return s_ok != 0;
-}
-
-// warp-aggregated append of `me` (for lanes with pred) to a queue
-__device__ __forceinline__ void queue_push(int *q, unsigned long long *count, bool pred, int me, int lane) {
+// warp-aggregated reservation of slots in a dynamic queue + tagged publication of `me` (for lanes with pred).  The
+// env's state must have been stored before the call.
+__device__ __forceinline__ void dq_push(unsigned long long *q, long long cap, unsigned long long *tail, unsigned epoch, bool pred,
+                                        int me, int lane, unsigned long long *err) {
   const unsigned full = 0xffffffffu;
   unsigned m = __ballot_sync(full, pred);
   if (!m) return;
   int leader = __ffs(m) - 1;
-  unsigned long long base = 0;
-  if (lane == leader) base = atomicAdd(count, (unsigned long long)__popc(m));
-  base = __shfl_sync(full, base, leader);
-  if (pred) q[base + __popc(m & ((1u << lane) - 1u))] = me;
+  unsigned long long at = 0;
+  if (lane == leader) at = atomicAdd(tail, (unsigned long long)__popc(m));
+  at = __shfl_sync(full, at, leader);
+  if (pred) {
+    unsigned long long idx = at + __popc(m & ((1u << lane) - 1u));
+    if ((long long)idx < cap) {
+      __threadfence();  // state before publication
+      *reinterpret_cast<volatile unsigned long long *>(q + idx) = ((unsigned long long)epoch << 32) | (unsigned)me;
+    } else {
+      atomicExch(err, 2ULL);  // cannot happen: every env is pushed at most kFfMaxVisits times
+    }
+  }
+}
+// Consumers take TICKETS: one atomicAdd per warp reserves the next slots of a queue, filled or not, and every lane then
+// polls its own slot (its own address: no contention) until a producer's tagged store lands there - entries and
+// waiting lanes are matched first come, first served.  (Claiming only what is already there needs a compare-and-swap
+// loop on the head, which collapses when a thousand warps go for the same late entries: measured 3 entries / us.)
+__device__ __forceinline__ long long dq_reserve(unsigned long long *head, unsigned idle_mask, int lane) {
+  long long at = 0;
+  if (lane == 0) at = (long long)atomicAdd(head, (unsigned long long)__popc(idle_mask));
+  at = __shfl_sync(0xffffffffu, at, 0);
+  return at + __popc(idle_mask & ((1u << lane) - 1u));
+}
+// the env index in slot `ticket` if its producer has published it (state visible to the caller afterwards), else -1
+__device__ __forceinline__ int dq_poll(const unsigned long long *q, long long ticket, unsigned epoch) {
+  unsigned long long v = *reinterpret_cast<const volatile unsigned long long *>(q + ticket);
+  if ((unsigned)(v >> 32) != epoch) return -1;
+  __threadfence();
+  return (int)(unsigned)v;
 }
 
 // state loads that bypass L1: another SM may have rewritten the env since this SM last saw it (same launch)
@@ -494,15 +515,13 @@ template <typename T> __device__ __forceinline__ void ff_store(T *base, int64_t 
   p7[1] = int_as(T(), L.step); p7[2] = int_as(T(), flags);
 }
 
-// Phase A for one warp.  The round's fast queue: the n0 entries step_kernel queued (front / back layout, qfront of them
-// at the front; round 0 only) followed by the entries phase B just appended to lateq; nfast in all, claimed through
-// *claim.  Envs that need a full substep are appended to fullq.
+// A flight warp.  n0 / qfront: step_kernel's queue (front / back layout); total: envs in flight in this launch.
 template <typename T>
-__device__ __forceinline__ void ff_phase_fast(const Scene<T> &sc, const StepIO &io, long long n0, long long qfront, const int *lateq,
-                                              long long nfast, unsigned long long *claim, int *fullq,
-                                              unsigned long long *nfull, int lane, int &nsub) {
+__device__ __forceinline__ void ff_flight_warp(const Scene<T> &sc, const StepIO &io, long long n0, long long qfront, long long total,
+                                               int lane, int &nsub) {
   const unsigned full = 0xffffffffu;
   T *base = static_cast<T *>(io.state);
+  unsigned long long *ctr = io.queue_ctr;
   FfLane<T> L;
   {  // defined values for lanes that never get an env (ff_fast is never run on them)
     T *z = reinterpret_cast<T *>(&L);
@@ -510,11 +529,15 @@ __device__ __forceinline__ void ff_phase_fast(const Scene<T> &sc, const StepIO &
     for (int i = 0; i < (int)(offsetof(FfLane<T>, step) / sizeof(T)); ++i) z[i] = 0;
     L.step = 0; L.events = 0;
   }
-  int me = 0, st = kIdle, waited = 0, step0 = 0;
-  bool exhausted = false, first = false, first_pending = false;
+  int me = 0, st = kIdle, waited = 0, step0 = 0, visits = 0;
+  long long ticket = 0;
+  unsigned serves = 0;
+  bool exhausted0 = n0 == 0, first = false, first_pending = false;
+  long long idle_since = 0;
+  unsigned nap = 0;  // idle back-off: thousands of warps polling one cache line would starve the servers' atomics on it
   for (;;) {
     // ---- substeps until enough lanes want to leave / claim (no call, no rare code in this loop)
-    unsigned run_m, wait_m;
+    unsigned run_m, leave_m;
 #pragma unroll 1
     for (;;) {
       if (st <= kFfLand) st = ff_fast<T>(sc, L, st);
@@ -527,101 +550,250 @@ __device__ __forceinline__ void ff_phase_fast(const Scene<T> &sc, const StepIO &
         first_pending = false;
       }
       run_m = __ballot_sync(full, st <= kFfLand);
-      wait_m = exhausted ? __ballot_sync(full, st == kFfFull || st == kFfDone) : ~run_m;
-      waited = wait_m ? waited + 1 : 0;
+      leave_m = __ballot_sync(full, st == kFfFull || st == kFfDone);
+      // lanes that wait: the leaving ones, and the idle ones while step_kernel's queue still has entries; idle lanes
+      // look at the late queue every kServeWait iterations
+      unsigned wait_m = exhausted0 ? leave_m : ~run_m;
+      waited = (wait_m | ~run_m) ? waited + 1 : 0;
       if (!run_m || __popc(wait_m) >= kServeMin || waited >= kServeWait) break;
     }
-    if (!(run_m | wait_m)) break;
     waited = 0;
-    // ---- lanes whose flight left ff_fast: state back to HBM, landed mark or the full queue
-    if (st == kFfFull || st == kFfDone) {
-      nsub += L.step - step0;
-      int flags = kFlagInFlight | (L.events << kFlagEventShift);
-      if (st == kFfDone) flags |= kFlagLanded | (TB_EV_COURT_BALL << kFlagLastShift);  // ff_fast ends on the court's top face only
-      ff_store(base, io.n, (int64_t)me, L, flags);
+    // ---- lanes whose flight left ff_fast: state back to HBM; landed mark, or the full queue
+    if (leave_m) {
+      const bool leaving = st == kFfFull || st == kFfDone;
+      if (leaving) {
+        nsub += L.step - step0;
+        int flags = kFlagInFlight | (L.events << kFlagEventShift) | (visits << kFlagVisitShift);
+        if (st == kFfDone) flags |= kFlagLanded | (TB_EV_COURT_BALL << kFlagLastShift);  // ff_fast ends on the court's top face only
+        ff_store(base, io.n, (int64_t)me, L, flags);
+      }
+      dq_push(io.dq_full, io.dq_cap, ctr + kCFullTail, io.epoch, st == kFfFull, me, lane, ctr + kCError);
+      unsigned done_m = __ballot_sync(full, st == kFfDone);
+      if (done_m) {
+        __threadfence();  // landed states before the count
+        if (lane == 0) atomicAdd(ctr + kCLanded, (unsigned long long)__popc(done_m));
+      }
+      if (leaving) st = kIdle;
     }
-    queue_push(fullq, nfull, st == kFfFull, me, lane);
-    if (st == kFfFull || st == kFfDone) st = kIdle;
-    // ---- idle lanes claim queue entries (one atomic per warp)
+#ifdef TB_FF_DIAG
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+      unsigned long long ld = ld_ctr(ctr + kCLanded), t = global_ns();
+      if (!ctr[kDPhase + 1] && ld * 2 >= (unsigned long long)total) ctr[kDPhase + 1] = t;
+      if (!ctr[kDPhase + 2] && ld * 10 >= (unsigned long long)total * 9) ctr[kDPhase + 2] = t;
+      if (!ctr[kDPhase + 3] && ld * 100 >= (unsigned long long)total * 99) ctr[kDPhase + 3] = t;
+    }
+#endif
+    // ---- lanes without an env: the next entries of step_kernel's queue (one atomic per warp); once that is empty, a
+    //      ticket each for the late queue, polled here every time round
+    bool got = false;
+    if (st == kWait) {
+      int e = dq_poll(io.dq_late, ticket, io.epoch);
+      if (e >= 0) { me = e; got = true; }
+    }
     unsigned idle = __ballot_sync(full, st == kIdle);
-    if (idle && !exhausted) {
-      int want = __popc(idle);
-      long long at = 0;
-      if (lane == 0) at = (long long)atomicAdd(claim, (unsigned long long)want);
-      at = __shfl_sync(full, at, 0);
-      if (at + want >= nfast) exhausted = true;
-      long long idx = at + __popc(idle & ((1u << lane) - 1u));
-      bool got = st == kIdle && idx < nfast;
-      bool to_full = false;
-      if (got) {
-        me = idx < qfront ? __ldcg(io.queue + idx) : idx < n0 ? __ldcg(io.queue + (io.n - 1 - (idx - qfront))) : __ldcg(lateq + (idx - n0));
-        int flags = ff_load(base, io.n, (int64_t)me, L);
-        step0 = L.step;
-        st = ff_classify(sc, L);
-        if (st == kFfFull) {  // starts within reach of something: untouched, straight to the full queue
-          to_full = true;
-        } else if (flags & kFlagFirst) {
-          // the flight's first substep carries no force (swingracket_env.py:105-107): with the target on the racket
-          // itself the force law gives exactly zero; the real target comes back after that substep (first_pending)
-          L.tgt[0] = L.rp[0]; L.tgt[1] = L.rp[1]; L.tgt[2] = L.rp[2];
-          first = true;
+    if (idle) {
+      const int rank = __popc(idle & ((1u << lane) - 1u));
+      // late entries first (a flight that goes on after a racket contact is likely a long one): as many tickets as
+      // entries wait right now, looked up every fourth time while step_kernel's queue lasts; everything after that
+      int nlate = 32;
+      if (!exhausted0) {
+        nlate = 0;
+        if ((serves++ & 3u) == 0) {
+          if (lane == 0) {
+            long long avail = (long long)(ld_ctr(ctr + kCLateTail) - ld_ctr(ctr + kCLateHead));
+            nlate = avail < 0 ? 0 : avail > 32 ? 32 : (int)avail;
+          }
+          nlate = __shfl_sync(full, nlate, 0);
         }
       }
-      queue_push(fullq, nfull, to_full, me, lane);
-      if (to_full) st = kIdle;
-      first_pending = __any_sync(full, first);
+      const bool pick_late = st == kIdle && rank < nlate;
+      const unsigned late_m = __ballot_sync(full, pick_late), init_m = idle & ~late_m;
+      if (late_m) {
+        long long t = dq_reserve(ctr + kCLateHead, late_m, lane);
+        if (pick_late) {
+          ticket = t;
+          st = t < io.dq_cap ? kWait : kRetired;  // (more tickets than slots: only possible long after the last entry)
+        }
+      }
+      if (init_m && !exhausted0) {
+        const int want = __popc(init_m);
+        long long at = 0;
+        if (lane == 0) at = (long long)atomicAdd(ctr + kCClaim0, (unsigned long long)want);
+        at = __shfl_sync(full, at, 0);
+        if (at + want >= n0) exhausted0 = true;
+        long long idx = at + __popc(init_m & ((1u << lane) - 1u));
+        if (st == kIdle && idx < n0) {
+          me = idx < qfront ? __ldcg(io.queue + idx) : __ldcg(io.queue + (io.n - 1 - (idx - qfront)));
+          got = true;
+        }
+      }
+    }
+    bool to_full = false;
+    if (got) {
+      int flags = ff_load(base, io.n, (int64_t)me, L);
+      visits = (flags >> kFlagVisitShift) & 3;
+      step0 = L.step;
+      st = ff_classify(sc, L);
+      if (st == kFfFull) {  // within reach of something (rounding apart, only after set_state): untouched, to the servers
+        to_full = true;
+      } else if (flags & kFlagFirst) {
+        // the flight's first substep carries no force (swingracket_env.py:105-107): with the target on the racket
+        // itself the force law gives exactly zero; the real target comes back after that substep (first_pending)
+        L.tgt[0] = L.rp[0]; L.tgt[1] = L.rp[1]; L.tgt[2] = L.rp[2];
+        first = true;
+      }
+    }
+    dq_push(io.dq_full, io.dq_cap, ctr + kCFullTail, io.epoch, to_full, me, lane, ctr + kCError);
+    if (to_full) st = kIdle;
+    first_pending = __any_sync(full, first);
+    const int got_any = __any_sync(full, got);
+    // ---- nothing to run and nothing to claim: done when every env has landed, else wait for the servers
+    if (!run_m && !got_any) {
+      if (ld_ctr(ctr + kCLanded) >= (unsigned long long)total) break;
+      long long now = clock64();
+      if (!idle_since) idle_since = now;
+      if (now - idle_since > kSpinLimit) { atomicExch(ctr + kCError, 4ULL); break; }
+      nap = nap ? min(nap * 2, 32000u) : 1000u;
+      __nanosleep(nap);
+    } else {
+      idle_since = 0;
+      nap = 0;
     }
   }
 }
 
-// Phase B for one warp: 32 queued envs at a time, one per lane, generic substeps until ff_fast applies again (or, with
-// to_end, until the env step is over).
+// A server warp: every lane holds one parked env at a time and takes generic substeps with it until ff_fast applies again
+// (or, for an env that keeps coming back, until its env step is over); then it hands the env on and claims the next one.
+// Chains differ wildly in length (one contact step ... a ball rolling on the racket face for the rest of its flight), so
+// lanes are refilled one by one, not batch by batch.
 template <typename T>
-__device__ __noinline__ void ff_phase_full(const Scene<T> &sc, const StepIO &io, const int *fullq, long long nfull,
-                                           unsigned long long *claim, int *nextq, unsigned long long *nnext, bool to_end,
-                                           int lane, int *nsub) {
+__device__ __noinline__ void ff_server_warp(const Scene<T> &sc, const StepIO &io, long long nfull0, long long total, int lane, int *nsub) {
   const unsigned full = 0xffffffffu;
   T *base = static_cast<T *>(io.state);
+  unsigned long long *ctr = io.queue_ctr;
+  bool exhausted0 = nfull0 == 0, busy = false, to_end = false, waiting = false;
+  long long idle_since = 0, ticket = 0;
+  unsigned nap = 0;
+#ifdef TB_FF_DIAG
+  int chain = 0;
+#endif
+  FfLane<T> L;
+  int me = 0, r = kFfDone, phase = 2, last = 0, visits = 0, step0 = 0;
+#ifdef TB_FF_DIAG
+  const unsigned long long ts0 = global_ns();
+#endif
   for (;;) {
-    long long at = 0;
-    if (lane == 0) at = (long long)atomicAdd(claim, 32ULL);
-    at = __shfl_sync(full, at, 0);
-    if (at >= nfull) break;
-    const bool have = at + lane < nfull;
-    int me = 0, r = kFfDone;
-    if (have) {
-      me = __ldcg(fullq + at + lane);
-      FfLane<T> L;
-      int flags = ff_load(base, io.n, (int64_t)me, L);
-      int phase = (flags & kFlagFirst) ? 1 : 2, last = 0;
-      const int step0 = L.step;
-      r = ff_classify(sc, L);  // fills the lane's squared speeds; an env is only queued here when this says kFfFull
-      do {
-        if (r == kFfFull) {
-          r = ff_full<T>(sc, &L, phase, &last);
-        } else {  // to_end only: the flight goes on in this lane
-          if (phase == 1) {  // the force-free first substep (see ff_phase_fast)
-            const T t0 = L.tgt[0], t1 = L.tgt[1], t2 = L.tgt[2];
-            L.tgt[0] = L.rp[0]; L.tgt[1] = L.rp[1]; L.tgt[2] = L.rp[2];
-            r = ff_fast<T>(sc, L, r);
-            L.tgt[0] = t0; L.tgt[1] = t1; L.tgt[2] = t2;
-          } else {
-            r = ff_fast<T>(sc, L, r);
-          }
-          last = TB_EV_COURT_BALL;  // if this was the last one: ff_fast ends on the court's top face only
-        }
-        phase = 2;
-      } while (r == kFfFull || (to_end && r != kFfDone));
-      *nsub += L.step - step0;
-      flags = kFlagInFlight | (L.events << kFlagEventShift);
-      if (r == kFfDone) flags |= kFlagLanded | (last << kFlagLastShift);
-      ff_store(base, io.n, (int64_t)me, L, flags);
+#ifdef TB_FF_DIAG
+    if (blockIdx.x == 0 && lane == 0) {
+      int bin = (int)((global_ns() - ts0) / 500000ULL);
+      if (bin < 76 && !ctr[128 + 5 * bin]) {
+        ctr[128 + 5 * bin] = ld_ctr(ctr + kCLanded) + 1; ctr[129 + 5 * bin] = ld_ctr(ctr + kCFullTail); ctr[130 + 5 * bin] = ld_ctr(ctr + kCFullHead);
+        ctr[131 + 5 * bin] = ld_ctr(ctr + kCLateTail); ctr[132 + 5 * bin] = ld_ctr(ctr + kCLateHead);
+      }
     }
-    queue_push(nextq, nnext, have && r != kFfDone, me, lane);
+#endif
+    // ---- lanes without an env: step_kernel's list (envs whose first fast-forward substep is a full one), then a ticket
+    //      each for the full queue.  At most kServerLanes envs at a time: lanes on different rare paths run one after
+    //      the other, so every busy lane lengthens the warp's iteration.
+    bool got = false;
+    if (waiting) {
+      int e = dq_poll(io.dq_full, ticket, io.epoch);
+      if (e >= 0) { me = e; got = true; waiting = false; }
+    }
+    const unsigned held = __ballot_sync(full, busy || waiting || got);
+    if (__popc(held) < kServerLanes) {
+      const unsigned cand = ~held & ((1u << kServerLanes) - 1u);  // lanes 0 .. kServerLanes-1 only ever hold envs
+      if (!exhausted0) {
+        const int want = __popc(cand);
+        long long at = 0;
+        if (lane == 0) at = (long long)atomicAdd(ctr + kCFullClaim0, (unsigned long long)want);
+        at = __shfl_sync(full, at, 0);
+        if (at + want >= nfull0) exhausted0 = true;
+        long long idx = at + __popc(cand & ((1u << lane) - 1u));
+        if (((cand >> lane) & 1u) && idx < nfull0) { me = __ldcg(io.queue_full + idx); got = true; }
+      } else {
+        long long t = dq_reserve(ctr + kCFullHead, cand, lane);
+        if (((cand >> lane) & 1u) && t < io.dq_cap) { ticket = t; waiting = true; }
+      }
+    }
+    if (got) {
+      int flags = ff_load(base, io.n, (int64_t)me, L);
+      phase = (flags & kFlagFirst) ? 1 : 2;
+      visits = min(((flags >> kFlagVisitShift) & 3) + 1, 3);
+      to_end = visits >= kFfMaxVisits;
+#ifdef TB_FF_DIAG
+      if (to_end) atomicAdd(ctr + kDPhase + 6, 1ULL);
+#endif
+      step0 = L.step;
+      last = 0;
+      r = ff_classify(sc, L);  // fills the lane's squared speeds; kFfFull, rounding apart
+      busy = true;
+    }
+    if (!__any_sync(full, busy)) {  // nothing to do: done when every env has landed
+      if (ld_ctr(ctr + kCLanded) >= (unsigned long long)total) break;
+      long long now = clock64();
+      if (!idle_since) idle_since = now;
+      if (now - idle_since > kSpinLimit) { atomicExch(ctr + kCError, 5ULL); break; }
+      nap = nap ? min(nap * 2, 4000u) : 500u;
+      __nanosleep(nap);
+      continue;
+    }
+    idle_since = 0;
+    nap = 0;
+    // ---- one substep per busy lane
+    bool leave = false;
+#ifdef TB_FF_DIAG
+    long long tb0 = clock64();
+    if (busy) ++chain;
+#endif
+    if (busy) {
+#ifdef TB_FF_DIAG
+      atomicAdd(ctr + kDPhase + (r == kFfFull ? 4 : 5), 1ULL);
+#endif
+      if (r == kFfFull) {
+        r = ff_full<T>(sc, &L, phase, &last);
+      } else {  // (to_end, or a rounding-level disagreement with the classification that queued the env)
+        if (phase == 1) {  // the force-free first substep (see ff_flight_warp)
+          const T t0 = L.tgt[0], t1 = L.tgt[1], t2 = L.tgt[2];
+          L.tgt[0] = L.rp[0]; L.tgt[1] = L.rp[1]; L.tgt[2] = L.rp[2];
+          r = ff_fast<T>(sc, L, r);
+          L.tgt[0] = t0; L.tgt[1] = t1; L.tgt[2] = t2;
+        } else {
+          r = ff_fast<T>(sc, L, r);
+        }
+        last = TB_EV_COURT_BALL;  // if this was the last one: ff_fast ends on the court's top face only
+      }
+      phase = 2;
+      leave = r == kFfDone || (r != kFfFull && !to_end);
+      if (leave) {
+        *nsub += L.step - step0;
+        int flags = kFlagInFlight | (L.events << kFlagEventShift) | (visits << kFlagVisitShift);
+        if (r == kFfDone) flags |= kFlagLanded | (last << kFlagLastShift);
+        ff_store(base, io.n, (int64_t)me, L, flags);
+        busy = false;
+#ifdef TB_FF_DIAG
+        atomicMax(ctr + kDPhase + 8, (unsigned long long)chain);
+        chain = 0;
+#endif
+      }
+    }
+#ifdef TB_FF_DIAG
+    if (__any_sync(full, busy || leave) && lane == 0) {
+      atomicAdd(ctr + kDPhase + 9, 1ULL);
+      atomicAdd(ctr + kDPhase + 10, (unsigned long long)(clock64() - tb0));
+      atomicMax(ctr + kDPhase + 11, global_ns());
+    }
+#endif
+    dq_push(io.dq_late, io.dq_cap, ctr + kCLateTail, io.epoch, leave && r != kFfDone, me, lane, ctr + kCError);
+    unsigned done_m = __ballot_sync(full, leave && r == kFfDone);
+    if (done_m) {
+      __threadfence();
+      if (lane == 0) atomicAdd(ctr + kCLanded, (unsigned long long)__popc(done_m));
+    }
   }
 }
 
-// Phase C for one warp-tile of 32 consecutive envs: complete the env step of those that landed.
+// The finishing pass for one warp-tile of 32 consecutive envs: complete the env step of those that landed.
 template <typename T>
 __device__ __noinline__ void ff_phase_finish(const Scene<T> &sc, const StepIO &io, int64_t tile0, WarpStats *wsp) {
   constexpr int KIND = TB_ENV_SWING;
@@ -672,45 +844,31 @@ __global__ void __launch_bounds__(kBlock, MinBlocks<T>::v) ff_kernel(const __gri
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   unsigned long long *ctr = io.queue_ctr;
   const long long qfront = (long long)ctr[kCFront];  // queued envs (written by step_kernel, same stream)
-  const long long qn0 = qfront + (long long)ctr[kCBack];
-  if (qn0 + (long long)ctr[kCFull(0)] == 0) return;
+  const long long qn0 = qfront + (long long)ctr[kCBack], nfull0 = (long long)ctr[kCFull0];
+  const long long total = qn0 + nfull0;
+  if (total == 0) return;
   WarpStats ws;
   ws.init(sacc[wib], lane);
-  unsigned epoch = 0;
   int nsub = 0;  // substeps this lane integrated
-  bool ok = true;
-  const bool diag = blockIdx.x == 0 && threadIdx.x == 0;  // phase times as this CTA sees them (barrier to barrier)
+  const bool diag = blockIdx.x == 0 && threadIdx.x == 0;  // times as this CTA's first warp sees them
   unsigned long long t_mark = diag ? global_ns() : 0;
-  // round r: phase B serves the full queue (round 0: what step_kernel put there), its survivors join the round's fast
-  // queue; phase A runs the flights; whatever needs a full substep again waits for round r + 1
-  for (int round = 0; ok; ++round) {
-    const int p = round & 1;
-    // the other parity's counters were last read before the barrier that ended the previous round
-    if (round > 0 && blockIdx.x == 0 && threadIdx.x == 0) {
-      ctr[kCFast(p ^ 1)] = 0; ctr[kCFastClaim(p ^ 1)] = 0; ctr[kCFull(p ^ 1)] = 0; ctr[kCFullClaim(p ^ 1)] = 0;
-    }
-    const long long nfull = (long long)ld_ctr(ctr + kCFull(p));
-    const bool to_end = round + 1 >= kFfMaxRounds;
-    if (nfull) ff_phase_full<T>(sc, io, io.queue_full, nfull, ctr + kCFullClaim(p), io.queue_b, ctr + kCFast(p), to_end, lane, &nsub);
-    if (!(ok = grid_barrier(ctr, epoch))) break;
-    if (diag) {
-      unsigned long long t = global_ns();
-      if (round < 6) ctr[kDPhase + 2 * round] = t - t_mark;
-      t_mark = t;
-      ctr[kDFullEnvs] += (unsigned long long)nfull;
-      ctr[kDRounds] = (unsigned long long)(round + 1);
-    }
-    const long long n0 = round == 0 ? qn0 : 0, nfast = n0 + (long long)ld_ctr(ctr + kCFast(p));
-    if (nfast) ff_phase_fast<T>(sc, io, n0, round == 0 ? qfront : 0, io.queue_b, nfast, ctr + kCFastClaim(p), io.queue_full, ctr + kCFull(p ^ 1), lane, nsub);
-    if (!(ok = grid_barrier(ctr, epoch))) break;
-    if (diag) {
-      unsigned long long t = global_ns();
-      if (round < 6) ctr[kDPhase + 2 * round + 1] = t - t_mark;
-      t_mark = t;
-    }
-    if (ld_ctr(ctr + kCFull(p ^ 1)) == 0) break;
+  const bool server = wib == kBlock / 32 - 1 && blockIdx.x % kServerStride == 0;
+  if (server) ff_server_warp<T>(sc, io, nfull0, total, lane, &nsub);
+  else ff_flight_warp<T>(sc, io, qn0, qfront, total, lane, nsub);
+  if (diag) {
+    unsigned long long t = global_ns();
+#ifdef TB_FF_DIAG
+    for (int i = 1; i <= 3; ++i) ctr[kDPhase + i] = ctr[kDPhase + i] ? ctr[kDPhase + i] - t_mark : 0;
+    ctr[kDPhase + 7] = ld_ctr(ctr + kCLateTail);
+    ctr[kDPhase + 11] = ctr[kDPhase + 11] ? ctr[kDPhase + 11] - t_mark : 0;
+#endif
+    ctr[kDPhase] = t - t_mark;
+    t_mark = t;
+    ctr[kDRounds] = 1;
+    ctr[kDFullEnvs] = ld_ctr(ctr + kCFullTail) + (unsigned long long)nfull0;
   }
-  if (ok) {
+  if (ld_ctr(ctr + kCError) == 0) {  // every env has landed, and their states are visible (fence before the count)
+    __threadfence();
     nsub = __reduce_add_sync(0xffffffffu, nsub);
     if (lane == 0) ws.acc[TB_STAT_PHYSICS_STEPS] += nsub;
     const int64_t stride = (int64_t)gridDim.x * kBlock;
@@ -1024,6 +1182,7 @@ template <typename T> static void build_scene(const Params &p, Scene<T> &sc) {
     sc.ffp_low = sc.floor_h[2] + sc.contact_threshold;  // formed in T like physics_step does
     sc.ffp_box[0] = (T)((double)sc.racket_box[0] + reach_r + grow); sc.ffp_box[1] = (T)((double)sc.racket_box[1] - reach_r - grow);
     sc.ffp_box[2] = (T)((double)sc.racket_box[2] + reach_r + grow);
+    sc.ffp_rim = (T)(reach_r + grow);
     sc.ffl_inv_dt = (T)(1.0 / p.dt); sc.ffl_erp_dt = (T)(p.contact_erp / p.dt); sc.ffl_m = (T)TB_BALL_MASS;
     sc.ffl_jinv_t = (T)(1.0 / (1.0 / TB_BALL_MASS + TB_BALL_RADIUS * TB_BALL_RADIUS / (0.4 * TB_BALL_MASS * TB_BALL_RADIUS * TB_BALL_RADIUS)));
     sc.ffp_court[0] = sc.floor_h[0] + 1; sc.ffp_court[1] = sc.floor_h[1] + 1;
@@ -1064,7 +1223,10 @@ struct tb_ctx {
   uint8_t *d_done = nullptr, *d_events = nullptr, *d_mask = nullptr;
   int64_t launches = 0;
   int *queue = nullptr;                      // fast-forward work queue (env indices), num_envs entries
-  int *queue_b = nullptr, *queue_full = nullptr;
+  int *queue_full = nullptr;
+  unsigned long long *dq = nullptr;          // the two dynamic queues of ff_kernel, dq_cap tagged slots each
+  long long dq_cap = 0;
+  unsigned epoch = 0;
   unsigned long long *queue_ctrs = nullptr;  // two counter sets (kCtrWords each) used by alternate steps
   int parity = 0;
   unsigned ff_grid = 0;                      // persistent grid of ff_kernel
@@ -1137,7 +1299,10 @@ template <typename T> static int ff_grid_size(tb_ctx *c, unsigned *grid) {
 }
 // One env step = step_kernel (+ ff_kernel for SwingRacket) on `stream`.
 static int launch_step(tb_ctx *c, StepIO &io, cudaStream_t stream, bool stage = false) {
-  io.queue = c->queue; io.queue_b = c->queue_b; io.queue_full = c->queue_full;
+  io.queue = c->queue; io.queue_full = c->queue_full;
+  io.dq_full = c->dq; io.dq_late = c->dq ? c->dq + c->dq_cap : nullptr; io.dq_cap = c->dq_cap;
+  if (++c->epoch == 0) c->epoch = 1;  // (a slot written 2^32 steps ago with the same tag would have to survive untouched)
+  io.epoch = c->epoch;
   io.queue_ctr = c->queue_ctrs + kCtrWords * c->parity;
   io.queue_ctr_next = c->queue_ctrs + kCtrWords * (c->parity ^ 1);
   c->parity ^= 1;
@@ -1239,12 +1404,17 @@ int tb_create(const tb_config *cfg, tb_ctx **out) {
   if (e == cudaSuccess) e = cudaMalloc(&c->stats, TB_NUM_STATS * sizeof(unsigned long long));
   if (e == cudaSuccess) e = cudaMalloc(&c->queue_ctrs, 2 * kCtrWords * sizeof(unsigned long long));
   if (e == cudaSuccess && cfg->env_kind == TB_ENV_SWING) e = cudaMalloc(&c->queue, (size_t)cfg->num_envs * sizeof(int));
-  if (e == cudaSuccess && cfg->env_kind == TB_ENV_SWING) e = cudaMalloc(&c->queue_b, (size_t)cfg->num_envs * sizeof(int));
+  if (e == cudaSuccess && cfg->env_kind == TB_ENV_SWING) {
+    // every env is pushed to either dynamic queue at most kFfMaxVisits times per launch
+    c->dq_cap = (long long)cfg->num_envs * (kFfMaxVisits + 1) + (1 << 18);  // + a ticket for every lane that may end up waiting
+    e = cudaMalloc(&c->dq, (size_t)c->dq_cap * 2 * sizeof(unsigned long long));
+  }
   if (e == cudaSuccess && cfg->env_kind == TB_ENV_SWING) e = cudaMalloc(&c->queue_full, (size_t)cfg->num_envs * sizeof(int));
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaMemsetAsync(c->state, 0, bytes, c->own_stream);
   if (e == cudaSuccess) e = cudaMemsetAsync(c->stats, 0, TB_NUM_STATS * sizeof(unsigned long long), c->own_stream);
   if (e == cudaSuccess) e = cudaMemsetAsync(c->queue_ctrs, 0, 2 * kCtrWords * sizeof(unsigned long long), c->own_stream);
+  if (e == cudaSuccess && c->dq) e = cudaMemsetAsync(c->dq, 0, (size_t)c->dq_cap * 2 * sizeof(unsigned long long), c->own_stream);  // tag 0 = no epoch
   if (e == cudaSuccess) {
     // identity quaternion, episode = -1 so the first reset starts episode 0
     std::size_t n = (size_t)cfg->num_envs;
@@ -1280,7 +1450,7 @@ int tb_destroy(tb_ctx *c) {
   DeviceGuard g(c->cfg.device);
   if (c->own_stream) { cudaStreamSynchronize(c->own_stream); cudaStreamDestroy(c->own_stream); }
   for (int i = 0; i < 3; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
-  cudaFree(c->state); cudaFree(c->stats); cudaFree(c->queue_ctrs); cudaFree(c->queue); cudaFree(c->queue_b); cudaFree(c->queue_full); cudaFree(c->pid);
+  cudaFree(c->state); cudaFree(c->stats); cudaFree(c->queue_ctrs); cudaFree(c->queue); cudaFree(c->dq); cudaFree(c->queue_full); cudaFree(c->pid);
   cudaFree(c->d_actions); cudaFree(c->d_obs); cudaFree(c->d_reward); cudaFree(c->d_term);
   cudaFree(c->d_done); cudaFree(c->d_events); cudaFree(c->d_mask);
   delete c;
@@ -1473,9 +1643,13 @@ int tb_ff_diagnostics(tb_ctx *c, int64_t *h_out) {
   // the set of the most recent step that entered the fast-forward: the one whose round count is non-zero and whose
   // twin was zeroed since (both non-zero cannot happen: every step_kernel zeroes the next step's set)
   const unsigned long long *s = h[kDRounds] ? h : h + kCtrWords;
-  for (int i = 0; i < 14; ++i) h_out[i] = (int64_t)s[kDRounds + i];
+  for (int i = 0; i < 14; ++i) h_out[i] = (int64_t)s[kDRounds + i];  // rounds, full-path envs, phase times
   h_out[14] = (int64_t)s[kDFinish];
   h_out[15] = (int64_t)s[kCError];
+  if (std::getenv("TB_FF_DIAG_DUMP"))
+    for (int b = 0; b < 76 && s[128 + 5 * b]; ++b)
+      std::fprintf(stderr, "t=%.1fms landed %llu fullq %llu/%llu lateq %llu/%llu\n", 0.5 * b, s[128 + 5 * b] - 1, s[130 + 5 * b], s[129 + 5 * b],
+                   s[132 + 5 * b], s[131 + 5 * b]);
   return 0;
 }
 
