@@ -1052,11 +1052,14 @@ template <typename T> __device__ __forceinline__ bool ff_substep(const Scene<T> 
 }
 
 // ------------------------------------------------------------------------------------------------ fast lane
-// What a lane of ff_kernel keeps in registers between substeps: omega in the body frame, tgt = spawn + (0,0,4), and
-// the squared speeds nb, nr, nw of ball, racket and omega - the classification of a state needs them and the next
-// substep's damping factors reuse them.
+// What a lane of ff_kernel keeps in registers between substeps: omega in the body frame, tgt = spawn + (0,0,4), the
+// squared speeds nb, nr, nw of ball, racket and omega - the classification of a state needs them and the next
+// substep's damping factors reuse them - and the ball's spin rate sb = |bw|, which free flight only scales
+// (bw <- bw f, so |bw| <- |bw| f: no square root per substep).  rq is NOT renormalised per substep here: the product
+// of unit quaternions drifts from unit length by rounding only (~1e-16 per substep, < 1e-14 over the longest flight);
+// ff_kernel renormalises when the lane's state goes back to HBM.
 template <typename T> struct FfLane {
-  T rp[3], rq[4], rv[3], wl[3], bp[3], bv[3], bw[3], tgt[3], goal[2], nb, nr, nw;
+  T rp[3], rq[4], rv[3], wl[3], bp[3], bv[3], bw[3], tgt[3], goal[2], nb, nr, nw, sb;
   int step, events;
 };
 // How the substep that starts from a state has to be taken:
@@ -1133,8 +1136,8 @@ template <typename T> __device__ __forceinline__ int ff_fast(const Scene<T> &sc,
   T fb = 1 - sc.ff_kl * (1 + M<T>::norm_damp(L.nb));
   L.bv[0] *= fb; L.bv[1] *= fb; L.bv[2] = L.bv[2] * fb + sc.ff_dtg;
   {  // unconditional: a warp almost always holds a ball that spins, and 0 * f stays 0 for the others
-    T fs = 1 - sc.ff_ka * (1 + M<T>::norm_damp(dot3(L.bw, L.bw)));
-    L.bw[0] *= fs; L.bw[1] *= fs; L.bw[2] *= fs;
+    T fs = 1 - sc.ff_ka * (1 + L.sb);
+    L.bw[0] *= fs; L.bw[1] *= fs; L.bw[2] *= fs; L.sb *= fs;
   }
   T fr = 1 - sc.ff_kl * (1 + M<T>::norm_damp(L.nr));
   L.rv[0] = L.rv[0] * fr + sc.ff_hack[0] * (L.rp[0] - L.tgt[0]);
@@ -1193,8 +1196,7 @@ template <typename T> __device__ __forceinline__ int ff_fast(const Scene<T> &sc,
     T y = cw * q1 + ay * q3 + ax * q2 - az * q0;
     T z = cw * q2 + az * q3 + ay * q0 - ax * q1;
     T w = cw * q3 - ax * q0 - ay * q1 - az * q2;
-    T inv = (T)1.5 - (T)0.5 * (x * x + y * y + z * z + w * w);
-    L.rq[0] = x * inv; L.rq[1] = y * inv; L.rq[2] = z * inv; L.rq[3] = w * inv;
+    L.rq[0] = x; L.rq[1] = y; L.rq[2] = z; L.rq[3] = w;
   }
   ++L.step;
   int next = ff_classify(sc, L);
@@ -1227,6 +1229,7 @@ __device__ __noinline__ int ff_full(const Scene<T> &sc, FfLane<T> *Lp, int phase
 #pragma unroll
   for (int i = 0; i < 4; ++i) Lp->rq[i] = s.rq[i];
   Lp->step = s.step; Lp->events = c.events;
+  Lp->sb = norm3(s.bw);
   *last = c.last;
   int next = ff_classify(sc, *Lp);
   return fin ? kFfDone : next;

@@ -23,12 +23,12 @@ namespace tb {
 constexpr int kPacks = 8;
 constexpr int kBlock = 128;     // threads per CTA of the step kernel
 #ifndef TB_MINB32
-#define TB_MINB32 4
+#define TB_MINB32 5
 #endif
 #ifndef TB_MINB64
-#define TB_MINB64 3
+#define TB_MINB64 4
 #endif
-// CTAs per SM the register budget is held to: 4 x 128 threads -> 128 regs/thread (f32), 3 -> 168 (f64); measured best on B200
+// CTAs per SM ff_kernel's register budget is held to: 5 x 128 threads -> 96 regs/thread (f32), 4 -> 128 (f64); measured best on B200
 template <typename T> struct MinBlocks { static constexpr int v = TB_MINB32; };
 template <> struct MinBlocks<double> { static constexpr int v = TB_MINB64; };
 
@@ -491,6 +491,7 @@ template <typename T> __device__ __forceinline__ int ff_load(const T *base, int6
   L.wl[0] = s.rw[0]; L.wl[1] = s.rw[1]; L.wl[2] = s.rw[2]; L.bp[2] = p3.w;
   L.bv[0] = p4.x; L.bv[1] = p4.y; L.bv[2] = p4.z; L.bw[0] = p4.w;
   L.bw[1] = p5.x; L.bw[2] = p5.y;
+  L.sb = norm3(L.bw);
   L.tgt[0] = p5.z; L.tgt[1] = p5.w; L.tgt[2] = p6.x + 4;  // swingracket_env.py:135-141
   L.goal[0] = p6.y; L.goal[1] = p6.z;
   L.step = (int)as_int(p7.y);
@@ -501,12 +502,15 @@ template <typename T> __device__ __forceinline__ int ff_load(const T *base, int6
 // lane -> HBM: the packs a flight changes (0..4, the spin half of 5) and step / flags of pack 7
 template <typename T> __device__ __forceinline__ void ff_store(T *base, int64_t n, int64_t me, const FfLane<T> &L, int flags) {
   St<T> s;
+  {  // ff_fast does not renormalise the quaternion per substep
+    T inv = M<T>::rsqrt(L.rq[0] * L.rq[0] + L.rq[1] * L.rq[1] + L.rq[2] * L.rq[2] + L.rq[3] * L.rq[3]);
 #pragma unroll
-  for (int i = 0; i < 4; ++i) s.rq[i] = L.rq[i];
+    for (int i = 0; i < 4; ++i) s.rq[i] = L.rq[i] * inv;
+  }
   s.rw[0] = L.wl[0]; s.rw[1] = L.wl[1]; s.rw[2] = L.wl[2];
   ff_leave(s);
   st_pack(base, n, 0, me, Pack<T>{L.rp[0], L.rp[1], L.rp[2], L.bp[0]});
-  st_pack(base, n, 1, me, Pack<T>{L.rq[0], L.rq[1], L.rq[2], L.rq[3]});
+  st_pack(base, n, 1, me, Pack<T>{s.rq[0], s.rq[1], s.rq[2], s.rq[3]});
   st_pack(base, n, 2, me, Pack<T>{L.rv[0], L.rv[1], L.rv[2], L.bp[1]});
   st_pack(base, n, 3, me, Pack<T>{s.rw[0], s.rw[1], s.rw[2], L.bp[2]});
   st_pack(base, n, 4, me, Pack<T>{L.bv[0], L.bv[1], L.bv[2], L.bw[0]});
