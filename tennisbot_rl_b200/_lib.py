@@ -75,7 +75,8 @@ def load():
     L.tb_reset_host.argtypes = [vp, vp, vp]
     L.tb_step_host.argtypes = [vp, vp, vp, vp, vp, vp, vp]
     L.tb_launch_count.argtypes = [vp, C.POINTER(i64)]
-    L.tb_ff_diagnostics.argtypes = [vp, C.POINTER(i64)]
+    if hasattr(L, "tb_ff_diagnostics"):  # absent from older builds loaded through TB_LIB_PATH for comparisons
+        L.tb_ff_diagnostics.argtypes = [vp, C.POINTER(i64)]
     L.tb_set_kernel_timing.argtypes = [vp, i32]
     L.tb_get_kernel_timing.argtypes = [vp, C.POINTER(dbl), C.POINTER(dbl), C.POINTER(i64)]
     _lib = L

@@ -70,6 +70,18 @@ template <typename T> __device__ __forceinline__ void load_state(const T *base, 
   s.aux[2] = p6.x; s.goal[0] = p6.y; s.goal[1] = p6.z; s.d0 = p6.w;
   s.ret = p7.x; s.step = (int)as_int(p7.y); s.flags = (int)as_int(p7.z); s.episode = (uint32_t)as_int(p7.w);
 }
+// Packs 5 and 6 hold episode constants (spawn / shoot force, goal, d0) next to the y, z spin of the ball, which is zero
+// until a frictional contact: step_kernel writes them back only when they changed (p5: spin or reset, p6: reset).
+template <typename T> __device__ __forceinline__ void store_state_changed(T *base, int64_t n, int64_t i, const St<T> &s, bool p5, bool p6) {
+  st_pack(base, n, 0, i, Pack<T>{s.rp[0], s.rp[1], s.rp[2], s.bp[0]});
+  st_pack(base, n, 1, i, Pack<T>{s.rq[0], s.rq[1], s.rq[2], s.rq[3]});
+  st_pack(base, n, 2, i, Pack<T>{s.rv[0], s.rv[1], s.rv[2], s.bp[1]});
+  st_pack(base, n, 3, i, Pack<T>{s.rw[0], s.rw[1], s.rw[2], s.bp[2]});
+  st_pack(base, n, 4, i, Pack<T>{s.bv[0], s.bv[1], s.bv[2], s.bw[0]});
+  if (p5) st_pack(base, n, 5, i, Pack<T>{s.bw[1], s.bw[2], s.aux[0], s.aux[1]});
+  if (p6) st_pack(base, n, 6, i, Pack<T>{s.aux[2], s.goal[0], s.goal[1], s.d0});
+  st_pack(base, n, 7, i, Pack<T>{s.ret, int_as(T(), s.step), int_as(T(), s.flags), int_as(T(), (int64_t)s.episode)});
+}
 template <typename T> __device__ __forceinline__ void store_state(T *base, int64_t n, int64_t i, const St<T> &s) {
   st_pack(base, n, 0, i, Pack<T>{s.rp[0], s.rp[1], s.rp[2], s.bp[0]});
   st_pack(base, n, 1, i, Pack<T>{s.rq[0], s.rq[1], s.rq[2], s.rq[3]});
@@ -314,8 +326,11 @@ __global__ void __launch_bounds__(kBlock, StepMinBlocks<T>::v) step_kernel(const
     for (int j = 0; j < AD; ++j) a[j] = valid ? s_tile[lane * AD + j] : 0.0f;
     __syncwarp();
   }
+  T spin1 = 0, spin2 = 0;
+  uint32_t episode0 = 0;
   if (valid) {
     load_state(base, io.n, me, s);
+    spin1 = s.bw[1]; spin2 = s.bw[2]; episode0 = s.episode;
     if (!STAGE) load_action<KIND>(io.actions, me, a);
     c.done = s.flags & kFlagDone;
     if (TB_UNLIKELY(io.pid != nullptr)) {
@@ -379,7 +394,10 @@ __global__ void __launch_bounds__(kBlock, StepMinBlocks<T>::v) step_kernel(const
       s.flags = (s.flags & ~(0xff << kFlagEventShift)) | kFlagInFlight | kFlagFirst | (c.events << kFlagEventShift);
     }
   }
-  if (valid) store_state(base, io.n, me, s);
+  if (valid) {
+    const bool restarted = s.episode != episode0;
+    store_state_changed(base, io.n, me, s, restarted || s.bw[1] != spin1 || s.bw[2] != spin2, restarted);
+  }
   ws.flush(io.stats);
 }
 
