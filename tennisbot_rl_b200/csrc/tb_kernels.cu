@@ -120,6 +120,7 @@ struct StepIO {
                                      // substep; envs whose flight goes on after one.  dq_cap slots each
   long long dq_cap;
   unsigned epoch;                    // step counter of the context, never 0: tag of this launch's queue slots
+  int prefetch_ahead;                // step_kernel: CTAs resident at a time (the L2 prefetch distance), 0 = none
   unsigned long long *queue_ctr;     // kCtrWords counters (kC* below): [0] front, [1] back entries appended by this
                                      // step's step_kernel, the rest ff_kernel's
   unsigned long long *queue_ctr_next;  // the set the NEXT step uses; step_kernel zeroes it
@@ -287,51 +288,21 @@ __device__ __forceinline__ void finish_api(const Scene<T> &sc, const StepIO &io,
 template <typename T> struct StepMinBlocks { static constexpr int v = TB_STEP_MINB32; };
 template <> struct StepMinBlocks<double> { static constexpr int v = TB_STEP_MINB64; };
 
-// STAGE: move the action / observation rows through warp-private shared-memory tiles (see below); chosen by the host
-// when the caller's buffers are pinned host memory, off for buffers in HBM where it only costs registers.
+// Everything an env step does once the state and the action of the warp's 32 envs sit in registers: the substep the
+// action drives, env logic, statistics, outputs, auto-reset, queueing for ff_kernel, state back to HBM.
 template <typename T, int KIND, bool STAGE>
-__global__ void __launch_bounds__(kBlock, StepMinBlocks<T>::v) step_kernel(const __grid_constant__ Scene<T> sc, const __grid_constant__ StepIO io) {
-  __shared__ unsigned long long sacc[kBlock / 32][TB_NUM_STATS];
-  __shared__ int s_cnt[3 * (kBlock / 32)];
-  __shared__ unsigned long long s_base[3];
-  // Each warp's 32 action rows come in and its 32 observation rows go out as one contiguous tile through shared
-  // memory (warp-private, __syncwarp only): [N, act] / [N, obs] float32 rows are 24 / 8 / 48 bytes, which per-thread
-  // accesses would turn into strided partial sectors - harmless in HBM behind L2, costly when the caller's buffers
-  // are pinned host memory and every sector is a PCIe transaction (tb_step_host's zero-copy path).
-  constexpr int AD = Dims<KIND>::act, OD = Dims<KIND>::obs;
-  __shared__ __align__(16) float s_tiles[STAGE ? kBlock / 32 : 1][STAGE ? 32 * OD : 4];
+__device__ __forceinline__ void step_tile(const Scene<T> &sc, const StepIO &io, int64_t tile0, int rows, bool valid, St<T> &s,
+                                          const float *a, WarpStats &ws, int *s_cnt, unsigned long long *s_base, float *s_tile) {
+  constexpr int OD = Dims<KIND>::obs;
   const unsigned full = 0xffffffffu;
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  float *s_tile = s_tiles[STAGE ? wib : 0];
-  WarpStats ws;
-  ws.init(sacc[wib], lane);
-  if (blockIdx.x == 0)
-    for (int i = threadIdx.x; i < kCtrWords; i += kBlock) io.queue_ctr_next[i] = 0;
-
-  const int64_t tile0 = (int64_t)blockIdx.x * kBlock + wib * 32, me = tile0 + lane;
-  const bool valid = me < io.n;
-  const int rows = io.n - tile0 >= 32 ? 32 : (io.n > tile0 ? (int)(io.n - tile0) : 0);
+  const int64_t me = tile0 + lane;
   T *base = static_cast<T *>(io.state);
-  St<T> s;
   StepCtl c = {0, 0, 0, 0.0f, false};
   bool fin = false;
-  float a[8];
-  if (STAGE) {
-    const float *src = io.actions + tile0 * AD;
-    const int nf = rows * AD, nv = nf >> 2;
-    for (int i = lane; i < nv; i += 32) reinterpret_cast<float4 *>(s_tile)[i] = reinterpret_cast<const float4 *>(src)[i];
-    for (int i = (nv << 2) + lane; i < nf; i += 32) s_tile[i] = src[i];
-    __syncwarp();
-#pragma unroll
-    for (int j = 0; j < AD; ++j) a[j] = valid ? s_tile[lane * AD + j] : 0.0f;
-    __syncwarp();
-  }
-  T spin1 = 0, spin2 = 0;
-  uint32_t episode0 = 0;
+  const T spin1 = s.bw[1], spin2 = s.bw[2];
+  const uint32_t episode0 = s.episode;
   if (valid) {
-    load_state(base, io.n, me, s);
-    spin1 = s.bw[1]; spin2 = s.bw[2]; episode0 = s.episode;
-    if (!STAGE) load_action<KIND>(io.actions, me, a);
     c.done = s.flags & kFlagDone;
     if (TB_UNLIKELY(io.pid != nullptr)) {
       T pid[8];
@@ -398,6 +369,65 @@ __global__ void __launch_bounds__(kBlock, StepMinBlocks<T>::v) step_kernel(const
     const bool restarted = s.episode != episode0;
     store_state_changed(base, io.n, me, s, restarted || s.bw[1] != spin1 || s.bw[2] != spin2, restarted);
   }
+}
+
+
+// STAGE: move the action / observation rows through warp-private shared-memory tiles (see below); chosen by the host
+// when the caller's buffers are pinned host memory, off for buffers in HBM where it only costs registers.
+template <typename T, int KIND, bool STAGE>
+__global__ void __launch_bounds__(kBlock, StepMinBlocks<T>::v) step_kernel(const __grid_constant__ Scene<T> sc, const __grid_constant__ StepIO io) {
+  __shared__ unsigned long long sacc[kBlock / 32][TB_NUM_STATS];
+  __shared__ int s_cnt[3 * (kBlock / 32)];
+  __shared__ unsigned long long s_base[3];
+  // Each warp's 32 action rows come in and its 32 observation rows go out as one contiguous tile through shared
+  // memory (warp-private, __syncwarp only): [N, act] / [N, obs] float32 rows are 24 / 8 / 48 bytes, which per-thread
+  // accesses would turn into strided partial sectors - harmless in HBM behind L2, costly when the caller's buffers
+  // are pinned host memory and every sector is a PCIe transaction (tb_step_host's zero-copy path).
+  constexpr int AD = Dims<KIND>::act, OD = Dims<KIND>::obs;
+  __shared__ __align__(16) float s_tiles[STAGE ? kBlock / 32 : 1][STAGE ? 32 * OD : 4];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  float *s_tile = s_tiles[STAGE ? wib : 0];
+  WarpStats ws;
+  ws.init(sacc[wib], lane);
+  if (blockIdx.x == 0)
+    for (int i = threadIdx.x; i < kCtrWords; i += kBlock) io.queue_ctr_next[i] = 0;
+
+  const int64_t tile0 = (int64_t)blockIdx.x * kBlock + wib * 32, me = tile0 + lane;
+  const bool valid = me < io.n;
+  const int rows = io.n - tile0 >= 32 ? 32 : (io.n > tile0 ? (int)(io.n - tile0) : 0);
+  St<T> s;
+  float a[8];
+  if (STAGE) {
+    const float *src = io.actions + tile0 * AD;
+    const int nf = rows * AD, nv = nf >> 2;
+    for (int i = lane; i < nv; i += 32) reinterpret_cast<float4 *>(s_tile)[i] = reinterpret_cast<const float4 *>(src)[i];
+    for (int i = (nv << 2) + lane; i < nf; i += 32) s_tile[i] = src[i];
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < AD; ++j) a[j] = valid ? s_tile[lane * AD + j] : 0.0f;
+    __syncwarp();
+  }
+  // One thread pulls the tile that the CTA one wave ahead will work on into L2 (bulk prefetches: eight pack chunks of
+  // 128 envs + their action rows), so that CTA's loads are L2 hits.  With 168-register threads only 12 warps fit an SM
+  // and every CTA loads once at the start of its life; the prefetch keeps HBM requests in flight during the
+  // arithmetic.  (A persistent variant that staged whole tiles in shared memory through cp.async.bulk + mbarrier was
+  // 15 % faster in float32 but slower in float64: two 35 KB stages x 3 CTAs leave almost no L1 for the rare paths'
+  // local-memory records.  Measured on B200, see DESIGN.md.)
+  if (!STAGE && threadIdx.x == 0 && io.prefetch_ahead > 0) {
+    const int64_t e0 = ((int64_t)blockIdx.x + io.prefetch_ahead) * kBlock;
+    if (e0 + kBlock <= io.n) {
+      const T *b0 = static_cast<const T *>(io.state);
+#pragma unroll
+      for (int p = 0; p < kPacks; ++p)
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(b0 + ((int64_t)p * io.n + e0) * 4), "r"((uint32_t)(kBlock * 4 * sizeof(T))) : "memory");
+      asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(io.actions + e0 * AD), "r"((uint32_t)(kBlock * AD * 4)) : "memory");
+    }
+  }
+  if (valid) {
+    load_state(static_cast<const T *>(io.state), io.n, me, s);
+    if (!STAGE) load_action<KIND>(io.actions, me, a);
+  }
+  step_tile<T, KIND, STAGE>(sc, io, tile0, rows, valid, s, a, ws, s_cnt, s_base, s_tile);
   ws.flush(io.stats);
 }
 
@@ -1252,6 +1282,7 @@ struct tb_ctx {
   unsigned long long *queue_ctrs = nullptr;  // two counter sets (kCtrWords each) used by alternate steps
   int parity = 0;
   unsigned ff_grid = 0;                      // persistent grid of ff_kernel
+  int step_resident = -1;                    // resident CTAs of step_kernel (its L2 prefetch distance)
   int control_mode = TB_CONTROL_FORCE;
   void *pid = nullptr;                       // controller memory, allocated by tb_set_control_mode(TB_CONTROL_PID)
   bool zero_copy = std::getenv("TB_HOST_STAGING") == nullptr;  // tb_step_host: address pinned host buffers from the kernels
@@ -1319,6 +1350,14 @@ template <typename T> static int ff_grid_size(tb_ctx *c, unsigned *grid) {
   *grid = (unsigned)(need < resident ? need : resident);
   return 0;
 }
+// CTAs of step_kernel that are resident at a time = how far ahead its L2 prefetch reaches.
+template <typename T, int KIND> static int step_resident_ctas(tb_ctx *c) {
+  int per_sm = 0, sms = 0;
+  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, step_kernel<T, KIND, false>, kBlock, 0));
+  CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->cfg.device));
+  c->step_resident = std::getenv("TB_NO_PREFETCH") ? 0 : sms * (per_sm > 0 ? per_sm : 1);
+  return 0;
+}
 // One env step = step_kernel (+ ff_kernel for SwingRacket) on `stream`.
 static int launch_step(tb_ctx *c, StepIO &io, cudaStream_t stream, bool stage = false) {
   io.queue = c->queue; io.queue_full = c->queue_full;
@@ -1331,10 +1370,15 @@ static int launch_step(tb_ctx *c, StepIO &io, cudaStream_t stream, bool stage = 
   const unsigned grid = grid_for(io.n, kBlock);
   const bool swing = c->cfg.env_kind == TB_ENV_SWING;
   if (c->timing) CU(cudaEventRecord(c->ev[0], stream));
-#define TB_LAUNCH_STEP(T, K, SC)                                                        \
-  do {                                                                                 \
-    if (stage) step_kernel<T, K, true><<<grid, kBlock, 0, stream>>>(SC, io);           \
-    else step_kernel<T, K, false><<<grid, kBlock, 0, stream>>>(SC, io);                \
+#define TB_LAUNCH_STEP(T, K, SC)                                                                           \
+  do {                                                                                                    \
+    if (stage) {                                                                                          \
+      step_kernel<T, K, true><<<grid, kBlock, 0, stream>>>(SC, io);                                       \
+    } else {                                                                                              \
+      if (c->step_resident < 0 && step_resident_ctas<T, K>(c)) return 1;                                  \
+      io.prefetch_ahead = c->step_resident;                                                               \
+      step_kernel<T, K, false><<<grid, kBlock, 0, stream>>>(SC, io);                                      \
+    }                                                                                                     \
   } while (0)
   if (c->cfg.precision == TB_F64) {
     if (swing) TB_LAUNCH_STEP(double, TB_ENV_SWING, c->sc64);
