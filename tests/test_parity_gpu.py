@@ -74,6 +74,52 @@ def test_f64_parity_trained_policy(oracle_lib):
     assert st[2] > 0.8 * st[0]  # racket hits in most episodes
 
 
+@pytest.mark.parametrize("params", [{"racket_scale": 2.5}, {"gravity_z": -3.0, "racket_scale": 1.6},
+                                    {"lin_damping": 0.0, "ang_damping": 0.0}])
+def test_f64_parity_fast_forward_paths(oracle_lib, params):
+    """Scenes that push many flights through every path of ff_kernel: a larger racket (contacts and near misses in
+    the fast-forward: server warps, repeated visits, flights finished by the servers), weak gravity (long flights,
+    800-step time-outs), no damping (balls leave the court: floor-edge contacts, time-outs).  Same bars as the
+    random-action test; the diagnostics must show that the generic full-substep path was actually used."""
+    n = 4096
+    b, o = _make("SwingRacket-v0", n, "f64", 17, oracle_lib)
+    for k, v in params.items():
+        b.set_param(k, v)
+        o.set_param(k, v)
+    np.testing.assert_array_equal(b.reset().cpu().numpy(), o.reset())
+    rng = np.random.default_rng(12)
+    rep, valid = run_parity(b, o, 52, lambda t, _obs: rng.uniform(-1, 1, (n, 6)), band=0.0, check_state_every=13)
+    print(rep, b.ff_diagnostics()[:3])
+    assert rep.event_mismatch_hard == 0 and rep.event_mismatch_near == 0
+    assert rep.max_state_err < TOL_F64_STATE and rep.max_obs_err < TOL_F64_OUT and rep.max_reward_err < TOL_F64_OUT
+    np.testing.assert_array_equal(b.read_stats(), o.read_stats())
+    d = b.ff_diagnostics()
+    assert d[15] == 0 and d[1] > 0  # no queue time-out; envs went through the server path in the last fast-forward
+
+
+@pytest.mark.parametrize("params", [{}, {"racket_scale": 2.5}, {"gravity_z": -3.0, "racket_scale": 1.6}])
+def test_f64_fast_forward_final_state(oracle_lib, params):
+    """Without auto-reset the state a fast-forward ends with stays in place: compare the whole record (racket pose and
+    spin after up to 775 substeps in ff_kernel's body-frame formulation, ball velocity and spin after the landing
+    impulse) with the oracle's, and the done flag of the record."""
+    from tennisbot_rl_b200.batch import TennisBatch
+
+    n = 4096
+    b = TennisBatch("SwingRacket-v0", n, device=0, seed=23, precision="f64", auto_reset=False)
+    o = oracle_lib.OracleEnv("SwingRacket-v0", n, seed=23, threads=8, auto_reset=False)
+    for k, v in params.items():
+        b.set_param(k, v)
+        o.set_param(k, v)
+    np.testing.assert_array_equal(b.reset().cpu().numpy(), o.reset())
+    rng = np.random.default_rng(31)
+    rep, valid = run_parity(b, o, 26, lambda t, _obs: rng.uniform(-1, 1, (n, 6)), band=0.0, check_state_every=26)
+    print(rep)
+    assert rep.event_mismatch_hard == 0 and rep.max_obs_err < TOL_F64_OUT and rep.max_reward_err < TOL_F64_OUT
+    gs, os_ = b.get_state().cpu().numpy(), o.get_state()
+    assert (gs[:, 30] == 1).all() and (os_[:, 30] == 1).all()  # every episode is over after 26 steps
+    assert np.abs(gs - os_).max() < TOL_F64_STATE
+
+
 @pytest.mark.parametrize("env,steps", [("SwingRacket-v0", 52), ("Tennisbot-v0", 700)])
 def test_f32_parity_with_band(oracle_lib, env, steps):
     """float32 path: every contact / done decision equals the oracle's unless the oracle's own margin to the
