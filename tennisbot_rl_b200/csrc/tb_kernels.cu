@@ -341,7 +341,17 @@ __device__ __forceinline__ void step_tile(const Scene<T> &sc, const StepIO &io, 
   bool queued = valid && !fin;
   if (KIND == TB_ENV_SWING) {
     constexpr int W = kBlock / 32;
-    int cls = queued ? (ff_classify_state(sc, s) == kFfFull ? 2 : (dot3(s.bv, s.bv) > (T)9 ? 0 : 1)) : 3;
+    int cls = 3;
+    if (queued) {
+      // front of the queue as well: a ball that is closing in on the racket's plane and would cross it within ~0.6 s.
+      // If the racket is there when it does, the flight that follows is a long one, and it should not start last.
+      const T x = s.rq[0], y = s.rq[1], z = s.rq[2], w = s.rq[3];
+      const T nx = 1 - 2 * (y * y + z * z), ny = 2 * (x * y + z * w), nz = 2 * (x * z - y * w);
+      const T d = nx * (s.bp[0] - s.rp[0]) + ny * (s.bp[1] - s.rp[1]) + nz * (s.bp[2] - s.rp[2]);
+      const T vn = nx * (s.bv[0] - s.rv[0]) + ny * (s.bv[1] - s.rv[1]) + nz * (s.bv[2] - s.rv[2]);
+      const bool closing = d * vn < 0 && M<T>::abs(d) < (T)0.6 * M<T>::abs(vn);
+      cls = ff_classify_state(sc, s) == kFfFull ? 2 : ((dot3(s.bv, s.bv) > (T)9 || closing) ? 0 : 1);
+    }
     unsigned m0 = __ballot_sync(full, cls == 0), m1 = __ballot_sync(full, cls == 1), m2 = __ballot_sync(full, cls == 2);
     if (lane == 0) { s_cnt[wib] = __popc(m0); s_cnt[W + wib] = __popc(m1); s_cnt[2 * W + wib] = __popc(m2); }
     __syncthreads();
