@@ -119,7 +119,8 @@ struct StepIO {
   unsigned long long *dq_full, *dq_late;  // ff_kernel's dynamic queues (slots tagged with `epoch`): envs parked for a full
                                      // substep; envs whose flight goes on after one.  dq_cap slots each
   long long dq_cap;
-  unsigned epoch;                    // step counter of the context, never 0: tag of this launch's queue slots
+  unsigned *epoch;                   // device word: step counter of the context, never 0: tag of this launch's queue slots
+                                     // (advanced by step_kernel itself, so a captured CUDA graph of steps can be replayed)
   int prefetch_ahead;                // step_kernel: CTAs resident at a time (the L2 prefetch distance), 0 = none
   unsigned long long *queue_ctr;     // kCtrWords counters (kC* below): [0] front, [1] back entries appended by this
                                      // step's step_kernel, the rest ff_kernel's
@@ -399,8 +400,13 @@ __global__ void __launch_bounds__(kBlock, StepMinBlocks<T>::v) step_kernel(const
   float *s_tile = s_tiles[STAGE ? wib : 0];
   WarpStats ws;
   ws.init(sacc[wib], lane);
-  if (blockIdx.x == 0)
+  if (blockIdx.x == 0) {
     for (int i = threadIdx.x; i < kCtrWords; i += kBlock) io.queue_ctr_next[i] = 0;
+    if (threadIdx.x == 0 && io.epoch) {  // the tag of this step's queue slots
+      unsigned e = *io.epoch + 1;
+      *io.epoch = e ? e : 1u;
+    }
+  }
 
   const int64_t tile0 = (int64_t)blockIdx.x * kBlock + wib * 32, me = tile0 + lane;
   const bool valid = me < io.n;
@@ -579,8 +585,8 @@ template <typename T> __device__ __forceinline__ void ff_store(T *base, int64_t 
 
 // A flight warp.  n0 / qfront: step_kernel's queue (front / back layout); total: envs in flight in this launch.
 template <typename T>
-__device__ __forceinline__ void ff_flight_warp(const Scene<T> &sc, const StepIO &io, long long n0, long long qfront, long long total,
-                                               int lane, int &nsub) {
+__device__ __forceinline__ void ff_flight_warp(const Scene<T> &sc, const StepIO &io, unsigned epoch, long long n0, long long qfront,
+                                               long long total, int lane, int &nsub) {
   const unsigned full = 0xffffffffu;
   T *base = static_cast<T *>(io.state);
   unsigned long long *ctr = io.queue_ctr;
@@ -629,7 +635,7 @@ __device__ __forceinline__ void ff_flight_warp(const Scene<T> &sc, const StepIO 
         if (st == kFfDone) flags |= kFlagLanded | (TB_EV_COURT_BALL << kFlagLastShift);  // ff_fast ends on the court's top face only
         ff_store(base, io.n, (int64_t)me, L, flags);
       }
-      dq_push(io.dq_full, io.dq_cap, ctr + kCFullTail, io.epoch, st == kFfFull, me, lane, ctr + kCError);
+      dq_push(io.dq_full, io.dq_cap, ctr + kCFullTail, epoch, st == kFfFull, me, lane, ctr + kCError);
       unsigned done_m = __ballot_sync(full, st == kFfDone);
       if (done_m) {
         __threadfence();  // landed states before the count
@@ -649,7 +655,7 @@ __device__ __forceinline__ void ff_flight_warp(const Scene<T> &sc, const StepIO 
     //      ticket each for the late queue, polled here every time round
     bool got = false;
     if (st == kWait) {
-      int e = dq_poll(io.dq_late, ticket, io.epoch);
+      int e = dq_poll(io.dq_late, ticket, epoch);
       if (e >= 0) { me = e; got = true; }
     }
     unsigned idle = __ballot_sync(full, st == kIdle);
@@ -705,7 +711,7 @@ __device__ __forceinline__ void ff_flight_warp(const Scene<T> &sc, const StepIO 
         first = true;
       }
     }
-    dq_push(io.dq_full, io.dq_cap, ctr + kCFullTail, io.epoch, to_full, me, lane, ctr + kCError);
+    dq_push(io.dq_full, io.dq_cap, ctr + kCFullTail, epoch, to_full, me, lane, ctr + kCError);
     if (to_full) st = kIdle;
     first_pending = __any_sync(full, first);
     const int got_any = __any_sync(full, got);
@@ -729,7 +735,8 @@ __device__ __forceinline__ void ff_flight_warp(const Scene<T> &sc, const StepIO 
 // Chains differ wildly in length (one contact step ... a ball rolling on the racket face for the rest of its flight), so
 // lanes are refilled one by one, not batch by batch.
 template <typename T>
-__device__ __noinline__ void ff_server_warp(const Scene<T> &sc, const StepIO &io, long long nfull0, long long total, int lane, int *nsub) {
+__device__ __noinline__ void ff_server_warp(const Scene<T> &sc, const StepIO &io, unsigned epoch, long long nfull0, long long total, int lane,
+                                            int *nsub) {
   const unsigned full = 0xffffffffu;
   T *base = static_cast<T *>(io.state);
   unsigned long long *ctr = io.queue_ctr;
@@ -759,7 +766,7 @@ __device__ __noinline__ void ff_server_warp(const Scene<T> &sc, const StepIO &io
     //      the other, so every busy lane lengthens the warp's iteration.
     bool got = false;
     if (waiting) {
-      int e = dq_poll(io.dq_full, ticket, io.epoch);
+      int e = dq_poll(io.dq_full, ticket, epoch);
       if (e >= 0) { me = e; got = true; waiting = false; }
     }
     const unsigned held = __ballot_sync(full, busy || waiting || got);
@@ -846,7 +853,7 @@ __device__ __noinline__ void ff_server_warp(const Scene<T> &sc, const StepIO &io
       atomicMax(ctr + kDPhase + 11, global_ns());
     }
 #endif
-    dq_push(io.dq_late, io.dq_cap, ctr + kCLateTail, io.epoch, leave && r != kFfDone, me, lane, ctr + kCError);
+    dq_push(io.dq_late, io.dq_cap, ctr + kCLateTail, epoch, leave && r != kFfDone, me, lane, ctr + kCError);
     unsigned done_m = __ballot_sync(full, leave && r == kFfDone);
     if (done_m) {
       __threadfence();
@@ -915,8 +922,9 @@ __global__ void __launch_bounds__(kBlock, MinBlocks<T>::v) ff_kernel(const __gri
   const bool diag = blockIdx.x == 0 && threadIdx.x == 0;  // times as this CTA's first warp sees them
   unsigned long long t_mark = diag ? global_ns() : 0;
   const bool server = wib == kBlock / 32 - 1 && blockIdx.x % kServerStride == 0;
-  if (server) ff_server_warp<T>(sc, io, nfull0, total, lane, &nsub);
-  else ff_flight_warp<T>(sc, io, qn0, qfront, total, lane, nsub);
+  const unsigned epoch = *io.epoch;  // advanced by this step's step_kernel
+  if (server) ff_server_warp<T>(sc, io, epoch, nfull0, total, lane, &nsub);
+  else ff_flight_warp<T>(sc, io, epoch, qn0, qfront, total, lane, nsub);
   if (diag) {
     unsigned long long t = global_ns();
 #ifdef TB_FF_DIAG
@@ -1288,7 +1296,7 @@ struct tb_ctx {
   int *queue_full = nullptr;
   unsigned long long *dq = nullptr;          // the two dynamic queues of ff_kernel, dq_cap tagged slots each
   long long dq_cap = 0;
-  unsigned epoch = 0;
+  unsigned *epoch = nullptr;                 // device word, see StepIO
   unsigned long long *queue_ctrs = nullptr;  // two counter sets (kCtrWords each) used by alternate steps
   int parity = 0;
   unsigned ff_grid = 0;                      // persistent grid of ff_kernel
@@ -1372,8 +1380,7 @@ template <typename T, int KIND> static int step_resident_ctas(tb_ctx *c) {
 static int launch_step(tb_ctx *c, StepIO &io, cudaStream_t stream, bool stage = false) {
   io.queue = c->queue; io.queue_full = c->queue_full;
   io.dq_full = c->dq; io.dq_late = c->dq ? c->dq + c->dq_cap : nullptr; io.dq_cap = c->dq_cap;
-  if (++c->epoch == 0) c->epoch = 1;  // (a slot written 2^32 steps ago with the same tag would have to survive untouched)
-  io.epoch = c->epoch;
+  io.epoch = c->epoch;  // (a slot written 2^32 steps ago with the same tag would have to survive untouched)
   io.queue_ctr = c->queue_ctrs + kCtrWords * c->parity;
   io.queue_ctr_next = c->queue_ctrs + kCtrWords * (c->parity ^ 1);
   c->parity ^= 1;
@@ -1490,6 +1497,8 @@ int tb_create(const tb_config *cfg, tb_ctx **out) {
   if (e == cudaSuccess) e = cudaMemsetAsync(c->state, 0, bytes, c->own_stream);
   if (e == cudaSuccess) e = cudaMemsetAsync(c->stats, 0, TB_NUM_STATS * sizeof(unsigned long long), c->own_stream);
   if (e == cudaSuccess) e = cudaMemsetAsync(c->queue_ctrs, 0, 2 * kCtrWords * sizeof(unsigned long long), c->own_stream);
+  if (e == cudaSuccess) e = cudaMalloc(&c->epoch, sizeof(unsigned));
+  if (e == cudaSuccess) e = cudaMemsetAsync(c->epoch, 0, sizeof(unsigned), c->own_stream);
   if (e == cudaSuccess && c->dq) e = cudaMemsetAsync(c->dq, 0, (size_t)c->dq_cap * 2 * sizeof(unsigned long long), c->own_stream);  // tag 0 = no epoch
   if (e == cudaSuccess) {
     // identity quaternion, episode = -1 so the first reset starts episode 0
@@ -1526,7 +1535,7 @@ int tb_destroy(tb_ctx *c) {
   DeviceGuard g(c->cfg.device);
   if (c->own_stream) { cudaStreamSynchronize(c->own_stream); cudaStreamDestroy(c->own_stream); }
   for (int i = 0; i < 3; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
-  cudaFree(c->state); cudaFree(c->stats); cudaFree(c->queue_ctrs); cudaFree(c->queue); cudaFree(c->dq); cudaFree(c->queue_full); cudaFree(c->pid);
+  cudaFree(c->state); cudaFree(c->stats); cudaFree(c->queue_ctrs); cudaFree(c->queue); cudaFree(c->dq); cudaFree(c->epoch); cudaFree(c->queue_full); cudaFree(c->pid);
   cudaFree(c->d_actions); cudaFree(c->d_obs); cudaFree(c->d_reward); cudaFree(c->d_term);
   cudaFree(c->d_done); cudaFree(c->d_events); cudaFree(c->d_mask);
   delete c;
