@@ -1114,6 +1114,65 @@ template <typename T> __device__ __forceinline__ int ff_classify_state(const Sce
   return ff_classify_core(sc, s.rp, s.rq, s.bp, s.goal, dot3(s.bv, s.bv), dot3(s.rv, s.rv), dot3(s.rw, s.rw), s.step);
 }
 
+// The control-phase substep of SwingRacket-v0 (swingracket_env.py:76-83) for an env that ff_classify_state() puts in
+// kFfFree: the substep cannot touch anything, so it is physics_step without detection, contact solve and clamps, as
+// one straight line: force and torque of the action at the COM (racket.py:92-100), damping as one factor per body,
+// Euler's equations in the body (= principal) frame, q <- q exp(omega_body dt) with the short half-angle series (the
+// classification bounds |omega| and every speed with room for one substep of the largest action).  Equal to
+// physics_step in exact arithmetic, to ~1e-16 per substep in floating point.  Returns the event bits of the substep
+// (TB_EV_RACKET_LOW at most).  step_kernel defers every other env to the generic path (ff_kernel's prologue).
+template <typename T> __device__ __forceinline__ int ctl_fast(const Scene<T> &sc, St<T> &s, const float *a) {
+  const T dt = sc.dt;
+  T R[9];
+  quat_to_mat(s.rq, R);
+  int bits;
+  {  // TB_EV_RACKET_LOW at the start-of-step pose, exact test as in physics_step
+    T zlo = R[8] * sc.racket_obb[1], zhi = R[8] * sc.racket_obb[2];
+    T low = s.rp[2] - M<T>::abs(R[6]) * sc.racket.half_thick - M<T>::abs(R[7]) * sc.racket_obb[0] + (zlo < zhi ? zlo : zhi) - sc.hull_margin;
+    bool is_low = (low <= sc.ffp_low) & (M<T>::abs(s.rp[0]) <= sc.ffp_court[0]) & (M<T>::abs(s.rp[1]) <= sc.ffp_court[1]);
+    bits = is_low ? TB_EV_RACKET_LOW : 0;
+  }
+  const T F[3] = {(T)a[0] * 400, (T)a[1] * 400, (T)a[2] * 400 + (T)(4 * 9.81)};
+  const T Tq[3] = {(T)a[3] * 5, (T)a[4] * 5, (T)a[5] * 5};
+  T fb = 1 - sc.ff_kl * (1 + M<T>::norm_damp(dot3(s.bv, s.bv)));
+  s.bv[0] *= fb; s.bv[1] *= fb; s.bv[2] = s.bv[2] * fb + sc.ff_dtg;
+  T fs = 1 - sc.ff_ka * (1 + M<T>::norm_damp(dot3(s.bw, s.bw)));
+  s.bw[0] *= fs; s.bw[1] *= fs; s.bw[2] *= fs;
+  T fr = 1 - sc.ff_kl * (1 + M<T>::norm_damp(dot3(s.rv, s.rv)));
+  const T dtm = dt * sc.racket_inv_m;
+  s.rv[0] = s.rv[0] * fr + dtm * F[0]; s.rv[1] = s.rv[1] * fr + dtm * F[1]; s.rv[2] = s.rv[2] * fr + (dtm * F[2] + sc.ff_dtg);
+  T fw = 1 - sc.ff_ka * (1 + M<T>::norm_damp(dot3(s.rw, s.rw)));  // |omega| is the same in both frames
+  T wl[3], tl[3];
+  matT_vec(R, s.rw, wl);
+  matT_vec(R, Tq, tl);
+  T p12 = wl[1] * wl[2], p20 = wl[2] * wl[0], p01 = wl[0] * wl[1];
+  wl[0] = wl[0] * fw - sc.ff_gyro[0] * p12 + dt * sc.racket_inv_i[0] * tl[0];
+  wl[1] = wl[1] * fw - sc.ff_gyro[1] * p20 + dt * sc.racket_inv_i[1] * tl[1];
+  wl[2] = wl[2] * fw - sc.ff_gyro[2] * p01 + dt * sc.racket_inv_i[2] * tl[2];
+  mat_vec(R, wl, s.rw);
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    s.bp[i] += dt * s.bv[i];
+    s.rp[i] += dt * s.rv[i];
+  }
+  {
+    T sinc, cw;
+    sinc_cos_short(sc.ff_qx2 * dot3(wl, wl), &sinc, &cw);
+    T k = (T)0.5 * dt * sinc;
+    T ax = wl[0] * k, ay = wl[1] * k, az = wl[2] * k;
+    const T q0 = s.rq[0], q1 = s.rq[1], q2 = s.rq[2], q3 = s.rq[3];
+    T x = cw * q0 + ax * q3 + az * q1 - ay * q2;
+    T y = cw * q1 + ay * q3 + ax * q2 - az * q0;
+    T z = cw * q2 + az * q3 + ay * q0 - ax * q1;
+    T w = cw * q3 - ax * q0 - ay * q1 - az * q2;
+    T n2 = x * x + y * y + z * z + w * w;
+    T inv = (T)1.5 - (T)0.5 * n2;  // first-order renormalisation, see integrate_quat
+    if (TB_UNLIKELY(M<T>::abs(n2 - 1) > (T)1e-4)) inv = fast_rsqrt(n2);
+    s.rq[0] = x * inv; s.rq[1] = y * inv; s.rq[2] = z * inv; s.rq[3] = w * inv;
+  }
+  return bits;
+}
+
 // The substep without a narrow phase: ff_substep with phase 2, no clamp, the short series and at most the one contact
 // a free-falling ball ends almost every flight with - the court's top face (kind == kFfLand).  There the contact
 // normal is +z, the tangents btPlaneSpace1 gives are -y and +x, and the three rows of a single sphere contact

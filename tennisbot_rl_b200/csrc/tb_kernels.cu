@@ -116,6 +116,8 @@ struct StepIO {
   unsigned long long *stats;
   int *queue;                        // env indices waiting for ff_kernel: long flights from the front, short from the back
   int *queue_full;                   // envs whose FIRST fast-forward substep needs the full treatment (step_kernel fills it)
+  int *queue_ctl;                    // SwingRacket envs whose control-phase substep needs the generic path (deferred by
+                                     // step_kernel, taken by ff_kernel's prologue)
   unsigned long long *dq_full, *dq_late;  // ff_kernel's dynamic queues (slots tagged with `epoch`): envs parked for a full
                                      // substep; envs whose flight goes on after one.  dq_cap slots each
   long long dq_cap;
@@ -194,6 +196,8 @@ constexpr int kCClaim0 = 5;       // claimed entries of queue (ff_kernel's fligh
 constexpr int kCFullClaim0 = 6;   // claimed entries of queue_full (ff_kernel's servers)
 constexpr int kCFullTail = 16, kCFullHead = 17;  // dq_full: reserved by producers / claimed by servers
 constexpr int kCLateTail = 32, kCLateHead = 33;  // dq_late: reserved by servers / claimed by flight lanes
+constexpr int kCCtl = 13;         // entries of queue_ctl
+constexpr int kCBarrier = 96;     // ff_kernel's grid barrier (own line)
 constexpr int kCLanded = 64;      // envs whose env step is over (own line: everybody polls it at the end)
 
 struct WarpStats {
@@ -286,24 +290,52 @@ __device__ __forceinline__ void finish_api(const Scene<T> &sc, const StepIO &io,
 #ifndef TB_STEP_MINB64
 #define TB_STEP_MINB64 3
 #endif
-template <typename T> struct StepMinBlocks { static constexpr int v = TB_STEP_MINB32; };
-template <> struct StepMinBlocks<double> { static constexpr int v = TB_STEP_MINB64; };
+#ifndef TB_STEP_SWING_MINB32
+#define TB_STEP_SWING_MINB32 5
+#endif
+#ifndef TB_STEP_SWING_MINB64
+#define TB_STEP_SWING_MINB64 4
+#endif
+// CTAs per SM the register budget of step_kernel is held to.  SwingRacket's instantiation holds the straight-line control
+// substep only (everything else is deferred to ff_kernel), Tennisbot's the generic physics_step.
+template <typename T, int KIND> struct StepMinBlocks { static constexpr int v = KIND == TB_ENV_SWING ? TB_STEP_SWING_MINB32 : TB_STEP_MINB32; };
+template <int KIND> struct StepMinBlocks<double, KIND> { static constexpr int v = KIND == TB_ENV_SWING ? TB_STEP_SWING_MINB64 : TB_STEP_MINB64; };
 
 // Everything an env step does once the state and the action of the warp's 32 envs sit in registers: the substep the
 // action drives, env logic, statistics, outputs, auto-reset, queueing for ff_kernel, state back to HBM.
-template <typename T, int KIND, bool STAGE>
-__device__ __forceinline__ void step_tile(const Scene<T> &sc, const StepIO &io, int64_t tile0, int rows, bool valid, St<T> &s,
+// DEFER (step_kernel, SwingRacket): envs that ff_classify_state() puts in kFfFree take the straight-line ctl_fast; every
+// other env is left untouched and appended to queue_ctl, for ff_kernel's prologue to run this same function on it
+// with DEFER off - gathered into dense warps there, and with the generic path's registers and rare code kept out of
+// step_kernel.  me: the lane's env (tile0 + lane in step_kernel; tile0 is only used by the STAGE row tiles).
+template <typename T, int KIND, bool STAGE, bool DEFER>
+__device__ __forceinline__ void step_tile(const Scene<T> &sc, const StepIO &io, int64_t tile0, int64_t me, int rows, bool valid, St<T> &s,
                                           const float *a, WarpStats &ws, int *s_cnt, unsigned long long *s_base, float *s_tile) {
   constexpr int OD = Dims<KIND>::obs;
   const unsigned full = 0xffffffffu;
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  const int64_t me = tile0 + lane;
   T *base = static_cast<T *>(io.state);
   StepCtl c = {0, 0, 0, 0.0f, false};
   bool fin = false;
   const T spin1 = s.bw[1], spin2 = s.bw[2];
   const uint32_t episode0 = s.episode;
-  if (valid) {
+  if (DEFER) {
+    bool defer = false;
+    if (valid) {
+      defer = io.pid != nullptr || (s.flags & kFlagDone) || ff_classify_state(sc, s) != kFfFree;
+      if (!defer) {
+        c.events = ctl_fast<T>(sc, s, a);
+        fin = !(++s.step > 25);  // swingracket_env.py:85-86; no contact, hence no reward in this substep
+      }
+    }
+    unsigned dm = __ballot_sync(full, defer);
+    if (TB_UNLIKELY(dm)) {
+      unsigned long long at = 0;
+      if (lane == 0) at = atomicAdd(io.queue_ctr + kCCtl, (unsigned long long)__popc(dm));
+      at = __shfl_sync(full, at, 0);
+      if (defer) io.queue_ctl[at + __popc(dm & ((1u << lane) - 1u))] = (int)me;
+    }
+    valid = valid && !defer;
+  } else if (valid) {
     c.done = s.flags & kFlagDone;
     if (TB_UNLIKELY(io.pid != nullptr)) {
       T pid[8];
@@ -386,7 +418,7 @@ __device__ __forceinline__ void step_tile(const Scene<T> &sc, const StepIO &io, 
 // STAGE: move the action / observation rows through warp-private shared-memory tiles (see below); chosen by the host
 // when the caller's buffers are pinned host memory, off for buffers in HBM where it only costs registers.
 template <typename T, int KIND, bool STAGE>
-__global__ void __launch_bounds__(kBlock, StepMinBlocks<T>::v) step_kernel(const __grid_constant__ Scene<T> sc, const __grid_constant__ StepIO io) {
+__global__ void __launch_bounds__(kBlock, StepMinBlocks<T, KIND>::v) step_kernel(const __grid_constant__ Scene<T> sc, const __grid_constant__ StepIO io) {
   __shared__ unsigned long long sacc[kBlock / 32][TB_NUM_STATS];
   __shared__ int s_cnt[3 * (kBlock / 32)];
   __shared__ unsigned long long s_base[3];
@@ -443,7 +475,7 @@ __global__ void __launch_bounds__(kBlock, StepMinBlocks<T>::v) step_kernel(const
     load_state(static_cast<const T *>(io.state), io.n, me, s);
     if (!STAGE) load_action<KIND>(io.actions, me, a);
   }
-  step_tile<T, KIND, STAGE>(sc, io, tile0, rows, valid, s, a, ws, s_cnt, s_base, s_tile);
+  step_tile<T, KIND, STAGE, KIND == TB_ENV_SWING>(sc, io, tile0, me, rows, valid, s, a, ws, s_cnt, s_base, s_tile);
   ws.flush(io.stats);
 }
 
@@ -486,6 +518,30 @@ constexpr int kFfMaxVisits = 3;  // an env that comes to the servers this often 
 constexpr long long kSpinLimit = 1LL << 33;  // clock cycles (~4 s) any wait may take before the launch gives up
 
 __device__ __forceinline__ unsigned long long ld_ctr(const unsigned long long *p) { return *reinterpret_cast<const volatile unsigned long long *>(p); }
+// All CTAs of the (co-resident) grid meet.  Returns false if the barrier could not complete (a time-out, or another CTA
+// gave up): the launch then ends without finishing its envs instead of hanging the device.
+__device__ __forceinline__ bool grid_barrier(unsigned long long *ctr) {
+  __shared__ int s_ok;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(ctr + kCBarrier, 1ULL);
+    int ok = 1;
+    long long t0 = clock64();
+    while (ld_ctr(ctr + kCBarrier) < (unsigned long long)gridDim.x) {
+      __nanosleep(100);
+      if (clock64() - t0 > kSpinLimit) {
+        atomicExch(ctr + kCError, 6ULL);
+        ok = 0;
+        break;
+      }
+    }
+    __threadfence();
+    s_ok = ok;
+  }
+  __syncthreads();
+  return s_ok != 0;
+}
 __device__ __forceinline__ unsigned long long global_ns() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
@@ -907,17 +963,47 @@ __device__ __noinline__ void ff_phase_finish(const Scene<T> &sc, const StepIO &i
   }
 }
 
+// ff_kernel's prologue for one CTA (out of line: the generic step's registers and spills stay out of the flight loop)
+template <typename T>
+__device__ __noinline__ void ff_prologue(const Scene<T> &sc, const StepIO &io, long long nctl, WarpStats *wsp, int *s_cnt,
+                                         unsigned long long *s_base, float *s_dummy) {
+  for (long long b0 = (long long)blockIdx.x * kBlock; b0 < nctl; b0 += (long long)gridDim.x * kBlock) {
+    const long long idx = b0 + threadIdx.x;
+    const bool valid = idx < nctl;
+    const int64_t me = valid ? (int64_t)io.queue_ctl[idx] : 0;
+    St<T> s;
+    float a[8];
+    if (valid) {
+      load_state(static_cast<const T *>(io.state), io.n, me, s);
+      load_action<TB_ENV_SWING>(io.actions, me, a);
+    }
+    step_tile<T, TB_ENV_SWING, false, false>(sc, io, 0, me, 0, valid, s, a, *wsp, s_cnt, s_base, s_dummy);
+  }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(kBlock, MinBlocks<T>::v) ff_kernel(const __grid_constant__ Scene<T> sc, const __grid_constant__ StepIO io) {
   __shared__ unsigned long long sacc[kBlock / 32][TB_NUM_STATS];
+  __shared__ int s_cnt[3 * (kBlock / 32)];
+  __shared__ unsigned long long s_base[3];
+  __shared__ float s_dummy[4];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   unsigned long long *ctr = io.queue_ctr;
-  const long long qfront = (long long)ctr[kCFront];  // queued envs (written by step_kernel, same stream)
-  const long long qn0 = qfront + (long long)ctr[kCBack], nfull0 = (long long)ctr[kCFull0];
-  const long long total = qn0 + nfull0;
-  if (total == 0) return;
+  const long long nctl = (long long)ctr[kCCtl];  // (written by step_kernel, same stream)
+  if (nctl == 0 && ctr[kCFront] + ctr[kCBack] + ctr[kCFull0] == 0) return;
   WarpStats ws;
   ws.init(sacc[wib], lane);
+  // ---- prologue: the control-phase substeps step_kernel deferred (ball within reach of something, PID mode, ...),
+  //      gathered into dense warps and taken through the generic path; those that were an env's 26th step join the
+  //      queues below, hence the grid barrier
+  if (nctl) {
+    ff_prologue<T>(sc, io, nctl, &ws, s_cnt, s_base, s_dummy);
+    if (!grid_barrier(ctr)) { ws.flush(io.stats); return; }
+  }
+  const long long qfront = (long long)ld_ctr(ctr + kCFront);  // queued envs
+  const long long qn0 = qfront + (long long)ld_ctr(ctr + kCBack), nfull0 = (long long)ld_ctr(ctr + kCFull0);
+  const long long total = qn0 + nfull0;
+  if (total == 0) { ws.flush(io.stats); return; }
   int nsub = 0;  // substeps this lane integrated
   const bool diag = blockIdx.x == 0 && threadIdx.x == 0;  // times as this CTA's first warp sees them
   unsigned long long t_mark = diag ? global_ns() : 0;
@@ -1293,7 +1379,7 @@ struct tb_ctx {
   uint8_t *d_done = nullptr, *d_events = nullptr, *d_mask = nullptr;
   int64_t launches = 0;
   int *queue = nullptr;                      // fast-forward work queue (env indices), num_envs entries
-  int *queue_full = nullptr;
+  int *queue_full = nullptr, *queue_ctl = nullptr;
   unsigned long long *dq = nullptr;          // the two dynamic queues of ff_kernel, dq_cap tagged slots each
   long long dq_cap = 0;
   unsigned *epoch = nullptr;                 // device word, see StepIO
@@ -1378,7 +1464,7 @@ template <typename T, int KIND> static int step_resident_ctas(tb_ctx *c) {
 }
 // One env step = step_kernel (+ ff_kernel for SwingRacket) on `stream`.
 static int launch_step(tb_ctx *c, StepIO &io, cudaStream_t stream, bool stage = false) {
-  io.queue = c->queue; io.queue_full = c->queue_full;
+  io.queue = c->queue; io.queue_full = c->queue_full; io.queue_ctl = c->queue_ctl;
   io.dq_full = c->dq; io.dq_late = c->dq ? c->dq + c->dq_cap : nullptr; io.dq_cap = c->dq_cap;
   io.epoch = c->epoch;  // (a slot written 2^32 steps ago with the same tag would have to survive untouched)
   io.queue_ctr = c->queue_ctrs + kCtrWords * c->parity;
@@ -1493,6 +1579,7 @@ int tb_create(const tb_config *cfg, tb_ctx **out) {
     e = cudaMalloc(&c->dq, (size_t)c->dq_cap * 2 * sizeof(unsigned long long));
   }
   if (e == cudaSuccess && cfg->env_kind == TB_ENV_SWING) e = cudaMalloc(&c->queue_full, (size_t)cfg->num_envs * sizeof(int));
+  if (e == cudaSuccess && cfg->env_kind == TB_ENV_SWING) e = cudaMalloc(&c->queue_ctl, (size_t)cfg->num_envs * sizeof(int));
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaMemsetAsync(c->state, 0, bytes, c->own_stream);
   if (e == cudaSuccess) e = cudaMemsetAsync(c->stats, 0, TB_NUM_STATS * sizeof(unsigned long long), c->own_stream);
@@ -1535,7 +1622,7 @@ int tb_destroy(tb_ctx *c) {
   DeviceGuard g(c->cfg.device);
   if (c->own_stream) { cudaStreamSynchronize(c->own_stream); cudaStreamDestroy(c->own_stream); }
   for (int i = 0; i < 3; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
-  cudaFree(c->state); cudaFree(c->stats); cudaFree(c->queue_ctrs); cudaFree(c->queue); cudaFree(c->dq); cudaFree(c->epoch); cudaFree(c->queue_full); cudaFree(c->pid);
+  cudaFree(c->state); cudaFree(c->stats); cudaFree(c->queue_ctrs); cudaFree(c->queue); cudaFree(c->dq); cudaFree(c->epoch); cudaFree(c->queue_full); cudaFree(c->queue_ctl); cudaFree(c->pid);
   cudaFree(c->d_actions); cudaFree(c->d_obs); cudaFree(c->d_reward); cudaFree(c->d_term);
   cudaFree(c->d_done); cudaFree(c->d_events); cudaFree(c->d_mask);
   delete c;
