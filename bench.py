@@ -106,12 +106,12 @@ class ClockSampler:
 
 
 def measured_traffic(env, precision, n):
-    """DRAM bytes of one step_kernel launch (dram__bytes_read.sum + dram__bytes_write.sum) from the committed ncu capture
-    of the same workload, else None."""
+    """DRAM bytes of one env step of the whole batch (dram__bytes_read.sum + dram__bytes_write.sum of a step_kernel launch
+    + 1/26 of a fast-forward ff_kernel launch) from the committed ncu captures of the same workload, else None."""
     p = ROOT / "profiles" / "r1_traffic.json"
     if env == "SwingRacket-v0" and precision == "f64" and n == 1 << 20 and p.exists():
         try:
-            return float(json.loads(p.read_text())["step_kernel_dram_bytes_per_launch"])
+            return float(json.loads(p.read_text())["dram_bytes_per_env_step_launch_pair"])
         except Exception:
             pass
     return None
@@ -317,20 +317,25 @@ def run_b200(args, rank, world):
                        "alignment_steps": align,
                        "l2_policy": "working set per launch %.0f MB > 126 MB L2 (inputs larger than L2)" % (n * algo / 1e6),
                        "parallelism": f"env-sharded x{world}, no data-path collective; int64[10] stats all-reduce per {EPISODE_STEPS} steps"},
-            # the dominant kernel = the one with the larger share of the step time.  step_kernel is HBM-bound: its
-            # algorithmic bytes (action + obs + reward + done + state read + state written) over its mean
-            # launch duration.  The whole-step figure (both kernels, same bytes) is kept beside it.
-            "roofline": {"bound": "hbm", "kernel": "step_kernel", "achieved": step_gbs, "peak": peak, "unit": "GB/s",
-                         "frac": step_gbs / peak,
+            # One env step is a pair of launches whose shares shift with the precision and the step of the episode, so the
+            # headline roofline figure is the whole step: algorithmic bytes of an env step (action + obs +
+            # reward + done + state read + state written) over the mean step time of the timed region.  Per kernel:
+            # step_kernel is HBM-bound (its own algorithmic fraction and the DRAM bytes ncu saw per launch are given);
+            # ff_kernel is bound by the FP64 pipe / latency, not by memory (profiles/).
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": measured_traffic(args.env, args.precision, n), "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": n * algo, "algorithmic_bytes_per_env_step": algo,
-                         "ms_per_launch": ms_step, "share_of_step_time": ms_a / max(ms_a + ms_b, 1e-9),
-                         "whole_step": {"achieved": achieved, "frac": achieved / peak,
-                                        "scope": "step_kernel + ff_kernel: algorithmic bytes of the step / mean step time of the timed region"},
-                         "ff_kernel": {"ms_per_launch": ms_b / max(nk, 1), "share_of_step_time": ms_b / max(ms_a + ms_b, 1e-9),
-                                       "ms_per_fast_forward_launch": ms_b / max(nk, 1) * (EPISODE_STEPS if args.env == "SwingRacket-v0" else 1),
-                                       "bound": "fp64 pipe / latency: ~150 dependent FP64 instructions per physics substep, "
-                                                "~110 substeps per env on its 26th step; not memory-bound (see profiles/)"}},
+                         "scope": "whole env step = step_kernel + ff_kernel: algorithmic bytes of the step / mean step time",
+                         "kernels": {
+                             "step_kernel": {"ms_per_launch": ms_step, "achieved_gbs": step_gbs, "frac": step_gbs / peak, "bound": "hbm",
+                                             "share_of_step_time": ms_a / max(ms_a + ms_b, 1e-9),
+                                             "note": "algorithmic bytes of all envs over this kernel's mean launch time; in SwingRacket the "
+                                                     "envs whose control substep can touch something (up to ~30 % in the last steps of an "
+                                                     "episode) are only classified here and stepped by ff_kernel's prologue"},
+                             "ff_kernel": {"ms_per_launch": ms_b / max(nk, 1), "share_of_step_time": ms_b / max(ms_a + ms_b, 1e-9),
+                                           "ms_per_episode": ms_b / max(nk, 1) * (EPISODE_STEPS if args.env == "SwingRacket-v0" else 1),
+                                           "bound": "fp64 pipe / latency: ~150 dependent FP64 instructions per physics substep, "
+                                                    "~110 substeps per env on its 26th step; not memory-bound (see profiles/)"}}},
             "e2e": {"value": total_envs * args.e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "steps": args.e2e_steps, "api": "TennisBatch.step_host -> tb_step_host: pinned host buffers in and out; the kernels read the actions from and write obs/reward/done to host memory over PCIe themselves (both directions concurrent with the compute)"},
             "gpu_launches": int(launches),
