@@ -120,6 +120,32 @@ def test_f64_fast_forward_final_state(oracle_lib, params):
     assert np.abs(gs - os_).max() < TOL_F64_STATE
 
 
+def test_f64_parity_hit_env_tracking_policy(oracle_lib):
+    """Config 3 shape (incoming-ball env *with racket-ball contact*): random actions almost never meet the ball, so the
+    racket is steered towards the ball's y (a scripted policy on the oracle's observation).  A few hundred episodes then
+    contain racket-ball contact steps (asserted), which exercises the dynamic two-body solve and the hit rewards
+    (tennisbot_env.py:170-180)."""
+    n = 4096
+    b, o = _make("Tennisbot-v0", n, "f64", 31, oracle_lib)
+    obs0 = o.reset()
+    np.testing.assert_array_equal(b.reset().cpu().numpy(), obs0)
+    rng = np.random.default_rng(2)
+
+    def policy(t, obs):
+        a = np.zeros((n, 2))
+        a[:, 0] = rng.uniform(-0.2, 0.2, n)
+        a[:, 1] = np.clip(4.0 * (obs[:, 7] - obs[:, 1]) - 1.5 * obs[:, 4], -1, 1)  # PD on ball y - racket y
+        return a
+
+    rep, valid = run_parity(b, o, 900, policy, band=0.0, check_state_every=50, obs0=obs0)
+    print(rep, b.read_stats().tolist())
+    assert rep.event_mismatch_hard == 0 and rep.event_mismatch_near == 0
+    assert rep.max_state_err < TOL_F64_STATE and rep.max_obs_err < TOL_F64_OUT and rep.max_reward_err < TOL_F64_OUT
+    st = b.read_stats()
+    np.testing.assert_array_equal(st, o.read_stats())
+    assert st[0] > 0 and st[2] > 0.05 * st[0]  # several times the hit rate of random actions (the racket cannot choose its height)
+
+
 @pytest.mark.parametrize("env,steps", [("SwingRacket-v0", 52), ("Tennisbot-v0", 700)])
 def test_f32_parity_with_band(oracle_lib, env, steps):
     """float32 path: every contact / done decision equals the oracle's unless the oracle's own margin to the
