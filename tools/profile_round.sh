@@ -1,6 +1,6 @@
 #!/bin/bash
 # Run on the GPU box (gpurun): launch list of a short bench run + full captures of the two step kernels (f64, 1 Mi envs).
-# usage: tools/profile_round.sh r1
+# usage: tools/profile_round.sh r1   (then summarise with tools/ncu_summary.py / ncu_lines.py into profiles/)
 R=${1:-r1}
 set -x
 python bench.py --steps 26 --warmup 26 --skip-cpu-baseline > gpurun_out/bench_plain_$R.log 2>&1 &&
