@@ -172,13 +172,16 @@ template <int KIND> __device__ __forceinline__ void random_action(uint64_t seed,
 //
 //   step_kernel  one thread per env, plain grid: loads state + action (128-bit coalesced), runs the substep the
 //                action drives and the env logic; envs whose step is complete write obs / reward / done,
-//                auto-reset and store their state.  HBM-bound.  Envs that enter the fast-forward store their state
-//                with the in-flight mark and append their index to a work queue (one atomic per CTA).
-//   ff_kernel    persistent warps; every LANE is a small state machine that pulls an env from the queue, keeps
-//                its state in registers for the whole fast-forward (one substep per loop iteration) and, when the
-//                ball lands / times out, finishes the env step and goes back for another env.  A lane stuck in an
-//                800-substep flight delays nobody.  ALU/latency-bound; launched on every step, exits at once
-//                when the queue is empty.
+//                auto-reset and store their state.  HBM-bound.  SwingRacket: only the straight-line substep
+//                (ctl_fast) lives here; an env within reach of anything is appended to a list instead.  Envs that
+//                enter the fast-forward store their state with the in-flight mark and append their index to one of
+//                three work lists (one atomic per CTA and list).
+//   ff_kernel    (SwingRacket) persistent; prologue: the deferred control substeps through the generic path, in dense
+//                warps.  Then flight warps (every LANE a small state machine that claims an env, keeps its flight state
+//                in registers, one straight-line substep per loop iteration) and server warps (generic substeps for
+//                flights that come within reach of something), linked by ticketed queues; finally the completion pass
+//                for every env that landed.  FP64-pipe / latency-bound; launched on every step, exits at once when
+//                nothing is queued.
 //
 // Episode statistics are warp-uniform popc()/redux sums kept in shared memory, one atomic per counter per warp.
 constexpr int kFlagDone = 1, kFlagInFlight = 2, kFlagEventShift = 8;
@@ -188,7 +191,7 @@ constexpr int kFlagFirst = 8;       // the flight's first substep (no external f
 constexpr int kFlagLastShift = 16;  // contact bits of the flight's last substep
 constexpr int kFlagVisitShift = 4;  // 2 bits: visits to the full path during this flight
 // counter words of one step's set
-constexpr int kCtrWords = 512;  // (words 128.. : TB_FF_DIAG time series)  // four 128-byte lines: what is polled never shares a line with what is claimed from
+constexpr int kCtrWords = 512;  // words that are polled never share a 128-byte line with words that are claimed from; words 128.. : TB_FF_DIAG time series
 constexpr int kCFront = 0, kCBack = 1, kCError = 3;
 constexpr int kDRounds = 48, kDFullEnvs = 49, kDPhase = 50, kDFinish = 62;  // tb_ff_diagnostics
 constexpr int kCFull0 = 4;        // entries of queue_full (appended by step_kernel)
@@ -1393,7 +1396,7 @@ struct tb_ctx {
   bool timing = false;                       // tb_set_kernel_timing
   cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
   double ms_step = 0, ms_ff = 0;
-  int64_t timed_steps = 0;  // persistent grid of step_kernel<.., ROLLOUT=false/true>
+  int64_t timed_steps = 0;
 };
 
 struct DeviceGuard {
