@@ -159,10 +159,12 @@ int tb_step_host(tb_ctx *ctx, const float *h_actions, float *h_obs, float *h_rew
 /* number of kernels this context has launched (bench.py's gpu_launches) */
 int tb_launch_count(tb_ctx *ctx, int64_t *launches);
 
-/* Diagnostics of the most recent SwingRacket fast-forward (tb_step's second kernel): out[0] = rounds, out[1] = envs that
- * took the generic full-substep path at least once, out[2 + 2r], out[3 + 2r] = nanoseconds spent in round r's full and
- * fast phases (r < 6), out[14] = nanoseconds of the finishing pass, out[15] = non-zero if a grid barrier gave up.
- * Synchronises the context's last stream work.  h_out: 16 x int64. */
+/* Diagnostics of the most recent SwingRacket fast-forward (the launch of tb_step's second kernel on an env's 26th
+ * step; read it before the next step): out[0] = 1 if one ran, out[1] = visits of envs to the generic full-substep path
+ * (server warps), out[2] = nanoseconds until every flight had landed, out[3..13] = reserved (instrumented builds),
+ * out[14] = nanoseconds of the finishing pass, out[15] = non-zero if a wait inside a fast-forward launch of this
+ * context has ever timed out (sticky; that launch left envs unfinished instead of hanging the device, and
+ * tb_read_stats fails from then on).  Synchronises the device.  h_out: 16 x int64. */
 int tb_ff_diagnostics(tb_ctx *ctx, int64_t *h_out);
 
 /* Per-kernel device timing for roofline reports.  While enabled, every tb_step brackets its two kernels with CUDA

@@ -124,6 +124,7 @@ struct StepIO {
   unsigned *epoch;                   // device word: step counter of the context, never 0: tag of this launch's queue slots
                                      // (advanced by step_kernel itself, so a captured CUDA graph of steps can be replayed)
   int prefetch_ahead;                // step_kernel: CTAs resident at a time (the L2 prefetch distance), 0 = none
+  unsigned long long *fault;         // sticky: non-zero once a wait inside ff_kernel has timed out (tb_read_stats fails then)
   unsigned long long *queue_ctr;     // kCtrWords counters (kC* below): [0] front, [1] back entries appended by this
                                      // step's step_kernel, the rest ff_kernel's
   unsigned long long *queue_ctr_next;  // the set the NEXT step uses; step_kernel zeroes it
@@ -1001,7 +1002,11 @@ __global__ void __launch_bounds__(kBlock, MinBlocks<T>::v) ff_kernel(const __gri
   //      queues below, hence the grid barrier
   if (nctl) {
     ff_prologue<T>(sc, io, nctl, &ws, s_cnt, s_base, s_dummy);
-    if (!grid_barrier(ctr)) { ws.flush(io.stats); return; }
+    if (!grid_barrier(ctr)) {
+      if (threadIdx.x == 0) atomicExch(io.fault, 6ULL);
+      ws.flush(io.stats);
+      return;
+    }
   }
   const long long qfront = (long long)ld_ctr(ctr + kCFront);  // queued envs
   const long long qn0 = qfront + (long long)ld_ctr(ctr + kCBack), nfull0 = (long long)ld_ctr(ctr + kCFull0);
@@ -1026,6 +1031,7 @@ __global__ void __launch_bounds__(kBlock, MinBlocks<T>::v) ff_kernel(const __gri
     ctr[kDRounds] = 1;
     ctr[kDFullEnvs] = ld_ctr(ctr + kCFullTail) + (unsigned long long)nfull0;
   }
+  if (ld_ctr(ctr + kCError) != 0 && threadIdx.x == 0) atomicExch(io.fault, ld_ctr(ctr + kCError));
   if (ld_ctr(ctr + kCError) == 0) {  // every env has landed, and their states are visible (fence before the count)
     __threadfence();
     nsub = __reduce_add_sync(0xffffffffu, nsub);
@@ -1386,6 +1392,7 @@ struct tb_ctx {
   unsigned long long *dq = nullptr;          // the two dynamic queues of ff_kernel, dq_cap tagged slots each
   long long dq_cap = 0;
   unsigned *epoch = nullptr;                 // device word, see StepIO
+  unsigned long long *fault = nullptr;       // device word, see StepIO
   unsigned long long *queue_ctrs = nullptr;  // two counter sets (kCtrWords each) used by alternate steps
   int parity = 0;
   unsigned ff_grid = 0;                      // persistent grid of ff_kernel
@@ -1468,6 +1475,7 @@ template <typename T, int KIND> static int step_resident_ctas(tb_ctx *c) {
 // One env step = step_kernel (+ ff_kernel for SwingRacket) on `stream`.
 static int launch_step(tb_ctx *c, StepIO &io, cudaStream_t stream, bool stage = false) {
   io.queue = c->queue; io.queue_full = c->queue_full; io.queue_ctl = c->queue_ctl;
+  io.fault = c->fault;
   io.dq_full = c->dq; io.dq_late = c->dq ? c->dq + c->dq_cap : nullptr; io.dq_cap = c->dq_cap;
   io.epoch = c->epoch;  // (a slot written 2^32 steps ago with the same tag would have to survive untouched)
   io.queue_ctr = c->queue_ctrs + kCtrWords * c->parity;
@@ -1587,6 +1595,8 @@ int tb_create(const tb_config *cfg, tb_ctx **out) {
   if (e == cudaSuccess) e = cudaMemsetAsync(c->state, 0, bytes, c->own_stream);
   if (e == cudaSuccess) e = cudaMemsetAsync(c->stats, 0, TB_NUM_STATS * sizeof(unsigned long long), c->own_stream);
   if (e == cudaSuccess) e = cudaMemsetAsync(c->queue_ctrs, 0, 2 * kCtrWords * sizeof(unsigned long long), c->own_stream);
+  if (e == cudaSuccess) e = cudaMalloc(&c->fault, sizeof(unsigned long long));
+  if (e == cudaSuccess) e = cudaMemsetAsync(c->fault, 0, sizeof(unsigned long long), c->own_stream);
   if (e == cudaSuccess) e = cudaMalloc(&c->epoch, sizeof(unsigned));
   if (e == cudaSuccess) e = cudaMemsetAsync(c->epoch, 0, sizeof(unsigned), c->own_stream);
   if (e == cudaSuccess && c->dq) e = cudaMemsetAsync(c->dq, 0, (size_t)c->dq_cap * 2 * sizeof(unsigned long long), c->own_stream);  // tag 0 = no epoch
@@ -1625,7 +1635,7 @@ int tb_destroy(tb_ctx *c) {
   DeviceGuard g(c->cfg.device);
   if (c->own_stream) { cudaStreamSynchronize(c->own_stream); cudaStreamDestroy(c->own_stream); }
   for (int i = 0; i < 3; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
-  cudaFree(c->state); cudaFree(c->stats); cudaFree(c->queue_ctrs); cudaFree(c->queue); cudaFree(c->dq); cudaFree(c->epoch); cudaFree(c->queue_full); cudaFree(c->queue_ctl); cudaFree(c->pid);
+  cudaFree(c->state); cudaFree(c->stats); cudaFree(c->queue_ctrs); cudaFree(c->queue); cudaFree(c->dq); cudaFree(c->epoch); cudaFree(c->fault); cudaFree(c->queue_full); cudaFree(c->queue_ctl); cudaFree(c->pid);
   cudaFree(c->d_actions); cudaFree(c->d_obs); cudaFree(c->d_reward); cudaFree(c->d_term);
   cudaFree(c->d_done); cudaFree(c->d_events); cudaFree(c->d_mask);
   delete c;
@@ -1721,9 +1731,15 @@ int tb_read_stats(tb_ctx *c, int64_t *h_stats, int clear, void *stream) {
   GUARD(c);
   if (!h_stats) return fail("%s", "tb_read_stats: h_stats is NULL");
   cudaStream_t s = (cudaStream_t)stream;
+  unsigned long long fault = 0;
   CU(cudaMemcpyAsync(h_stats, c->stats, TB_NUM_STATS * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+  CU(cudaMemcpyAsync(&fault, c->fault, sizeof fault, cudaMemcpyDeviceToHost, s));
   if (clear) CU(cudaMemsetAsync(c->stats, 0, TB_NUM_STATS * sizeof(int64_t), s));
   CU(cudaStreamSynchronize(s));
+  if (fault) {  // never seen; a wait in ff_kernel gave up (kSpinLimit) and that launch left envs unfinished
+    std::snprintf(g_err, sizeof g_err, "tb_read_stats: a fast-forward launch timed out waiting on its work queues (code %llu); the batch state is incomplete", fault);
+    return 1;
+  }
   return 0;
 }
 
@@ -1821,6 +1837,11 @@ int tb_ff_diagnostics(tb_ctx *c, int64_t *h_out) {
   for (int i = 0; i < 14; ++i) h_out[i] = (int64_t)s[kDRounds + i];  // rounds, full-path envs, phase times
   h_out[14] = (int64_t)s[kDFinish];
   h_out[15] = (int64_t)s[kCError];
+  {
+    unsigned long long fault = 0;
+    CU(cudaMemcpy(&fault, c->fault, sizeof fault, cudaMemcpyDeviceToHost));
+    if (fault) h_out[15] = (int64_t)fault;
+  }
   if (std::getenv("TB_FF_DIAG_DUMP"))
     for (int b = 0; b < 76 && s[128 + 5 * b]; ++b)
       std::fprintf(stderr, "t=%.1fms landed %llu fullq %llu/%llu lateq %llu/%llu\n", 0.5 * b, s[128 + 5 * b] - 1, s[130 + 5 * b], s[129 + 5 * b],
