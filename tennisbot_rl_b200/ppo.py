@@ -62,7 +62,7 @@ class SwingPPO:
         self.n = n = int(num_envs)
         self.env = TennisBatch("SwingRacket-v0", n, device=device, seed=seed, precision=precision)
         self.ac = ActorCritic().to(self.dev)
-        self.opt = torch.optim.Adam(self.ac.parameters(), lr=lr, eps=1e-5)
+        self.opt = torch.optim.Adam(self.ac.parameters(), lr=lr, eps=1e-5, capturable=use_graph)
         self.epochs, self.minibatches = epochs, minibatches
         self.gamma, self.lam, self.clip, self.ent_coef, self.vf_coef, self.max_norm = 0.99, 0.95, 0.2, 0.002, 0.5, 0.5
         z = lambda *s: torch.zeros(s, device=self.dev)  # noqa: E731
@@ -72,6 +72,11 @@ class SwingPPO:
         self.graph = None
         self.use_graph = use_graph
         self.rollout_s = 0.0
+        # one minibatch update as a CUDA graph over static buffers (the update is ~40 small kernels, 80 times per iteration)
+        self.mb = EPISODE * n // minibatches
+        self.upd_graph = None
+        self.mb_obs, self.mb_act = z(self.mb, 6), z(self.mb, 6)
+        self.mb_logp, self.mb_adv, self.mb_ret = z(self.mb), z(self.mb), z(self.mb)
 
     # ------------------------------------------------------------------ rollout
     def _rollout_body(self):
@@ -130,21 +135,44 @@ class SwingPPO:
         B = EPISODE * n
         fo, fa, fl = self.obs_buf.reshape(B, 6), self.act_buf.reshape(B, 6), self.logp_buf.reshape(B)
         fadv, fret = adv.reshape(B), ret.reshape(B)
-        mb = B // self.minibatches
+        mb = self.mb
         for _ in range(self.epochs):
             perm = torch.randperm(B, device=self.dev)
             for k in range(self.minibatches):
                 idx = perm[k * mb:(k + 1) * mb]
-                ratio = (ac.log_prob(fo[idx], fa[idx]) - fl[idx]).exp()
-                a_ = fadv[idx]
-                a_ = (a_ - a_.mean()) / (a_.std() + 1e-8)
-                pg = -torch.min(ratio * a_, ratio.clamp(1 - self.clip, 1 + self.clip) * a_).mean()
-                vloss = 0.5 * (ac.value(fo[idx]) - fret[idx]).pow(2).mean()
-                loss = pg + self.vf_coef * vloss - self.ent_coef * ac.entropy()
-                self.opt.zero_grad(set_to_none=False)  # the captured rollout reads the parameters, not the grads; keep both in place
-                loss.backward()
-                nn.utils.clip_grad_norm_(ac.parameters(), self.max_norm)
-                self.opt.step()
+                torch.index_select(fo, 0, idx, out=self.mb_obs)
+                torch.index_select(fa, 0, idx, out=self.mb_act)
+                torch.index_select(fl, 0, idx, out=self.mb_logp)
+                torch.index_select(fadv, 0, idx, out=self.mb_adv)
+                torch.index_select(fret, 0, idx, out=self.mb_ret)
+                if not self.use_graph:
+                    self._minibatch_step()
+                    continue
+                if self.upd_graph is None:
+                    s = torch.cuda.Stream(self.dev)
+                    s.wait_stream(torch.cuda.current_stream(self.dev))
+                    with torch.cuda.stream(s):
+                        for _w in range(3):
+                            self._minibatch_step()
+                    torch.cuda.current_stream(self.dev).wait_stream(s)
+                    self.upd_graph = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(self.upd_graph):
+                        self._minibatch_step()
+                else:
+                    self.upd_graph.replay()
+
+    def _minibatch_step(self):
+        ac = self.ac
+        ratio = (ac.log_prob(self.mb_obs, self.mb_act) - self.mb_logp).exp()
+        a_ = self.mb_adv
+        a_ = (a_ - a_.mean()) / (a_.std() + 1e-8)
+        pg = -torch.min(ratio * a_, ratio.clamp(1 - self.clip, 1 + self.clip) * a_).mean()
+        vloss = 0.5 * (ac.value(self.mb_obs) - self.mb_ret).pow(2).mean()
+        loss = pg + self.vf_coef * vloss - self.ent_coef * ac.entropy()
+        self.opt.zero_grad(set_to_none=False)  # grads stay in place: the captured graphs refer to their storage
+        loss.backward()
+        nn.utils.clip_grad_norm_(ac.parameters(), self.max_norm)
+        self.opt.step()
 
     def train(self, iters=150, target=31.5, log=None):
         history, reached, t0 = [], None, time.time()
