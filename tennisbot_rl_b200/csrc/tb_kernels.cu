@@ -831,7 +831,7 @@ __device__ __noinline__ void ff_server_warp(const Scene<T> &sc, const StepIO &io
     }
     const unsigned held = __ballot_sync(full, busy || waiting || got);
     if (__popc(held) < kServerLanes) {
-      const unsigned cand = ~held & ((1u << kServerLanes) - 1u);  // lanes 0 .. kServerLanes-1 only ever hold envs
+      const unsigned cand = ~held & (kServerLanes >= 32 ? 0xffffffffu : (1u << (kServerLanes & 31)) - 1u);  // lanes 0 .. kServerLanes-1 only ever hold envs
       if (!exhausted0) {
         const int want = __popc(cand);
         long long at = 0;
