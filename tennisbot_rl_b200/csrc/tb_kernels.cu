@@ -15,6 +15,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <new>
+#include <utility>
 
 #include "tb_device.cuh"
 
@@ -305,6 +306,12 @@ __device__ __forceinline__ void finish_api(const Scene<T> &sc, const StepIO &io,
 template <typename T, int KIND> struct StepMinBlocks { static constexpr int v = KIND == TB_ENV_SWING ? TB_STEP_SWING_MINB32 : TB_STEP_MINB32; };
 template <int KIND> struct StepMinBlocks<double, KIND> { static constexpr int v = KIND == TB_ENV_SWING ? TB_STEP_SWING_MINB64 : TB_STEP_MINB64; };
 
+// Programmatic dependent launch (sm_90+): a kernel launched with the stream-serialisation attribute may be staged on the
+// device while its predecessor drains; it must not touch the predecessor's results before pdl_wait(), which returns once
+// that grid has completed and flushed.  Without the attribute both are no-ops.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // Everything an env step does once the state and the action of the warp's 32 envs sit in registers: the substep the
 // action drives, env logic, statistics, outputs, auto-reset, queueing for ff_kernel, state back to HBM.
 // DEFER (step_kernel, SwingRacket): envs that ff_classify_state() puts in kFfFree take the straight-line ctl_fast; every
@@ -434,6 +441,7 @@ __global__ void __launch_bounds__(kBlock, StepMinBlocks<T, KIND>::v) step_kernel
   __shared__ __align__(16) float s_tiles[STAGE ? kBlock / 32 : 1][STAGE ? 32 * OD : 4];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   float *s_tile = s_tiles[STAGE ? wib : 0];
+  pdl_wait();  // (programmatic dependent launch: this grid may be staged while the previous kernel of the stream drains)
   WarpStats ws;
   ws.init(sacc[wib], lane);
   if (blockIdx.x == 0) {
@@ -481,6 +489,7 @@ __global__ void __launch_bounds__(kBlock, StepMinBlocks<T, KIND>::v) step_kernel
   }
   step_tile<T, KIND, STAGE, KIND == TB_ENV_SWING>(sc, io, tile0, me, rows, valid, s, a, ws, s_cnt, s_base, s_tile);
   ws.flush(io.stats);
+  pdl_trigger();
 }
 
 // Fast-forward continuation (SwingRacket only): one persistent launch (a CTA per resident slot) whose warps have roles:
@@ -993,6 +1002,7 @@ __global__ void __launch_bounds__(kBlock, MinBlocks<T>::v) ff_kernel(const __gri
   __shared__ float s_dummy[4];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   unsigned long long *ctr = io.queue_ctr;
+  pdl_wait();
   const long long nctl = (long long)ctr[kCCtl];  // (written by step_kernel, same stream)
   if (nctl == 0 && ctr[kCFront] + ctr[kCBack] + ctr[kCFull0] == 0) return;
   WarpStats ws;
@@ -1397,6 +1407,7 @@ struct tb_ctx {
   int parity = 0;
   unsigned ff_grid = 0;                      // persistent grid of ff_kernel
   int step_resident = -1;                    // resident CTAs of step_kernel (its L2 prefetch distance)
+  bool pdl = std::getenv("TB_NO_PDL") == nullptr;  // programmatic dependent launch of the step's kernels
   int control_mode = TB_CONTROL_FORCE;
   void *pid = nullptr;                       // controller memory, allocated by tb_set_control_mode(TB_CONTROL_PID)
   bool zero_copy = std::getenv("TB_HOST_STAGING") == nullptr;  // tb_step_host: address pinned host buffers from the kernels
@@ -1472,6 +1483,16 @@ template <typename T, int KIND> static int step_resident_ctas(tb_ctx *c) {
   c->step_resident = std::getenv("TB_NO_PREFETCH") ? 0 : sms * (per_sm > 0 ? per_sm : 1);
   return 0;
 }
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_pdl(bool pdl, void (*kernel)(KArgs...), unsigned grid, cudaStream_t stream, Args &&...args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kBlock); cfg.dynamicSmemBytes = 0; cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
 // One env step = step_kernel (+ ff_kernel for SwingRacket) on `stream`.
 static int launch_step(tb_ctx *c, StepIO &io, cudaStream_t stream, bool stage = false) {
   io.queue = c->queue; io.queue_full = c->queue_full; io.queue_ctl = c->queue_ctl;
@@ -1487,11 +1508,11 @@ static int launch_step(tb_ctx *c, StepIO &io, cudaStream_t stream, bool stage = 
 #define TB_LAUNCH_STEP(T, K, SC)                                                                           \
   do {                                                                                                    \
     if (stage) {                                                                                          \
-      step_kernel<T, K, true><<<grid, kBlock, 0, stream>>>(SC, io);                                       \
+      CU(launch_pdl(c->pdl, step_kernel<T, K, true>, grid, stream, SC, io));                             \
     } else {                                                                                              \
       if (c->step_resident < 0 && step_resident_ctas<T, K>(c)) return 1;                                  \
       io.prefetch_ahead = c->step_resident;                                                               \
-      step_kernel<T, K, false><<<grid, kBlock, 0, stream>>>(SC, io);                                      \
+      CU(launch_pdl(c->pdl, step_kernel<T, K, false>, grid, stream, SC, io));                            \
     }                                                                                                     \
   } while (0)
   if (c->cfg.precision == TB_F64) {
@@ -1508,10 +1529,10 @@ static int launch_step(tb_ctx *c, StepIO &io, cudaStream_t stream, bool stage = 
   if (swing) {
     if (c->cfg.precision == TB_F64) {
       if (!c->ff_grid && ff_grid_size<double>(c, &c->ff_grid)) return 1;
-      ff_kernel<double><<<c->ff_grid, kBlock, 0, stream>>>(c->sc64, io);
+      CU(launch_pdl(c->pdl, ff_kernel<double>, c->ff_grid, stream, c->sc64, io));
     } else {
       if (!c->ff_grid && ff_grid_size<float>(c, &c->ff_grid)) return 1;
-      ff_kernel<float><<<c->ff_grid, kBlock, 0, stream>>>(c->sc32, io);
+      CU(launch_pdl(c->pdl, ff_kernel<float>, c->ff_grid, stream, c->sc32, io));
     }
     c->launches++;
     CU(cudaGetLastError());
