@@ -1607,7 +1607,12 @@ int tb_create(const tb_config *cfg, tb_ctx **out) {
   if (e == cudaSuccess && cfg->env_kind == TB_ENV_SWING) e = cudaMalloc(&c->queue, (size_t)cfg->num_envs * sizeof(int));
   if (e == cudaSuccess && cfg->env_kind == TB_ENV_SWING) {
     // every env is pushed to either dynamic queue at most kFfMaxVisits times per launch
-    c->dq_cap = (long long)cfg->num_envs * (kFfMaxVisits + 1) + (1 << 18);  // + a ticket for every lane that may end up waiting
+    {
+      // + a ticket for every lane that may end up waiting: ff_kernel's grid is at most ceil(n / 128) CTAs and never more
+      // than fit the device (<= 2048 CTAs of 128 threads on any sm_100 part)
+      long long ctas = (cfg->num_envs + kBlock - 1) / kBlock;
+      c->dq_cap = (long long)cfg->num_envs * (kFfMaxVisits + 1) + (ctas < 2048 ? ctas : 2048) * kBlock;
+    }
     e = cudaMalloc(&c->dq, (size_t)c->dq_cap * 2 * sizeof(unsigned long long));
   }
   if (e == cudaSuccess && cfg->env_kind == TB_ENV_SWING) e = cudaMalloc(&c->queue_full, (size_t)cfg->num_envs * sizeof(int));
