@@ -122,13 +122,14 @@ struct StepIO {
   unsigned long long *dq_full, *dq_late;  // ff_kernel's dynamic queues (slots tagged with `epoch`): envs parked for a full
                                      // substep; envs whose flight goes on after one.  dq_cap slots each
   long long dq_cap;
-  unsigned *epoch;                   // device word: step counter of the context, never 0: tag of this launch's queue slots
-                                     // (advanced by step_kernel itself, so a captured CUDA graph of steps can be replayed)
+  unsigned *epoch;                   // two device words: [0] steps completed (read by step_kernel, advanced by ff_kernel),
+                                     // [1] = [0] + 1 written by step_kernel = the tag of this step's queue slots
   int prefetch_ahead;                // step_kernel: CTAs resident at a time (the L2 prefetch distance), 0 = none
   unsigned long long *fault;         // sticky: non-zero once a wait inside ff_kernel has timed out (tb_read_stats fails then)
-  unsigned long long *queue_ctr;     // kCtrWords counters (kC* below): [0] front, [1] back entries appended by this
-                                     // step's step_kernel, the rest ff_kernel's
-  unsigned long long *queue_ctr_next;  // the set the NEXT step uses; step_kernel zeroes it
+  unsigned long long *queue_ctrs;    // two sets of kCtrWords counters (kC* below) used by alternate steps: [0] front,
+                                     // [1] back entries appended by the step's step_kernel, the rest ff_kernel's.  Which set
+                                     // a step uses is decided on the device (ctr_sets), so captured CUDA graphs of any
+                                     // number of steps can be replayed
   void *pid;                         // TB_CONTROL_PID: 2 packs x N of controller memory, else nullptr
 };
 
@@ -306,6 +307,12 @@ __device__ __forceinline__ void finish_api(const Scene<T> &sc, const StepIO &io,
 template <typename T, int KIND> struct StepMinBlocks { static constexpr int v = KIND == TB_ENV_SWING ? TB_STEP_SWING_MINB32 : TB_STEP_MINB32; };
 template <int KIND> struct StepMinBlocks<double, KIND> { static constexpr int v = KIND == TB_ENV_SWING ? TB_STEP_SWING_MINB64 : TB_STEP_MINB64; };
 
+// The counter set of the step with index e (= epoch[0] when its step_kernel starts): sets alternate, and every step_kernel
+// zeroes the set of the step after it.  Indices run 0 .. kEpochLast - 1 and wrap (an even period, so the sets keep
+// alternating); tags are index + 1, so no tag is 0, the value of a slot that was never written.
+constexpr unsigned kEpochLast = 0xfffffffeu;
+__device__ __forceinline__ unsigned long long *ctr_set(const StepIO &io, unsigned e) { return io.queue_ctrs + (size_t)(e & 1u) * kCtrWords; }
+
 // Programmatic dependent launch (sm_90+): a kernel launched with the stream-serialisation attribute may be staged on the
 // device while its predecessor drains; it must not touch the predecessor's results before pdl_wait(), which returns once
 // that grid has completed and flushed.  Without the attribute both are no-ops.
@@ -319,8 +326,9 @@ __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.lau
 // with DEFER off - gathered into dense warps there, and with the generic path's registers and rare code kept out of
 // step_kernel.  me: the lane's env (tile0 + lane in step_kernel; tile0 is only used by the STAGE row tiles).
 template <typename T, int KIND, bool STAGE, bool DEFER>
-__device__ __forceinline__ void step_tile(const Scene<T> &sc, const StepIO &io, int64_t tile0, int64_t me, int rows, bool valid, St<T> &s,
-                                          const float *a, WarpStats &ws, int *s_cnt, unsigned long long *s_base, float *s_tile) {
+__device__ __forceinline__ void step_tile(const Scene<T> &sc, const StepIO &io, unsigned long long *qctr, int64_t tile0, int64_t me, int rows,
+                                          bool valid, St<T> &s, const float *a, WarpStats &ws, int *s_cnt, unsigned long long *s_base,
+                                          float *s_tile) {
   constexpr int OD = Dims<KIND>::obs;
   const unsigned full = 0xffffffffu;
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -341,7 +349,7 @@ __device__ __forceinline__ void step_tile(const Scene<T> &sc, const StepIO &io, 
     unsigned dm = __ballot_sync(full, defer);
     if (TB_UNLIKELY(dm)) {
       unsigned long long at = 0;
-      if (lane == 0) at = atomicAdd(io.queue_ctr + kCCtl, (unsigned long long)__popc(dm));
+      if (lane == 0) at = atomicAdd(qctr + kCCtl, (unsigned long long)__popc(dm));
       at = __shfl_sync(full, at, 0);
       if (defer) io.queue_ctl[at + __popc(dm & ((1u << lane) - 1u))] = (int)me;
     }
@@ -407,7 +415,7 @@ __device__ __forceinline__ void step_tile(const Scene<T> &sc, const StepIO &io, 
         s_cnt[k * W + w] = tot;
         tot += a;
       }
-      unsigned long long *ctr = io.queue_ctr + (k == 0 ? kCFront : k == 1 ? kCBack : kCFull0);
+      unsigned long long *ctr = qctr + (k == 0 ? kCFront : k == 1 ? kCBack : kCFull0);
       s_base[k] = tot ? atomicAdd(ctr, (unsigned long long)tot) : 0ULL;
     }
     __syncthreads();
@@ -444,12 +452,12 @@ __global__ void __launch_bounds__(kBlock, StepMinBlocks<T, KIND>::v) step_kernel
   pdl_wait();  // (programmatic dependent launch: this grid may be staged while the previous kernel of the stream drains)
   WarpStats ws;
   ws.init(sacc[wib], lane);
+  const unsigned e = io.epoch[0];  // index of this step; constant while this grid runs (ff_kernel advances it)
+  unsigned long long *qctr = ctr_set(io, e);
   if (blockIdx.x == 0) {
-    for (int i = threadIdx.x; i < kCtrWords; i += kBlock) io.queue_ctr_next[i] = 0;
-    if (threadIdx.x == 0 && io.epoch) {  // the tag of this step's queue slots
-      unsigned e = *io.epoch + 1;
-      *io.epoch = e ? e : 1u;
-    }
+    unsigned long long *next = ctr_set(io, e + 1u);
+    for (int i = threadIdx.x; i < kCtrWords; i += kBlock) next[i] = 0;
+    if (threadIdx.x == 0) io.epoch[1] = e + 1u;  // the tag of this step's queue slots, never 0
   }
 
   const int64_t tile0 = (int64_t)blockIdx.x * kBlock + wib * 32, me = tile0 + lane;
@@ -487,7 +495,7 @@ __global__ void __launch_bounds__(kBlock, StepMinBlocks<T, KIND>::v) step_kernel
     load_state(static_cast<const T *>(io.state), io.n, me, s);
     if (!STAGE) load_action<KIND>(io.actions, me, a);
   }
-  step_tile<T, KIND, STAGE, KIND == TB_ENV_SWING>(sc, io, tile0, me, rows, valid, s, a, ws, s_cnt, s_base, s_tile);
+  step_tile<T, KIND, STAGE, KIND == TB_ENV_SWING>(sc, io, qctr, tile0, me, rows, valid, s, a, ws, s_cnt, s_base, s_tile);
   ws.flush(io.stats);
   pdl_trigger();
 }
@@ -560,6 +568,7 @@ __device__ __forceinline__ unsigned long long global_ns() {
   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
   return t;
 }
+
 
 // warp-aggregated reservation of slots in a dynamic queue + tagged publication of `me` (for lanes with pred).  The
 // env's state must have been stored before the call.
@@ -658,7 +667,7 @@ __device__ __forceinline__ void ff_flight_warp(const Scene<T> &sc, const StepIO 
                                                long long total, int lane, int &nsub) {
   const unsigned full = 0xffffffffu;
   T *base = static_cast<T *>(io.state);
-  unsigned long long *ctr = io.queue_ctr;
+  unsigned long long *ctr = ctr_set(io, epoch - 1u);
   FfLane<T> L;
   {  // defined values for lanes that never get an env (ff_fast is never run on them)
     T *z = reinterpret_cast<T *>(&L);
@@ -808,7 +817,7 @@ __device__ __noinline__ void ff_server_warp(const Scene<T> &sc, const StepIO &io
                                             int *nsub) {
   const unsigned full = 0xffffffffu;
   T *base = static_cast<T *>(io.state);
-  unsigned long long *ctr = io.queue_ctr;
+  unsigned long long *ctr = ctr_set(io, epoch - 1u);
   bool exhausted0 = nfull0 == 0, busy = false, to_end = false, waiting = false;
   long long idle_since = 0, ticket = 0;
   unsigned nap = 0;
@@ -978,8 +987,8 @@ __device__ __noinline__ void ff_phase_finish(const Scene<T> &sc, const StepIO &i
 
 // ff_kernel's prologue for one CTA (out of line: the generic step's registers and spills stay out of the flight loop)
 template <typename T>
-__device__ __noinline__ void ff_prologue(const Scene<T> &sc, const StepIO &io, long long nctl, WarpStats *wsp, int *s_cnt,
-                                         unsigned long long *s_base, float *s_dummy) {
+__device__ __noinline__ void ff_prologue(const Scene<T> &sc, const StepIO &io, unsigned long long *ctr, long long nctl, WarpStats *wsp,
+                                         int *s_cnt, unsigned long long *s_base, float *s_dummy) {
   for (long long b0 = (long long)blockIdx.x * kBlock; b0 < nctl; b0 += (long long)gridDim.x * kBlock) {
     const long long idx = b0 + threadIdx.x;
     const bool valid = idx < nctl;
@@ -990,7 +999,7 @@ __device__ __noinline__ void ff_prologue(const Scene<T> &sc, const StepIO &io, l
       load_state(static_cast<const T *>(io.state), io.n, me, s);
       load_action<TB_ENV_SWING>(io.actions, me, a);
     }
-    step_tile<T, TB_ENV_SWING, false, false>(sc, io, 0, me, 0, valid, s, a, *wsp, s_cnt, s_base, s_dummy);
+    step_tile<T, TB_ENV_SWING, false, false>(sc, io, ctr, 0, me, 0, valid, s, a, *wsp, s_cnt, s_base, s_dummy);
   }
 }
 
@@ -1001,8 +1010,10 @@ __global__ void __launch_bounds__(kBlock, MinBlocks<T>::v) ff_kernel(const __gri
   __shared__ unsigned long long s_base[3];
   __shared__ float s_dummy[4];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  unsigned long long *ctr = io.queue_ctr;
   pdl_wait();
+  const unsigned epoch = io.epoch[1];  // this step's tag, written by its step_kernel; the step's index is epoch - 1
+  if (blockIdx.x == 0 && threadIdx.x == 0) io.epoch[0] = epoch == kEpochLast ? 0u : epoch;  // (read by the next step_kernel only)
+  unsigned long long *ctr = ctr_set(io, epoch - 1u);
   const long long nctl = (long long)ctr[kCCtl];  // (written by step_kernel, same stream)
   if (nctl == 0 && ctr[kCFront] + ctr[kCBack] + ctr[kCFull0] == 0) return;
   WarpStats ws;
@@ -1011,7 +1022,7 @@ __global__ void __launch_bounds__(kBlock, MinBlocks<T>::v) ff_kernel(const __gri
   //      gathered into dense warps and taken through the generic path; those that were an env's 26th step join the
   //      queues below, hence the grid barrier
   if (nctl) {
-    ff_prologue<T>(sc, io, nctl, &ws, s_cnt, s_base, s_dummy);
+    ff_prologue<T>(sc, io, ctr, nctl, &ws, s_cnt, s_base, s_dummy);
     if (!grid_barrier(ctr)) {
       if (threadIdx.x == 0) atomicExch(io.fault, 6ULL);
       ws.flush(io.stats);
@@ -1026,7 +1037,6 @@ __global__ void __launch_bounds__(kBlock, MinBlocks<T>::v) ff_kernel(const __gri
   const bool diag = blockIdx.x == 0 && threadIdx.x == 0;  // times as this CTA's first warp sees them
   unsigned long long t_mark = diag ? global_ns() : 0;
   const bool server = wib == kBlock / 32 - 1 && blockIdx.x % kServerStride == 0;
-  const unsigned epoch = *io.epoch;  // advanced by this step's step_kernel
   if (server) ff_server_warp<T>(sc, io, epoch, nfull0, total, lane, &nsub);
   else ff_flight_warp<T>(sc, io, epoch, qn0, qfront, total, lane, nsub);
   if (diag) {
@@ -1404,7 +1414,6 @@ struct tb_ctx {
   unsigned *epoch = nullptr;                 // device word, see StepIO
   unsigned long long *fault = nullptr;       // device word, see StepIO
   unsigned long long *queue_ctrs = nullptr;  // two counter sets (kCtrWords each) used by alternate steps
-  int parity = 0;
   unsigned ff_grid = 0;                      // persistent grid of ff_kernel
   int step_resident = -1;                    // resident CTAs of step_kernel (its L2 prefetch distance)
   bool pdl = std::getenv("TB_NO_PDL") == nullptr;  // programmatic dependent launch of the step's kernels
@@ -1499,9 +1508,7 @@ static int launch_step(tb_ctx *c, StepIO &io, cudaStream_t stream, bool stage = 
   io.fault = c->fault;
   io.dq_full = c->dq; io.dq_late = c->dq ? c->dq + c->dq_cap : nullptr; io.dq_cap = c->dq_cap;
   io.epoch = c->epoch;  // (a slot written 2^32 steps ago with the same tag would have to survive untouched)
-  io.queue_ctr = c->queue_ctrs + kCtrWords * c->parity;
-  io.queue_ctr_next = c->queue_ctrs + kCtrWords * (c->parity ^ 1);
-  c->parity ^= 1;
+  io.queue_ctrs = c->queue_ctrs;
   const unsigned grid = grid_for(io.n, kBlock);
   const bool swing = c->cfg.env_kind == TB_ENV_SWING;
   if (c->timing) CU(cudaEventRecord(c->ev[0], stream));
@@ -1623,8 +1630,8 @@ int tb_create(const tb_config *cfg, tb_ctx **out) {
   if (e == cudaSuccess) e = cudaMemsetAsync(c->queue_ctrs, 0, 2 * kCtrWords * sizeof(unsigned long long), c->own_stream);
   if (e == cudaSuccess) e = cudaMalloc(&c->fault, sizeof(unsigned long long));
   if (e == cudaSuccess) e = cudaMemsetAsync(c->fault, 0, sizeof(unsigned long long), c->own_stream);
-  if (e == cudaSuccess) e = cudaMalloc(&c->epoch, sizeof(unsigned));
-  if (e == cudaSuccess) e = cudaMemsetAsync(c->epoch, 0, sizeof(unsigned), c->own_stream);
+  if (e == cudaSuccess) e = cudaMalloc(&c->epoch, 2 * sizeof(unsigned));
+  if (e == cudaSuccess) e = cudaMemsetAsync(c->epoch, 0, 2 * sizeof(unsigned), c->own_stream);
   if (e == cudaSuccess && c->dq) e = cudaMemsetAsync(c->dq, 0, (size_t)c->dq_cap * 2 * sizeof(unsigned long long), c->own_stream);  // tag 0 = no epoch
   if (e == cudaSuccess) {
     // identity quaternion, episode = -1 so the first reset starts episode 0

@@ -113,7 +113,7 @@ class SwingPPO:
                 self.env.read_stats(clear=True)
                 self.graph = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(self.graph):
-                    self._rollout_body()  # an even number of env steps: the library alternates two counter sets per step
+                    self._rollout_body()
                 torch.cuda.synchronize()
                 t0 = time.time()
             self.graph.replay()

@@ -44,6 +44,44 @@ def test_env_steps_replay_in_a_cuda_graph():
     np.testing.assert_array_equal(state_g, state_e)
 
 
+def test_odd_number_of_steps_per_graph_replays():
+    """A graph holding an ODD number of env steps (the library alternates two counter sets per step; which one a step
+    uses is decided on the device) replayed across episode ends equals the same steps issued eagerly."""
+    from tennisbot_rl_b200.batch import TennisBatch
+
+    n, k, replays = 4096, 13, 6  # 13 steps per graph: every second replay contains the 26th step's fast-forward
+    acts = torch.empty((k, n, 6), device="cuda").uniform_(-1, 1, generator=torch.Generator("cuda").manual_seed(5))
+
+    def run(graph):
+        b = TennisBatch("SwingRacket-v0", n, seed=11)
+        b.reset()
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for t in range(k):
+                b.step(acts[t])
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        if graph:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                for t in range(k):
+                    b.step(acts[t])
+            for _ in range(replays):
+                g.replay()
+        else:
+            for _ in range(replays):
+                for t in range(k):
+                    b.step(acts[t])
+        torch.cuda.synchronize()
+        return b.read_stats(), b.get_state().cpu().numpy()
+
+    st_g, state_g = run(True)
+    st_e, state_e = run(False)
+    assert st_g[0] > 0 and (st_g == st_e).all(), (st_g, st_e)
+    np.testing.assert_array_equal(state_g, state_e)
+
+
 def test_ppo_learns_on_the_gpu_env():
     from tennisbot_rl_b200.ppo import SwingPPO
 
