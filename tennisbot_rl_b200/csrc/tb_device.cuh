@@ -784,6 +784,8 @@ template <typename T> __device__ __forceinline__ void pid_force(const Scene<T> &
 //   phase 0: the substep driven by the action (swingracket_env.py:76-83)
 //   phase 1: first fast-forward substep, no external force (the step above cleared them) (:105-107)
 //   phase 2: later fast-forward substeps, driven by the "hack" force queued after the previous one (:135-141)
+template <typename T> __device__ __forceinline__ int hit_physics(const Scene<T> &sc, St<T> &s, const T *F, const T *Fb);  // below
+
 struct StepCtl {
   int phase, events, hit;
   float reward;
@@ -837,7 +839,11 @@ __device__ __forceinline__ bool env_substep(const Scene<T> &sc, St<T> &s, const 
     }
     T Fb[3] = {0, 0, 0};
     if (s.step < 5) { Fb[0] = s.aux[0]; Fb[1] = s.aux[1]; Fb[2] = s.aux[2]; }
+#ifdef TB_HIT_GENERIC  // (A/B builds only: the generic step in line, as before hit_fast existed)
     int bits = physics_step<T, false>(sc, s, F, zero, Fb);
+#else
+    int bits = hit_physics<T>(sc, s, F, Fb);
+#endif
     int k = ++s.step;
     c.events = bits;
     if (k < 5) { c.done = false; return true; }  // returns False regardless of self.done (tennisbot_env.py:138-139)
@@ -1071,7 +1077,7 @@ constexpr int kFfDone = 3;  // (returned by the step functions) the env step is 
 // Conservative (a lane may be sent to ff_full for nothing, never the other way), and decided by the env's own state
 // only, so which path integrates a given substep never depends on the other lanes of the warp.
 // nb, nr, nw: squared speeds of ball, racket and racket spin.
-template <typename T>
+template <typename T, bool WITH_GOAL = true>
 __device__ __forceinline__ int ff_classify_core(const Scene<T> &sc, const T *rp, const T *rq, const T *bp, const T *goal, T nb, T nr,
                                                 T nw, int step) {
   const T x = rq[0], y = rq[1], z = rq[2], w = rq[3];
@@ -1097,10 +1103,12 @@ __device__ __forceinline__ int ff_classify_core(const Scene<T> &sc, const T *rp,
     }
   }
   const T ax = M<T>::abs(bp[0]), ay = M<T>::abs(bp[1]), az = M<T>::abs(bp[2]);
-  T gx = bp[0] - goal[0], gy = bp[1] - goal[1];
   bool full = racket | (!(ax > sc.ffp_net[0]) & !(az > sc.ffp_net[2]) & !(ay > sc.ffp_net[1])) |
-              (!(az > sc.ffp_goal_z) & !(gx * gx + gy * gy > sc.ffp_goal_r2)) |
-              !(nb < sc.ffp_v2) | !(nr < sc.ffp_v2) | !(nw < sc.ffp_a2) | (step >= 800);
+              !(nb < sc.ffp_v2) | !(nr < sc.ffp_v2) | !(nw < sc.ffp_a2);
+  if (WITH_GOAL) {  // SwingRacket: the goal disc and the 800-step time-out (Tennisbot-v0 has neither in its scene)
+    T gx = bp[0] - goal[0], gy = bp[1] - goal[1];
+    full |= (!(az > sc.ffp_goal_z) & !(gx * gx + gy * gy > sc.ffp_goal_r2)) | (step >= 800);
+  }
   bool floor = !(az > sc.ffp_floor[2]) & !(ax > sc.ffp_floor[0]) & !(ay > sc.ffp_floor[1]);
   bool face = (bp[2] > sc.ffp_face[2]) & (ax < sc.ffp_face[0]) & (ay < sc.ffp_face[1]);
   return (full | (floor & !face)) ? kFfFull : (floor ? kFfLand : kFfFree);
@@ -1169,6 +1177,150 @@ template <typename T> __device__ __forceinline__ int ctl_fast(const Scene<T> &sc
     T inv = (T)1.5 - (T)0.5 * n2;  // first-order renormalisation, see integrate_quat
     if (TB_UNLIKELY(M<T>::abs(n2 - 1) > (T)1e-4)) inv = fast_rsqrt(n2);
     s.rq[0] = x * inv; s.rq[1] = y * inv; s.rq[2] = z * inv; s.rq[3] = w * inv;
+  }
+  return bits;
+}
+
+// Tennisbot-v0's substep (tennisbot_env.py:112-121) for a state ff_classify_core<T, false> does not send to the generic
+// path: physics_step<T, false> without detection, solve and clamps, as one straight line - planar force on the racket
+// at the COM (racket.py:92-100), the shoot force on the ball during the first frames (objects.py:67-72), damping as one
+// factor per body, and the one contact that is routine in this env, the ball's bounce on the court's top face
+// (kind == kFfLand), in closed form exactly as in ff_fast below.  The racket only rotates after a ball has hit it
+// (no torque is ever applied): that case runs Euler's equations in the body frame like ctl_fast.  Equal to
+// physics_step in exact arithmetic, to ~1e-16 per substep in floating point.  Returns the event bits of the substep
+// (TB_EV_RACKET_LOW, TB_EV_COURT_BALL).
+template <typename T> __device__ __forceinline__ int hit_fast(const Scene<T> &sc, St<T> &s, const T *F, const T *Fb, int kind) {
+  const T dt = sc.dt;
+  int bits;
+  {  // TB_EV_RACKET_LOW at the start-of-step pose, exact test as in physics_step
+    const T x = s.rq[0], y = s.rq[1], z = s.rq[2], w = s.rq[3];
+    T r6 = 2 * (x * z - y * w), r7 = 2 * (y * z + x * w), r8 = 1 - 2 * (x * x + y * y);
+    T zlo = r8 * sc.racket_obb[1], zhi = r8 * sc.racket_obb[2];
+    T low = s.rp[2] - M<T>::abs(r6) * sc.racket.half_thick - M<T>::abs(r7) * sc.racket_obb[0] + (zlo < zhi ? zlo : zhi) - sc.hull_margin;
+    bool is_low = (low <= sc.ffp_low) & (M<T>::abs(s.rp[0]) <= sc.ffp_court[0]) & (M<T>::abs(s.rp[1]) <= sc.ffp_court[1]);
+    bits = is_low ? TB_EV_RACKET_LOW : 0;
+  }
+  // signed distance of the ball to the court's top face at the start-of-step pose (box_distance's face case)
+  const T d_floor = (s.bp[2] - (sc.floor_h[2] - sc.box_margin)) - (sc.ball_r + sc.box_margin);
+  const T dtb = dt * sc.ball_inv_m, dtm = dt * sc.racket_inv_m;
+  T fb = 1 - sc.ff_kl * (1 + M<T>::norm_damp(dot3(s.bv, s.bv)));
+  s.bv[0] = s.bv[0] * fb + dtb * Fb[0]; s.bv[1] = s.bv[1] * fb + dtb * Fb[1]; s.bv[2] = s.bv[2] * fb + (dtb * Fb[2] + sc.ff_dtg);
+  T fs = 1 - sc.ff_ka * (1 + M<T>::norm_damp(dot3(s.bw, s.bw)));
+  s.bw[0] *= fs; s.bw[1] *= fs; s.bw[2] *= fs;
+  T fr = 1 - sc.ff_kl * (1 + M<T>::norm_damp(dot3(s.rv, s.rv)));
+  s.rv[0] = s.rv[0] * fr + dtm * F[0]; s.rv[1] = s.rv[1] * fr + dtm * F[1]; s.rv[2] = s.rv[2] * fr + (dtm * F[2] + sc.ff_dtg);
+  const bool rotating = (s.rw[0] != 0) | (s.rw[1] != 0) | (s.rw[2] != 0);
+  T wl[3] = {0, 0, 0};
+  if (TB_UNLIKELY(rotating)) {
+    T R[9];
+    quat_to_mat(s.rq, R);
+    T fw = 1 - sc.ff_ka * (1 + M<T>::norm_damp(dot3(s.rw, s.rw)));  // |omega| is the same in both frames
+    matT_vec(R, s.rw, wl);
+    T p12 = wl[1] * wl[2], p20 = wl[2] * wl[0], p01 = wl[0] * wl[1];
+    wl[0] = wl[0] * fw - sc.ff_gyro[0] * p12;
+    wl[1] = wl[1] * fw - sc.ff_gyro[1] * p20;
+    wl[2] = wl[2] * fw - sc.ff_gyro[2] * p01;
+    mat_vec(R, wl, s.rw);
+  }
+  if (TB_UNLIKELY(kind == kFfLand && d_floor <= sc.contact_threshold)) {  // the bounce: see ff_fast
+    bits |= TB_EV_COURT_BALL;
+    const T rb = sc.ball_r, inv_m = sc.ball_inv_m, inv_i = sc.ball_inv_i;
+    T rel = s.bv[2];
+    T e = M<T>::abs(rel) < sc.rest_vel_threshold ? (T)0 : -sc.rest_court * rel;
+    if (e < 0) e = 0;
+    T pen = d_floor + sc.slop, vel_err = e - rel, pos_err = 0;
+    if (pen > 0) vel_err -= pen * sc.ffl_inv_dt;
+    else pos_err = -pen * sc.ffl_erp_dt;
+    T lam_n = (pos_err + vel_err) * sc.ffl_m;
+    if (lam_n > 0) {
+      s.bv[2] += lam_n * inv_m;
+      T s1 = (s.bv[1] + rb * s.bw[0]) * sc.ffl_jinv_t, s2 = -(s.bv[0] - rb * s.bw[1]) * sc.ffl_jinv_t;
+      T lim = sc.mu_court * lam_n, m2 = s1 * s1 + s2 * s2;
+      if (m2 > lim * lim) {
+        T y = (T)rsqrtf((float)m2);  // float estimate + two Newton steps: ~1e-15 relative
+        y = y * ((T)1.5 - (T)0.5 * m2 * y * y);
+        y = y * ((T)1.5 - (T)0.5 * m2 * y * y);
+        T sf = lim * y;
+        s1 *= sf; s2 *= sf;
+      }
+      s.bv[1] -= s1 * inv_m; s.bw[0] -= rb * s1 * inv_i;
+      s.bv[0] += s2 * inv_m; s.bw[1] -= rb * s2 * inv_i;
+      const T vmax = sc.max_coord_vel;  // the clamp physics_step applies after a solve
+#pragma unroll
+      for (int i = 0; i < 3; ++i) { s.bv[i] = clampv(s.bv[i], -vmax, vmax); s.bw[i] = clampv(s.bw[i], -vmax, vmax); }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    s.bp[i] += dt * s.bv[i];
+    s.rp[i] += dt * s.rv[i];
+  }
+  if (TB_UNLIKELY(rotating)) {
+    T sinc, cw;
+    sinc_cos_short(sc.ff_qx2 * dot3(wl, wl), &sinc, &cw);
+    T k = (T)0.5 * dt * sinc;
+    T ax = wl[0] * k, ay = wl[1] * k, az = wl[2] * k;
+    const T q0 = s.rq[0], q1 = s.rq[1], q2 = s.rq[2], q3 = s.rq[3];
+    T x = cw * q0 + ax * q3 + az * q1 - ay * q2;
+    T y = cw * q1 + ay * q3 + ax * q2 - az * q0;
+    T z = cw * q2 + az * q3 + ay * q0 - ax * q1;
+    T w = cw * q3 - ax * q0 - ay * q1 - az * q2;
+    T n2 = x * x + y * y + z * z + w * w;
+    T inv = (T)1.5 - (T)0.5 * n2;  // first-order renormalisation, see integrate_quat
+    if (TB_UNLIKELY(M<T>::abs(n2 - 1) > (T)1e-4)) inv = fast_rsqrt(n2);
+    s.rq[0] = x * inv; s.rq[1] = y * inv; s.rq[2] = z * inv; s.rq[3] = w * inv;
+  }
+  return bits;
+}
+// The generic substep of Tennisbot-v0, out of line (ball within reach of the racket, the net or an edge of the floor; a
+// speed near the clamp): data crosses through *r only, so the caller's state stays in registers around the call.
+template <typename T> struct HitRec {
+  T rp[3], rq[4], rv[3], rw[3], bp[3], bv[3], bw[3], F[3], Fb[3];
+};
+template <typename T> __device__ __noinline__ int hit_generic(const Scene<T> &sc, HitRec<T> *r) {
+  St<T> s;
+  T zero[3] = {0, 0, 0}, F[3], Fb[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    s.rp[i] = r->rp[i]; s.rv[i] = r->rv[i]; s.rw[i] = r->rw[i]; s.bp[i] = r->bp[i]; s.bv[i] = r->bv[i]; s.bw[i] = r->bw[i];
+    F[i] = r->F[i]; Fb[i] = r->Fb[i];
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) s.rq[i] = r->rq[i];
+  int bits = physics_step<T, false>(sc, s, F, zero, Fb);
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    r->rp[i] = s.rp[i]; r->rv[i] = s.rv[i]; r->rw[i] = s.rw[i]; r->bp[i] = s.bp[i]; r->bv[i] = s.bv[i]; r->bw[i] = s.bw[i];
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) r->rq[i] = s.rq[i];
+  return bits;
+}
+
+// One stepSimulation() of Tennisbot-v0 with racket force F and ball force Fb: contact-free substeps and bounces on the
+// court's top face take the straight line, everything else the generic step out of line (a few substeps per episode:
+// ball within reach of the racket, the net or a floor edge).  Returns the event bits.
+template <typename T> __device__ __forceinline__ int hit_physics(const Scene<T> &sc, St<T> &s, const T *F, const T *Fb) {
+  int bits;
+  const int kind = ff_classify_core<T, false>(sc, s.rp, s.rq, s.bp, s.goal, dot3(s.bv, s.bv), dot3(s.rv, s.rv), dot3(s.rw, s.rw), 0);
+  if (kind != kFfFull) {
+    bits = hit_fast<T>(sc, s, F, Fb, kind);
+  } else {
+    HitRec<T> r;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      r.rp[i] = s.rp[i]; r.rv[i] = s.rv[i]; r.rw[i] = s.rw[i]; r.bp[i] = s.bp[i]; r.bv[i] = s.bv[i]; r.bw[i] = s.bw[i];
+      r.F[i] = F[i]; r.Fb[i] = Fb[i];
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) r.rq[i] = s.rq[i];
+    bits = hit_generic<T>(sc, &r);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      s.rp[i] = r.rp[i]; s.rv[i] = r.rv[i]; s.rw[i] = r.rw[i]; s.bp[i] = r.bp[i]; s.bv[i] = r.bv[i]; s.bw[i] = r.bw[i];
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) s.rq[i] = r.rq[i];
   }
   return bits;
 }

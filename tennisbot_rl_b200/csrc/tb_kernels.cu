@@ -436,8 +436,11 @@ __device__ __forceinline__ void step_tile(const Scene<T> &sc, const StepIO &io, 
 
 // STAGE: move the action / observation rows through warp-private shared-memory tiles (see below); chosen by the host
 // when the caller's buffers are pinned host memory, off for buffers in HBM where it only costs registers.
-template <typename T, int KIND, bool STAGE>
-__global__ void __launch_bounds__(kBlock, StepMinBlocks<T, KIND>::v) step_kernel(const __grid_constant__ Scene<T> sc, const __grid_constant__ StepIO io) {
+// MINB: CTAs per SM the registers are capped for, 0 = StepMinBlocks (the fastest build for grids of many waves).  The host
+// picks MINB = 4 (128 registers, some spills) for Tennisbot-v0 grids that fit the SMs in ONE wave at 4 CTAs per SM but
+// not at the default 3 - 65 536 envs = 512 CTAs on 148 SMs is such a size: no second, nearly empty wave.
+template <typename T, int KIND, bool STAGE, int MINB = 0>
+__global__ void __launch_bounds__(kBlock, MINB ? MINB : StepMinBlocks<T, KIND>::v) step_kernel(const __grid_constant__ Scene<T> sc, const __grid_constant__ StepIO io) {
   __shared__ unsigned long long sacc[kBlock / 32][TB_NUM_STATS];
   __shared__ int s_cnt[3 * (kBlock / 32)];
   __shared__ unsigned long long s_base[3];
@@ -1416,6 +1419,7 @@ struct tb_ctx {
   unsigned long long *queue_ctrs = nullptr;  // two counter sets (kCtrWords each) used by alternate steps
   unsigned ff_grid = 0;                      // persistent grid of ff_kernel
   int step_resident = -1;                    // resident CTAs of step_kernel (its L2 prefetch distance)
+  bool one_wave4 = false;                    // Tennisbot-v0: launch the 4-CTAs-per-SM build of step_kernel (see its MINB)
   bool pdl = std::getenv("TB_NO_PDL") == nullptr;  // programmatic dependent launch of the step's kernels
   int control_mode = TB_CONTROL_FORCE;
   void *pid = nullptr;                       // controller memory, allocated by tb_set_control_mode(TB_CONTROL_PID)
@@ -1490,6 +1494,12 @@ template <typename T, int KIND> static int step_resident_ctas(tb_ctx *c) {
   CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, step_kernel<T, KIND, false>, kBlock, 0));
   CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->cfg.device));
   c->step_resident = std::getenv("TB_NO_PREFETCH") ? 0 : sms * (per_sm > 0 ? per_sm : 1);
+  if (KIND == TB_ENV_HIT) {  // see step_kernel's MINB
+    int per_sm4 = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm4, step_kernel<T, TB_ENV_HIT, false, 4>, kBlock, 0));
+    const int64_t grid = (c->cfg.num_envs + kBlock - 1) / kBlock;
+    c->one_wave4 = per_sm4 > per_sm && grid > (int64_t)sms * per_sm && grid <= (int64_t)sms * per_sm4;
+  }
   return 0;
 }
 template <typename... KArgs, typename... Args>
@@ -1519,7 +1529,12 @@ static int launch_step(tb_ctx *c, StepIO &io, cudaStream_t stream, bool stage = 
     } else {                                                                                              \
       if (c->step_resident < 0 && step_resident_ctas<T, K>(c)) return 1;                                  \
       io.prefetch_ahead = c->step_resident;                                                               \
-      CU(launch_pdl(c->pdl, step_kernel<T, K, false>, grid, stream, SC, io));                            \
+      if (K == TB_ENV_HIT && c->one_wave4) {                                                              \
+        io.prefetch_ahead = 0;                                                                            \
+        CU(launch_pdl(c->pdl, step_kernel<T, TB_ENV_HIT, false, 4>, grid, stream, SC, io));               \
+      } else {                                                                                            \
+        CU(launch_pdl(c->pdl, step_kernel<T, K, false>, grid, stream, SC, io));                          \
+      }                                                                                                   \
     }                                                                                                     \
   } while (0)
   if (c->cfg.precision == TB_F64) {
