@@ -146,6 +146,42 @@ def test_f64_parity_hit_env_tracking_policy(oracle_lib):
     assert st[0] > 0 and st[2] > 0.05 * st[0]  # several times the hit rate of random actions (the racket cannot choose its height)
 
 
+@pytest.mark.parametrize("params,tol_state,tol_out", [
+    ({"racket_scale": 2.5}, TOL_F64_STATE, TOL_F64_OUT),
+    ({"lin_damping": 0.0, "ang_damping": 0.0}, TOL_F64_STATE, TOL_F64_OUT),
+    # balls come to rest and roll on the court here: hundreds of consecutive contact steps, each turning position
+    # rounding into velocity at 1/dt = 240.  Measured 3.2e-6 (3.8e-6 with the generic step in line, -DTB_HIT_GENERIC):
+    # the amplification is the contact model's, not the straight line's, hence the wider bar for this scene only
+    ({"gravity_z": -25.0, "racket_scale": 1.6}, 2e-5, 2e-5)])
+def test_f64_parity_hit_env_paths(oracle_lib, params, tol_state, tol_out):
+    """Scenes that push Tennisbot-v0 through every branch of its substep (hit_fast / the generic step out of line): a
+    larger racket steered at the ball (many contacts, then a spinning racket on the straight line for the rest of the
+    episode), no damping (fast balls: net and floor-edge contacts, balls leaving the court), strong gravity (many
+    bounces per episode on the closed-form floor contact).  Same bars as the random-action test."""
+    n = 4096
+    b, o = _make("Tennisbot-v0", n, "f64", 37, oracle_lib)
+    for k, v in params.items():
+        b.set_param(k, v)
+        o.set_param(k, v)
+    obs0 = o.reset()
+    np.testing.assert_array_equal(b.reset().cpu().numpy(), obs0)
+    rng = np.random.default_rng(3)
+
+    def policy(t, obs):
+        a = np.zeros((n, 2))
+        a[:, 0] = rng.uniform(-0.5, 0.5, n)
+        a[:, 1] = np.clip(4.0 * (obs[:, 7] - obs[:, 1]) - 1.5 * obs[:, 4], -1, 1)
+        return a
+
+    rep, valid = run_parity(b, o, 700, policy, band=0.0, check_state_every=50, obs0=obs0)
+    st = b.read_stats()
+    print(rep, st.tolist())
+    assert rep.event_mismatch_hard == 0 and rep.event_mismatch_near == 0
+    assert rep.max_state_err < tol_state and rep.max_obs_err < tol_out and rep.max_reward_err < tol_out
+    np.testing.assert_array_equal(st, o.read_stats())
+    assert st[0] > 0
+
+
 @pytest.mark.parametrize("env,steps", [("SwingRacket-v0", 52), ("Tennisbot-v0", 700)])
 def test_f32_parity_with_band(oracle_lib, env, steps):
     """float32 path: every contact / done decision equals the oracle's unless the oracle's own margin to the
