@@ -109,9 +109,10 @@ def measured_traffic(env, precision, n):
     """DRAM bytes of one env step of the whole batch (dram__bytes_read.sum + dram__bytes_write.sum of a step_kernel launch
     + 1/26 of a fast-forward ff_kernel launch) from the committed ncu captures of the same workload, else None."""
     p = ROOT / "profiles" / "r1_traffic.json"
-    if env == "SwingRacket-v0" and precision == "f64" and n == 1 << 20 and p.exists():
+    key = {"SwingRacket-v0": "dram_bytes_per_env_step_launch_pair", "Tennisbot-v0": "hit_step_kernel_dram_bytes_per_launch"}[env]
+    if precision == "f64" and n == 1 << 20 and p.exists():
         try:
-            return float(json.loads(p.read_text())["dram_bytes_per_env_step_launch_pair"])
+            return float(json.loads(p.read_text())[key])
         except Exception:
             pass
     return None

@@ -12,3 +12,8 @@ ncu --set full --clock-control none --import-source on -k regex:ff_kernel -s 25 
 ncu --set full --clock-control none --import-source on -k regex:step_kernel -s 10 -c 1 -o gpurun_out/prof_${R}_step_f64 \
     python tools/prof_swing.py f64 1048576 > gpurun_out/ncu_step_$R.log 2>&1
 tail -n 2 gpurun_out/ncu_ff_$R.log gpurun_out/ncu_step_$R.log
+# Tennisbot-v0: one step_kernel launch once the episodes have desynchronised (1 Mi envs, f64)
+python tools/prof_swing.py f64 1048576 Tennisbot-v0 1300 > gpurun_out/plain_hit_f64_$R.log 2>&1 &&
+ncu --set full --clock-control none --import-source on -k regex:step_kernel -s 1250 -c 1 -o gpurun_out/prof_${R}_hit_step_f64 \
+    python tools/prof_swing.py f64 1048576 Tennisbot-v0 1300 > gpurun_out/ncu_hit_$R.log 2>&1
+tail -n 2 gpurun_out/ncu_hit_$R.log
