@@ -928,10 +928,19 @@ __device__ __noinline__ void ff_server_warp(const Scene<T> &sc, const StepIO &io
       }
     }
 #ifdef TB_FF_DIAG
-    if (__any_sync(full, busy || leave) && lane == 0) {
-      atomicAdd(ctr + kDPhase + 9, 1ULL);
-      atomicAdd(ctr + kDPhase + 10, (unsigned long long)(clock64() - tb0));
-      atomicMax(ctr + kDPhase + 11, global_ns());
+    {
+      const unsigned bm = __ballot_sync(full, busy || leave);
+      if (bm && lane == 0) {
+        const unsigned long long dtc = (unsigned long long)(clock64() - tb0), tn = global_ns();
+        atomicAdd(ctr + kDPhase + 9, 1ULL);
+        atomicAdd(ctr + kDPhase + 10, dtc);
+        atomicMax(ctr + kDPhase + 11, tn);
+        // iteration time by the number of lanes that took a substep (1, 2, 3-4, 5-8, 9-16, 17-32): words 112.. for
+        // the whole launch, 80.. for iterations later than 1.5 ms into it
+        const int nb = __popc(bm), bin = nb <= 1 ? 0 : 32 - __clz(nb - 1);
+        atomicAdd(ctr + 112 + 2 * bin, 1ULL); atomicAdd(ctr + 113 + 2 * bin, dtc);
+        if (tn - ts0 > 1500000ULL) { atomicAdd(ctr + 80 + 2 * bin, 1ULL); atomicAdd(ctr + 81 + 2 * bin, dtc); }
+      }
     }
 #endif
     dq_push(io.dq_late, io.dq_cap, ctr + kCLateTail, epoch, leave && r != kFfDone, me, lane, ctr + kCError);
@@ -1890,6 +1899,11 @@ int tb_ff_diagnostics(tb_ctx *c, int64_t *h_out) {
     CU(cudaMemcpy(&fault, c->fault, sizeof fault, cudaMemcpyDeviceToHost));
     if (fault) h_out[15] = (int64_t)fault;
   }
+  if (std::getenv("TB_FF_DIAG_DUMP"))
+    for (int b = 0; b < 6; ++b)
+      std::fprintf(stderr, "server iterations with %d..%d lanes: %llu, mean %llu cycles; after 1.5 ms: %llu, mean %llu cycles\n", b ? (1 << (b - 1)) + 1 : 1,
+                   1 << b, s[112 + 2 * b], s[112 + 2 * b] ? s[113 + 2 * b] / s[112 + 2 * b] : 0ULL, s[80 + 2 * b],
+                   s[80 + 2 * b] ? s[81 + 2 * b] / s[80 + 2 * b] : 0ULL);
   if (std::getenv("TB_FF_DIAG_DUMP"))
     for (int b = 0; b < 76 && s[128 + 5 * b]; ++b)
       std::fprintf(stderr, "t=%.1fms landed %llu fullq %llu/%llu lateq %llu/%llu\n", 0.5 * b, s[128 + 5 * b] - 1, s[130 + 5 * b], s[129 + 5 * b],
