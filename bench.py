@@ -183,7 +183,7 @@ def run_reference(args, rank):
                                    f"{run.o.physics_steps()} physics substeps incl. warm-up"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ---------------------------------------------------------------------------------------------- B200 arm
@@ -360,17 +360,33 @@ def run_b200(args, rank, world):
             line["cpu_baseline"] = {"value": total / t_cpu, "unit": UNIT, "cores": cores, "kind": "port",
                                     "sample": f"{cpu_n} envs x {EPISODE_STEPS} env steps x {reps} episodes on {cores} threads "
                                               f"({t_cpu:.1f} s); restated CPU oracle, not PyBullet (absent from the image)"}
-        print(json.dumps(line), flush=True)
+        emit(line)
     batch.close()
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """The ONE JSON line of the contract, on the process's original stdout."""
+    out = _REAL_STDOUT if _REAL_STDOUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    global _REAL_STDOUT
     args = parse()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
+    # libraries write to fd 1 behind Python's back (NCCL prints its version banner there when NCCL_DEBUG is set on the
+    # box): keep the original stdout for the JSON line and send everything else to stderr
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args, rank)
         return
@@ -378,7 +394,7 @@ def main():
         # launched without torchrun: re-exec under torch.distributed.run
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
                "--master-addr", "127.0.0.1", "--master-port", os.environ.get("MASTER_PORT", "29517"), __file__] + sys.argv[1:]
-        sys.exit(subprocess.call(cmd))
+        sys.exit(subprocess.call(cmd, stdout=_REAL_STDOUT))
     run_b200(args, rank, world)
 
 
