@@ -5,6 +5,7 @@ import torch
 sys.path.insert(0, ".")
 from tennisbot_rl_b200.batch import TennisBatch
 prec = sys.argv[1]; n = int(sys.argv[2])
+torch.manual_seed(0)  # the same action ring in every process: variants are compared on identical work
 b = TennisBatch("SwingRacket-v0", n, precision=prec, seed=0)
 b.reset()
 acts = [torch.empty((n, b.act_dim), device="cuda").uniform_(-1, 1) for _ in range(4)]
