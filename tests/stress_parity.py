@@ -1,4 +1,5 @@
-"""One-off large parity run (not part of the test suite): CUDA path vs the CPU oracle on 262 144 SwingRacket envs x 78 steps
+"""One-off large parity run (a checker like the rest of tests/, but not collected by pytest: run `python tests/stress_parity.py` on a B200):
+CUDA path vs the CPU oracle on 262 144 SwingRacket envs x 78 steps
 and 65 536 Tennisbot envs x 1100 steps, random actions, f64.  Prints the parity report of tests/harness.py."""
 import sys, time
 import numpy as np
