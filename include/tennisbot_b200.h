@@ -133,7 +133,9 @@ int tb_reset_from(tb_ctx *ctx, const double *d_init, const uint8_t *d_mask, floa
  * Racket.apply_target_action racket.py:92-100, Ball.apply_force objects.py:67-72).  Two launches on `stream`:
  * step_kernel (every env, one substep) and, for SwingRacket, ff_kernel (the queued fast-forward flights).
  * d_actions float32 [N, act_dim]; d_obs float32 [N, obs_dim]; d_reward float32 [N]; d_done uint8 [N];
- * d_terminal_obs float32 [N, obs_dim] written for done envs only (may be NULL); d_events uint8 [N] (may be NULL). */
+ * d_terminal_obs float32 [N, obs_dim] written for done envs only (may be NULL); d_events uint8 [N] (may be NULL).
+ * Never synchronises with the host and keeps all per-step bookkeeping (queue counters, slot tags) in device memory, so
+ * any number of tb_step calls on a stream can be captured into a CUDA graph and replayed. */
 int tb_step(tb_ctx *ctx, const float *d_actions, float *d_obs, float *d_reward, uint8_t *d_done,
             float *d_terminal_obs, uint8_t *d_events, void *stream);
 
