@@ -303,7 +303,7 @@ template <typename T> struct Contact {
   T n[3], d, ra[3], rest, mu;
 };
 template <typename T> struct Row {
-  T u[3], rbxu[3], raxu[3], ia[3], jinv, rhs, lam;
+  T u[3], rbxu[3], raxu[3], ia[3], jinv, denom, rhs, lam;  // denom = 1 / jinv
 };
 // The rare-path functions below are out of line and exchange data through these records ONLY: no address of a
 // register-resident variable of the substep loop (state, control block) may escape into a call, or the compiler
@@ -374,6 +374,7 @@ __device__ __noinline__ void solve_contacts(const Scene<T> &sc, const ContactSet
         w.ia[0] = w.ia[1] = w.ia[2] = 0;
       }
       w.jinv = 1 / denom;
+      w.denom = denom;
       w.lam = 0;
       if (r == 0) {
         S e = fabs(rel) < (S)sc.rest_vel_threshold ? (S)0 : -(S)c.rest * rel;
@@ -404,7 +405,7 @@ __device__ __noinline__ void solve_contacts(const Scene<T> &sc, const ContactSet
         dwb[i] += w.rbxu[i] * dl * inv_ib;
         if (ct[k].dyn) { dva[i] -= w.u[i] * dl * inv_mr; dwa[i] -= w.ia[i] * dl; }
       }
-      S rr = dl / w.jinv;
+      S rr = dl * w.denom;  // (= dl / jinv to an ulp; feeds the early-exit test only: no division on the servers' critical path)
       if (rr * rr > resid) resid = rr * rr;
     }
 #pragma unroll 1
@@ -435,7 +436,7 @@ __device__ __noinline__ void solve_contacts(const Scene<T> &sc, const ContactSet
           dwb[i] += w.rbxu[i] * d * inv_ib;
           if (ct[k].dyn) { dva[i] -= w.u[i] * d * inv_mr; dwa[i] -= w.ia[i] * d; }
         }
-        S rr = d / w.jinv;
+        S rr = d * w.denom;
         if (rr * rr > resid) resid = rr * rr;
       }
     }

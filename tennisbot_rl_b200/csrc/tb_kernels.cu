@@ -538,7 +538,10 @@ __global__ void __launch_bounds__(kBlock, MINB ? MINB : StepMinBlocks<T, KIND>::
 constexpr int kServeMin = TB_FF_SERVE_MIN, kServeWait = TB_FF_SERVE_WAIT, kServerStride = TB_FF_SERVER_STRIDE, kServerLanes = TB_FF_SERVER_LANES;
 constexpr int kIdle = 4, kWait = 5, kRetired = 6;  // lane states 0..3 = kFfFree, kFfLand (running), kFfFull, kFfDone (leaving);
                                                    // no env; no env, holds a late-queue ticket; no env, never will
-constexpr int kFfMaxVisits = 3;  // an env that comes to the servers this often finishes its flight there
+#ifndef TB_FF_MAX_VISITS
+#define TB_FF_MAX_VISITS 3
+#endif
+constexpr int kFfMaxVisits = TB_FF_MAX_VISITS;  // an env that comes to the servers this often finishes its flight there
 constexpr long long kSpinLimit = 1LL << 33;  // clock cycles (~4 s) any wait may take before the launch gives up
 
 __device__ __forceinline__ unsigned long long ld_ctr(const unsigned long long *p) { return *reinterpret_cast<const volatile unsigned long long *>(p); }
@@ -664,6 +667,17 @@ template <typename T> __device__ __forceinline__ void ff_store(T *base, int64_t 
   p7[1] = int_as(T(), L.step); p7[2] = int_as(T(), flags);
 }
 
+#ifdef TB_FF_DIAG
+// log of the last ~100 envs to land: final step count, substeps of the last leg, visits to the servers, where it ended
+// (0 flight warp, 1 server, 2 server running the env to its end), time: words 300.. of the counter set, two per entry
+__device__ __forceinline__ void ff_diag_late(unsigned long long *ctr, int step, int leg, int visits, int where) {
+  unsigned long long i = atomicAdd(ctr + 299, 1ULL);
+  if (i < 100) {
+    ctr[300 + 2 * i] = (unsigned long long)step | ((unsigned long long)leg << 16) | ((unsigned long long)visits << 32) | ((unsigned long long)where << 40);
+    ctr[301 + 2 * i] = global_ns();
+  }
+}
+#endif
 // A flight warp.  n0 / qfront: step_kernel's queue (front / back layout); total: envs in flight in this launch.
 template <typename T>
 __device__ __forceinline__ void ff_flight_warp(const Scene<T> &sc, const StepIO &io, unsigned epoch, long long n0, long long qfront,
@@ -714,6 +728,9 @@ __device__ __forceinline__ void ff_flight_warp(const Scene<T> &sc, const StepIO 
         nsub += L.step - step0;
         int flags = kFlagInFlight | (L.events << kFlagEventShift) | (visits << kFlagVisitShift);
         if (st == kFfDone) flags |= kFlagLanded | (TB_EV_COURT_BALL << kFlagLastShift);  // ff_fast ends on the court's top face only
+#ifdef TB_FF_DIAG
+        if (st == kFfDone && ld_ctr(ctr + kCLanded) + 100 >= (unsigned long long)total) ff_diag_late(ctr, L.step, L.step - step0, visits, 0);
+#endif
         ff_store(base, io.n, (int64_t)me, L, flags);
       }
       dq_push(io.dq_full, io.dq_cap, ctr + kCFullTail, epoch, st == kFfFull, me, lane, ctr + kCError);
@@ -836,7 +853,7 @@ __device__ __noinline__ void ff_server_warp(const Scene<T> &sc, const StepIO &io
 #ifdef TB_FF_DIAG
     if (blockIdx.x == 0 && lane == 0) {
       int bin = (int)((global_ns() - ts0) / 500000ULL);
-      if (bin < 76 && !ctr[128 + 5 * bin]) {
+      if (bin < 34 && !ctr[128 + 5 * bin]) {
         ctr[128 + 5 * bin] = ld_ctr(ctr + kCLanded) + 1; ctr[129 + 5 * bin] = ld_ctr(ctr + kCFullTail); ctr[130 + 5 * bin] = ld_ctr(ctr + kCFullHead);
         ctr[131 + 5 * bin] = ld_ctr(ctr + kCLateTail); ctr[132 + 5 * bin] = ld_ctr(ctr + kCLateHead);
       }
@@ -909,7 +926,10 @@ __device__ __noinline__ void ff_server_warp(const Scene<T> &sc, const StepIO &io
           r = ff_fast<T>(sc, L, r);
           L.tgt[0] = t0; L.tgt[1] = t1; L.tgt[2] = t2;
         } else {
-          r = ff_fast<T>(sc, L, r);
+          // an env that is finished here (to_end) takes its contact-free substeps in one go: a server iteration lasts as
+          // long as the slowest generic substep among the warp's lanes (15-40 us), and the last env of a launch used
+          // to crawl through the end of its flight at one substep per iteration (0.4 ms of a 2.4 ms launch)
+          do r = ff_fast<T>(sc, L, r); while (to_end && r <= kFfLand);
         }
         last = TB_EV_COURT_BALL;  // if this was the last one: ff_fast ends on the court's top face only
       }
@@ -919,6 +939,9 @@ __device__ __noinline__ void ff_server_warp(const Scene<T> &sc, const StepIO &io
         *nsub += L.step - step0;
         int flags = kFlagInFlight | (L.events << kFlagEventShift) | (visits << kFlagVisitShift);
         if (r == kFfDone) flags |= kFlagLanded | (last << kFlagLastShift);
+#ifdef TB_FF_DIAG
+        if (r == kFfDone && ld_ctr(ctr + kCLanded) + 100 >= (unsigned long long)total) ff_diag_late(ctr, L.step, L.step - step0, visits, 1 + (to_end ? 1 : 0));
+#endif
         ff_store(base, io.n, (int64_t)me, L, flags);
         busy = false;
 #ifdef TB_FF_DIAG
@@ -1904,8 +1927,15 @@ int tb_ff_diagnostics(tb_ctx *c, int64_t *h_out) {
       std::fprintf(stderr, "server iterations with %d..%d lanes: %llu, mean %llu cycles; after 1.5 ms: %llu, mean %llu cycles\n", b ? (1 << (b - 1)) + 1 : 1,
                    1 << b, s[112 + 2 * b], s[112 + 2 * b] ? s[113 + 2 * b] / s[112 + 2 * b] : 0ULL, s[80 + 2 * b],
                    s[80 + 2 * b] ? s[81 + 2 * b] / s[80 + 2 * b] : 0ULL);
+  if (std::getenv("TB_FF_DIAG_DUMP")) {
+    unsigned long long tmax = 0;
+    for (int i = 0; i < 100 && i < (int)s[299]; ++i) tmax = s[301 + 2 * i] > tmax ? s[301 + 2 * i] : tmax;
+    for (int i = 0; i < 100 && i < (int)s[299]; ++i)
+      std::fprintf(stderr, "late landing: step %llu last leg %llu substeps visits %llu where %llu at -%.1f us\n", s[300 + 2 * i] & 0xffff,
+                   (s[300 + 2 * i] >> 16) & 0xffff, (s[300 + 2 * i] >> 32) & 0xff, s[300 + 2 * i] >> 40, (tmax - s[301 + 2 * i]) * 1e-3);
+  }
   if (std::getenv("TB_FF_DIAG_DUMP"))
-    for (int b = 0; b < 76 && s[128 + 5 * b]; ++b)
+    for (int b = 0; b < 34 && s[128 + 5 * b]; ++b)
       std::fprintf(stderr, "t=%.1fms landed %llu fullq %llu/%llu lateq %llu/%llu\n", 0.5 * b, s[128 + 5 * b] - 1, s[130 + 5 * b], s[129 + 5 * b],
                    s[132 + 5 * b], s[131 + 5 * b]);
   return 0;
