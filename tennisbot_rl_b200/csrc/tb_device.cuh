@@ -93,6 +93,12 @@ template <typename T> __device__ __forceinline__ T norm3(const T *a) { return M<
 template <typename T> __device__ __forceinline__ T norm3_fast(const T *a) { return M<T>::sqrt_fast(dot3(a, a)); }
 
 // ------------------------------------------------------------------------------------------------ scene
+#ifndef TB_EDGE_UNROLL
+#define TB_EDGE_UNROLL 6
+#endif
+// unroll depth of the loops over the edge tables: the entries are constant-bank loads with a lane-dependent index (long
+// latency), and a lone lane of a server warp has nothing else to overlap them with
+constexpr int kEdgeUnroll = TB_EDGE_UNROLL;
 constexpr int kRacketEdges = TB_RACKET_OUTLINE_N;
 constexpr int kGoalEdges = TB_GOAL_SIDES;
 
@@ -203,7 +209,7 @@ template <typename T, int NE>
 __device__ __noinline__ T prism_distance(const Prism<T, NE> &pr, T t, T u, T v, T far, T *n, T *q) {
   T max_side = -M<T>::inf();
   int max_edge = 0;
-#pragma unroll 2
+#pragma unroll kEdgeUnroll
   for (int i = 0; i < NE; ++i) {
     const Edge<T> &e = pr.e[i];
     T side = (u - e.ax) * e.nx + (v - e.ay) * e.ny;
@@ -1094,7 +1100,7 @@ __device__ __forceinline__ int ff_classify_core(const Scene<T> &sc, const T *rp,
       // ... and the outline itself: the signed distance to any edge line is a lower bound of the distance to the hull.
       // A ball that lingers beside a racket it missed (both in free fall) stays out of the full path this way.
       T max_side = -M<T>::inf();
-#pragma unroll 2
+#pragma unroll kEdgeUnroll
       for (int i = 0; i < kRacketEdges; ++i) {
         const Edge<T> &e = sc.racket.e[i];
         T side = (pl1 - e.ax) * e.nx + (pl2 - e.ay) * e.ny;
