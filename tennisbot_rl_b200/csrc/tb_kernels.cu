@@ -178,7 +178,9 @@ template <int KIND> __device__ __forceinline__ void random_action(uint64_t seed,
 //                auto-reset and store their state.  HBM-bound.  SwingRacket: only the straight-line substep
 //                (ctl_fast) lives here; an env within reach of anything is appended to a list instead.  Envs that
 //                enter the fast-forward store their state with the in-flight mark and append their index to one of
-//                three work lists (one atomic per CTA and list).
+//                three work lists (one atomic per CTA and list).  Tennisbot-v0: the straight-line substep hit_fast
+//                (floor bounce in closed form) in line, the generic step out of line for the few states within reach
+//                of the racket, the net or a floor edge.
 //   ff_kernel    (SwingRacket) persistent; prologue: the deferred control substeps through the generic path, in dense
 //                warps.  Then flight warps (every LANE a small state machine that claims an env, keeps its flight state
 //                in registers, one straight-line substep per loop iteration) and server warps (generic substeps for
@@ -303,7 +305,7 @@ __device__ __forceinline__ void finish_api(const Scene<T> &sc, const StepIO &io,
 #define TB_STEP_SWING_MINB64 4
 #endif
 // CTAs per SM the register budget of step_kernel is held to.  SwingRacket's instantiation holds the straight-line control
-// substep only (everything else is deferred to ff_kernel), Tennisbot's the generic physics_step.
+// substep only (everything else is deferred to ff_kernel), Tennisbot's hit_fast plus the generic physics_step out of line.
 template <typename T, int KIND> struct StepMinBlocks { static constexpr int v = KIND == TB_ENV_SWING ? TB_STEP_SWING_MINB32 : TB_STEP_MINB32; };
 template <int KIND> struct StepMinBlocks<double, KIND> { static constexpr int v = KIND == TB_ENV_SWING ? TB_STEP_SWING_MINB64 : TB_STEP_MINB64; };
 
