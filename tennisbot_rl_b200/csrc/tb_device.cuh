@@ -83,6 +83,8 @@ template <typename T> __device__ __forceinline__ void clamp_velocities(T *bv, T 
     }
   }
 }
+__device__ __forceinline__ void opaque(double &x) { asm volatile("" : "+d"(x)); }
+__device__ __forceinline__ void opaque(float &x) { asm volatile("" : "+f"(x)); }
 template <typename T> __device__ __forceinline__ T dot3(const T *a, const T *b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
 template <typename T> __device__ __forceinline__ void cross3(const T *a, const T *b, T *o) {
   o[0] = a[1] * b[2] - a[2] * b[1];
@@ -108,7 +110,26 @@ template <typename T> struct Edge {
 template <typename T, int NE> struct Prism {
   Edge<T> e[NE];
   T half_thick, bound_radius;
+  // Two regions that lie inside the outline for certain (prism_inside_fast): an ellipse centred on the v axis, shrunk on
+  // the host until it clears every edge line, and the quadrilateral between two outline edges and two lines of constant v
+  // (the racket's throat; tz_lo > tz_hi: none).  A ball that rests or rolls on the racket face, or lands on the goal
+  // disc, is inside one of them, and the loops over the edge table are skipped.
+  T in_c, in_inv_a, in_inv_b, tz_lo, tz_hi;
+  T t_ax[2], t_ay[2], t_nx[2], t_ny[2];
+  // ... and the converse (prism_outside_fast): out_a, out_b = semi-axes of an ellipse about the same centre that contains
+  // every outline vertex at or above out_v (all of them when there is no quadrilateral); below out_v the outline lies
+  // between the quadrilateral's two edge lines and above v = out_lo.
+  T out_a, out_b, out_v, out_lo;
+  T out_inv_a, out_inv_b;  // 1 / (out_a + rim), 1 / (out_b + rim) for the racket's rim (ffp_rim), rounded down
 };
+// true: (u, v) is strictly inside the outline (false says nothing)
+template <typename T, int NE> __device__ __forceinline__ bool prism_inside_fast(const Prism<T, NE> &pr, T u, T v) {
+  T du = u * pr.in_inv_a, dv = (v - pr.in_c) * pr.in_inv_b;
+  bool ell = du * du + dv * dv < 1;
+  bool quad = (v > pr.tz_lo) & (v < pr.tz_hi) & ((u - pr.t_ax[0]) * pr.t_nx[0] + (v - pr.t_ay[0]) * pr.t_ny[0] < 0) &
+              ((u - pr.t_ax[1]) * pr.t_nx[1] + (v - pr.t_ay[1]) * pr.t_ny[1] < 0);
+  return ell | quad;
+}
 
 template <typename T> struct Scene {
   T dt, gravity_z, lin_damping, ang_damping, max_coord_vel;
@@ -207,6 +228,12 @@ template <typename T> __device__ __forceinline__ void matT_vec(const T *R, const
 // n and q unset), and - only for a point outside the outline but within `far` - the closest point on its edges.
 template <typename T, int NE>
 __device__ __noinline__ T prism_distance(const Prism<T, NE> &pr, T t, T u, T v, T far, T *n, T *q) {
+  if (M<T>::abs(t) - pr.half_thick > 0 && prism_inside_fast(pr, u, v)) {  // over a face, inside the outline: the loops below
+    T st = t < 0 ? (T)-1 : (T)1;                                          // would end in exactly this case
+    n[0] = st; n[1] = 0; n[2] = 0;
+    q[0] = st * pr.half_thick; q[1] = u; q[2] = v;
+    return M<T>::abs(t) - pr.half_thick;
+  }
   T max_side = -M<T>::inf();
   int max_edge = 0;
 #pragma unroll kEdgeUnroll
@@ -302,6 +329,18 @@ template <typename T> __device__ __forceinline__ void plane_space(const T *n, T 
   }
 }
 
+// true: (u, v) is farther than `rim` from the outline for certain (false says nothing).  Far from the part at or above out_v:
+// outside the containing ellipse grown by rim (the parallel curve of an ellipse lies inside the ellipse with both semi-
+// axes grown by the offset).  Far from the part below out_v, which lies between two edge lines: beyond one of those lines,
+// below out_lo or above out_v, each by more than rim.
+template <typename T, int NE> __device__ __forceinline__ bool prism_outside_fast(const Prism<T, NE> &pr, T u, T v, T rim) {
+  T du = u * pr.out_inv_a, dv = (v - pr.in_c) * pr.out_inv_b;  // (rim == the rim the reciprocals were formed with)
+  bool far_head = du * du + dv * dv > 1;
+  bool far_quad = (pr.tz_lo > pr.tz_hi) | (v > pr.out_v + rim) | (v < pr.out_lo - rim) |
+                  ((u - pr.t_ax[0]) * pr.t_nx[0] + (v - pr.t_ay[0]) * pr.t_ny[0] > rim) |
+                  ((u - pr.t_ax[1]) * pr.t_nx[1] + (v - pr.t_ay[1]) * pr.t_ny[1] > rim);
+  return far_head & far_quad;
+}
 // ------------------------------------------------------------------------------------------------ contacts
 constexpr int kMaxContacts = 4;
 template <typename T> struct Contact {
@@ -331,9 +370,15 @@ constexpr int kNeedRacket = 1, kNeedFloor = 2, kNeedNet = 4, kNeedGoal = 8;
 // per episode), kept out of line so the substep loop stays small.  The rows are ALWAYS solved in double, also
 // by the float32 kernel: the residual early exit makes the impulse sensitive to the sweep count, and a float
 // solve that stops one sweep apart from the double oracle moves the ball's exit velocity by ~1e-2 m/s.
-template <typename T>
-__device__ __noinline__ void solve_contacts(const Scene<T> &sc, const ContactSet<T> *cs, int nc, SolveIO<T> *io) {
+// NC > 0: exactly NC contacts, every loop over contacts and rows unrolled so that the rows live in registers (one
+// contact is the rule: a server lane of ff_kernel working alone through a chain of contact substeps used to spend most of
+// its time on the local-memory round trips of the row table); NC == 0: nc contacts, rows in local memory.  Same
+// operations in the same order either way.
+template <typename T, int NC>
+__device__ __forceinline__ void solve_impl(const Scene<T> &sc, const ContactSet<T> *cs, int nc_dyn, SolveIO<T> *io) {
   typedef double S;
+  const int nc = NC ? NC : nc_dyn;
+  constexpr int UK = NC ? NC : 1, UR = NC ? 3 : 1;  // unroll depths
   const Contact<T> *ct = cs->c;
   const S rb = sc.ball_r, inv_mb = sc.ball_inv_m, inv_ib = sc.ball_inv_i, inv_mr = sc.racket_inv_m, dt = sc.dt;
   S R[9], bv[3], bw[3], rv[3], rw[3];
@@ -351,8 +396,8 @@ __device__ __noinline__ void solve_contacts(const Scene<T> &sc, const ContactSet
 #pragma unroll
   for (int i = 0; i < 3; ++i) { bv[i] = io->bv[i]; bw[i] = io->bw[i]; rv[i] = io->rv[i]; rw[i] = io->rw[i]; }
   S dvb[3] = {0, 0, 0}, dwb[3] = {0, 0, 0}, dva[3] = {0, 0, 0}, dwa[3] = {0, 0, 0};
-  Row<S> rows[kMaxContacts][3];
-#pragma unroll 1
+  Row<S> rows[NC ? NC : kMaxContacts][3];
+#pragma unroll UK
   for (int k = 0; k < nc; ++k) {
     const Contact<T> &c = ct[k];
     S dirs[3][3];
@@ -360,7 +405,7 @@ __device__ __noinline__ void solve_contacts(const Scene<T> &sc, const ContactSet
     plane_space<S>(dirs[0], dirs[1], dirs[2]);
     S rbv[3] = {-rb * dirs[0][0], -rb * dirs[0][1], -rb * dirs[0][2]};
     S ra[3] = {(S)c.ra[0], (S)c.ra[1], (S)c.ra[2]};
-#pragma unroll 1
+#pragma unroll UR
     for (int r = 0; r < 3; ++r) {
       Row<S> &w = rows[k][r];
       w.u[0] = dirs[r][0]; w.u[1] = dirs[r][1]; w.u[2] = dirs[r][2];
@@ -397,7 +442,7 @@ __device__ __noinline__ void solve_contacts(const Scene<T> &sc, const ContactSet
 #pragma unroll 1
   for (int it = 0; it < sc.iters; ++it) {
     S resid = 0;
-#pragma unroll 1
+#pragma unroll UK
     for (int k = 0; k < nc; ++k) {
       Row<S> &w = rows[k][0];
       S jd = dot3(w.u, dvb) + dot3(w.rbxu, dwb) - dot3(w.u, dva) - dot3(w.raxu, dwa);
@@ -414,7 +459,7 @@ __device__ __noinline__ void solve_contacts(const Scene<T> &sc, const ContactSet
       S rr = dl * w.denom;  // (= dl / jinv to an ulp; feeds the early-exit test only: no division on the servers' critical path)
       if (rr * rr > resid) resid = rr * rr;
     }
-#pragma unroll 1
+#pragma unroll UK
     for (int k = 0; k < nc; ++k) {
       S lam_n = rows[k][0].lam;
       if (!(lam_n > 0)) continue;
@@ -450,6 +495,14 @@ __device__ __noinline__ void solve_contacts(const Scene<T> &sc, const ContactSet
   }
 #pragma unroll
   for (int i = 0; i < 3; ++i) { io->dvb[i] = (T)dvb[i]; io->dwb[i] = (T)dwb[i]; io->dva[i] = (T)dva[i]; io->dwa[i] = (T)dwa[i]; }
+}
+template <typename T>
+__device__ __noinline__ void solve_contacts(const Scene<T> &sc, const ContactSet<T> *cs, int nc, SolveIO<T> *io) {
+#ifdef TB_SOLVE_UNROLL1
+  if (nc == 1) solve_impl<T, 1>(sc, cs, nc, io);
+  else
+#endif
+    solve_impl<T, 0>(sc, cs, nc, io);
 }
 
 // Narrow phase of every pair whose broad-phase test passed, one out-of-line call.  Appends to cs->c[] in the
@@ -761,9 +814,12 @@ template <typename T, int KIND> __device__ __forceinline__ void pack_obs(const S
   }
 }
 
+template <typename T> __device__ __forceinline__ T moved_dist(T bx, T by, T gx, T gy, T d0) {
+  T dx = bx - gx, dy = by - gy;
+  return (d0 - M<T>::sqrt(dx * dx + dy * dy)) / d0 * (T)20;
+}
 template <typename T> __device__ __forceinline__ T moved_dist_to_goal(const St<T> &s) {
-  T dx = s.bp[0] - s.goal[0], dy = s.bp[1] - s.goal[1];
-  return (s.d0 - M<T>::sqrt(dx * dx + dy * dy)) / s.d0 * (T)20;
+  return moved_dist(s.bp[0], s.bp[1], s.goal[0], s.goal[1], s.d0);
 }
 template <typename T> __device__ __forceinline__ T dist_to_reward(T d) {
   return d < (T)0.5 ? (T)20 : d < 1 ? (T)15 : d < 2 ? (T)10 : d < 3 ? (T)5 : d < 4 ? (T)1 : (T)0;
@@ -1084,7 +1140,8 @@ constexpr int kFfDone = 3;  // (returned by the step functions) the env step is 
 // Conservative (a lane may be sent to ff_full for nothing, never the other way), and decided by the env's own state
 // only, so which path integrates a given substep never depends on the other lanes of the warp.
 // nb, nr, nw: squared speeds of ball, racket and racket spin.
-template <typename T, bool WITH_GOAL = true>
+// QUICK: the outline test with its quick accept / reject first (ff_kernel's loops); else the plain loop (step_kernel).
+template <typename T, bool WITH_GOAL = true, bool QUICK = false>
 __device__ __forceinline__ int ff_classify_core(const Scene<T> &sc, const T *rp, const T *rq, const T *bp, const T *goal, T nb, T nr,
                                                 T nw, int step) {
   const T x = rq[0], y = rq[1], z = rq[2], w = rq[3];
@@ -1096,9 +1153,28 @@ __device__ __forceinline__ int ff_classify_core(const Scene<T> &sc, const T *rp,
     T pl1 = 2 * (x * y - z * w) * rel[0] + (1 - 2 * (x * x + z * z)) * rel[1] + 2 * (y * z + x * w) * rel[2];
     T pl2 = 2 * (x * z + y * w) * rel[0] + 2 * (y * z - x * w) * rel[1] + (1 - 2 * (x * x + y * y)) * rel[2];
     racket = !(M<T>::abs(pl1) > sc.ffp_box[0]) & !(pl2 > sc.ffp_box[2]) & !(pl2 < sc.ffp_box[1]);
-    if (racket) {
+    if (QUICK && racket) {
+      // ... and the outline itself.  Two quick tests settle all but a thin band around it (a flight lane whose ball falls
+      // alongside the racket comes here every substep); there the signed distance to every edge line decides (a lower
+      // bound of the distance to the hull).  The opaque copies pin all of this into the cold block: hoisted into the
+      // straight line of the substep it would cost every lane ~20 FP64 instructions, and as an out-of-line call it split
+      // the substep loop's schedule (measured on B200: +7 % on the whole fast-forward launch).
+      T q1 = pl1, q2 = pl2;
+      opaque(q1); opaque(q2);
+      if (prism_inside_fast(sc.racket, q1, q2)) racket = true;
+      else if (prism_outside_fast(sc.racket, q1, q2, sc.ffp_rim)) racket = false;
+      else {
+        T max_side = -M<T>::inf();
+#pragma unroll kEdgeUnroll
+        for (int i = 0; i < kRacketEdges; ++i) {
+          const Edge<T> &e = sc.racket.e[i];
+          T side = (q1 - e.ax) * e.nx + (q2 - e.ay) * e.ny;
+          max_side = side > max_side ? side : max_side;
+        }
+        racket = !(max_side > sc.ffp_rim);
+      }
+    } else if (!QUICK && racket) {
       // ... and the outline itself: the signed distance to any edge line is a lower bound of the distance to the hull.
-      // A ball that lingers beside a racket it missed (both in free fall) stays out of the full path this way.
       T max_side = -M<T>::inf();
 #pragma unroll kEdgeUnroll
       for (int i = 0; i < kRacketEdges; ++i) {
@@ -1122,7 +1198,7 @@ __device__ __forceinline__ int ff_classify_core(const Scene<T> &sc, const T *rp,
 }
 template <typename T> __device__ __forceinline__ int ff_classify(const Scene<T> &sc, FfLane<T> &L) {
   L.nb = dot3(L.bv, L.bv); L.nr = dot3(L.rv, L.rv); L.nw = dot3(L.wl, L.wl);
-  return ff_classify_core(sc, L.rp, L.rq, L.bp, L.goal, L.nb, L.nr, L.nw, L.step);
+  return ff_classify_core<T, true, true>(sc, L.rp, L.rq, L.bp, L.goal, L.nb, L.nr, L.nw, L.step);
 }
 // the same for a state record (omega in the world frame: same norm)
 template <typename T> __device__ __forceinline__ int ff_classify_state(const Scene<T> &sc, const St<T> &s) {
@@ -1451,6 +1527,202 @@ __device__ __noinline__ int ff_full(const Scene<T> &sc, FfLane<T> *Lp, int phase
   *last = c.last;
   int next = ff_classify(sc, *Lp);
   return fin ? kFfDone : next;
+}
+
+// The server warps' short cut for the substep that fills most of their time: the ball is high above the court and meets -
+// or just misses - the racket (over a face - projection inside the outline for certain, prism_inside_fast - the narrow
+// phase is one coordinate; near the rim it is prism_distance's loops).  Same substep as
+// ff_substep in exact arithmetic, to rounding otherwise, with a fraction of the instructions (a lone lane's generic substep
+// is bound by instruction fetch: ~3000 instructions of cold code):
+//   * the single contact's three rows are solved in IMPULSE space: A = J M^-1 J^T (3 x 3) once, then projected Gauss-Seidel
+//     on lambda alone - sweep for sweep what solve_contacts does on the velocities (jd_i = sum_j A_ij lambda_j), the same
+//     clamps and the same residual test, so it stops after the same sweep;
+//   * everything that involves the racket's rotation stays in its body frame: J's angular part is q x (R^T u), the effective
+//     inertia is diagonal there, and omega_body takes the impulse directly - no world-frame angular velocity, no R I^-1 R^T.
+// Returns what comes next like ff_full (the env step cannot end here), or -1 without touching *Lp when the state is outside
+// what this covers (ball low enough for the court, the net or the goal; a speed near the clamp; the time-out step): ff_full
+// takes it then.
+template <typename T>
+__device__ __noinline__ int ff_contact_lean(const Scene<T> &sc, FfLane<T> *Lp, int phase, int *last) {
+  if (sizeof(T) != 8) return -1;  // (the float32 kernel keeps the generic path: its rows are solved in double there)
+  const T dt = sc.dt, thr = sc.contact_threshold, rb = sc.ball_r;
+  if (!(Lp->nb < sc.ffp_v2) | !(Lp->nr < sc.ffp_v2) | !(Lp->nw < sc.ffp_a2) | (Lp->step >= 799)) return -1;
+  if (!(Lp->bp[2] > sc.ff_ball_z)) {  // low ball: only if the court, the net and the goal are all out of reach (ff_substep's tests)
+    const T b0 = Lp->bp[0], b1 = Lp->bp[1], b2 = Lp->bp[2];
+    const T reach_b = rb + sc.box_margin + thr, reach_g = rb + sc.hull_margin + thr, rxy = sc.goal_r + reach_g;
+    const T gx = b0 - Lp->goal[0], gy = b1 - Lp->goal[1];
+    const bool floor = !(M<T>::abs(b2) - sc.floor_h[2] > reach_b || M<T>::abs(b0) - sc.floor_h[0] > reach_b || M<T>::abs(b1) - sc.floor_h[1] > reach_b);
+    const bool net = !(M<T>::abs(b0) - sc.net_h[0] > reach_b || M<T>::abs(b2) - sc.net_h[2] > reach_b || M<T>::abs(b1) - sc.net_h[1] > reach_b);
+    const bool goal = M<T>::abs(b2) - sc.goal_hz <= reach_g && gx * gx + gy * gy <= rxy * rxy;
+    if (floor | net | goal) return -1;
+  }
+  T R[9], rq[4] = {Lp->rq[0], Lp->rq[1], Lp->rq[2], Lp->rq[3]};
+  quat_to_mat(rq, R);
+  const T rp[3] = {Lp->rp[0], Lp->rp[1], Lp->rp[2]}, bp[3] = {Lp->bp[0], Lp->bp[1], Lp->bp[2]};
+  T rel[3] = {bp[0] - rp[0], bp[1] - rp[1], bp[2] - rp[2]}, pl[3];
+  matT_vec(R, rel, pl);
+  // ---- (1) detection at the start-of-step poses
+  int bits = 0;
+  bool contact = false;
+  T d = 0, nl[3] = {1, 0, 0}, ql[3] = {0, 0, 0};  // normal and closest point of the hull core in the racket frame
+  {
+    const T reach = rb + sc.hull_margin + thr, rs = sc.racket.bound_radius + reach;
+    const bool near_racket = dot3(rel, rel) <= rs * rs && !(M<T>::abs(pl[0]) - sc.racket.half_thick > reach) &&
+                             !(M<T>::abs(pl[1]) - sc.racket_box[0] > reach) && !(pl[2] - sc.racket_box[2] > reach) &&
+                             !(sc.racket_box[1] - pl[2] > reach);
+    if (near_racket) {
+      const T et = M<T>::abs(pl[0]) - sc.racket.half_thick;
+      T dc;
+      if (et > 0 && prism_inside_fast(sc.racket, pl[1], pl[2])) {  // over a face
+        const T st = pl[0] < 0 ? (T)-1 : (T)1;
+        dc = et;
+        nl[0] = st;
+        ql[0] = st * sc.racket.half_thick; ql[1] = pl[1]; ql[2] = pl[2];
+      } else {  // near the rim, or inside the plate: the loops over the outline
+        dc = prism_distance<T, kRacketEdges>(sc.racket, pl[0], pl[1], pl[2], reach * (T)1.0001, nl, ql);
+      }
+      d = dc - (rb + sc.hull_margin);
+      contact = d <= thr;
+    }
+    T zlo = R[8] * sc.racket_obb[1], zhi = R[8] * sc.racket_obb[2];
+    T low = rp[2] - M<T>::abs(R[6]) * sc.racket.half_thick - M<T>::abs(R[7]) * sc.racket_obb[0] + (zlo < zhi ? zlo : zhi) - sc.hull_margin;
+    bits |= (low <= sc.floor_h[2] + thr && M<T>::abs(rp[0]) <= sc.floor_h[0] + 1 && M<T>::abs(rp[1]) <= sc.floor_h[1] + 1) ? TB_EV_RACKET_LOW : 0;
+  }
+  // ---- (2) velocities, as in ff_substep
+  T bv[3] = {Lp->bv[0], Lp->bv[1], Lp->bv[2]}, bw[3] = {Lp->bw[0], Lp->bw[1], Lp->bw[2]};
+  T rv[3] = {Lp->rv[0], Lp->rv[1], Lp->rv[2]}, wl[3] = {Lp->wl[0], Lp->wl[1], Lp->wl[2]};
+  {
+    T fb = 1 - sc.ff_kl * (1 + M<T>::norm_damp(Lp->nb));
+    bv[0] *= fb; bv[1] *= fb; bv[2] = bv[2] * fb + sc.ff_dtg;
+    if (nonzero3(bw)) {
+      T fs = 1 - sc.ff_ka * (1 + M<T>::norm_damp(dot3(bw, bw)));
+      bw[0] *= fs; bw[1] *= fs; bw[2] *= fs;
+    }
+    T fr = 1 - sc.ff_kl * (1 + M<T>::norm_damp(Lp->nr));
+    T h0 = 0, h1 = 0, h2 = sc.ff_dtg;
+    if (phase == 2) {
+      h0 = sc.ff_hack[0] * (rp[0] - Lp->tgt[0]);
+      h1 = sc.ff_hack[1] * (rp[1] - Lp->tgt[1]);
+      h2 = sc.ff_hack[2] * (rp[2] - Lp->tgt[2]) + sc.ff_dtg;
+    }
+    rv[0] = rv[0] * fr + h0; rv[1] = rv[1] * fr + h1; rv[2] = rv[2] * fr + h2;
+    T fw = 1 - sc.ff_ka * (1 + M<T>::norm_damp(Lp->nw));
+    T p12 = wl[1] * wl[2], p20 = wl[2] * wl[0], p01 = wl[0] * wl[1];
+    wl[0] = wl[0] * fw - sc.ff_gyro[0] * p12;
+    wl[1] = wl[1] * fw - sc.ff_gyro[1] * p20;
+    wl[2] = wl[2] * fw - sc.ff_gyro[2] * p01;
+  }
+  // ---- (3) the contact
+  if (contact) {
+    bits |= TB_EV_RACKET_BALL;
+    const T inv_mb = sc.ball_inv_m, inv_ib = sc.ball_inv_i, inv_mr = sc.racket_inv_m;
+    // world frame: normal u0 = R nl and Bullet's two tangents; body frame: ub_j = R^T u_j, contact point qs on the hull
+    T u[3][3], ub[3][3], l[3][3], li[3][3], rbxu[3][3];
+    mat_vec(R, nl, u[0]);
+    plane_space<T>(u[0], u[1], u[2]);
+    ub[0][0] = nl[0]; ub[0][1] = nl[1]; ub[0][2] = nl[2];
+    matT_vec(R, u[1], ub[1]);
+    matT_vec(R, u[2], ub[2]);
+    const T qs[3] = {ql[0] + sc.hull_margin * nl[0], ql[1] + sc.hull_margin * nl[1], ql[2] + sc.hull_margin * nl[2]};
+    const T rbv[3] = {-rb * u[0][0], -rb * u[0][1], -rb * u[0][2]};
+    T A[3][3], jinv[3], rhs[3], lam[3] = {0, 0, 0};
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      cross3(qs, ub[j], l[j]);
+      cross3(rbv, u[j], rbxu[j]);
+#pragma unroll
+      for (int i = 0; i < 3; ++i) li[j][i] = l[j][i] * sc.racket_inv_i[i];
+    }
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      T relv = dot3(u[j], bv) + dot3(rbxu[j], bw) - (dot3(u[j], rv) + dot3(l[j], wl));
+      A[j][j] = inv_mb + dot3(rbxu[j], rbxu[j]) * inv_ib + (inv_mr + dot3(l[j], li[j]));
+      jinv[j] = 1 / A[j][j];
+      if (j == 0) {
+        T e = M<T>::abs(relv) < sc.rest_vel_threshold ? (T)0 : -sc.rest_racket * relv;
+        if (e < 0) e = 0;
+        T pen = d + sc.slop, vel_err = e - relv, pos_err = 0;
+        if (pen > 0) vel_err -= pen / dt;
+        else pos_err = -pen * sc.erp / dt;
+        rhs[0] = (pos_err + vel_err) * jinv[0];
+      } else {
+        rhs[j] = -relv * jinv[j];
+      }
+    }
+    A[0][1] = A[1][0] = dot3(l[0], li[1]); A[0][2] = A[2][0] = dot3(l[0], li[2]); A[1][2] = A[2][1] = dot3(l[1], li[2]);
+#pragma unroll 1
+    for (int it = 0; it < sc.iters; ++it) {
+      T resid = 0;
+      {
+        T jd = A[0][0] * lam[0] + A[0][1] * lam[1] + A[0][2] * lam[2];
+        T dl = rhs[0] - jd * jinv[0], sum = lam[0] + dl;
+        if (sum < 0) { dl = -lam[0]; sum = 0; }
+        lam[0] = sum;
+        T rr = dl * A[0][0];
+        resid = rr * rr;
+      }
+      if (lam[0] > 0) {
+        const T lim = sc.mu_racket * lam[0];
+        T jd1 = A[1][0] * lam[0] + A[1][1] * lam[1] + A[1][2] * lam[2], jd2 = A[2][0] * lam[0] + A[2][1] * lam[1] + A[2][2] * lam[2];
+        T s1 = lam[1] + (rhs[1] - jd1 * jinv[1]), s2 = lam[2] + (rhs[2] - jd2 * jinv[2]);
+        T m2 = s1 * s1 + s2 * s2;
+        if (m2 > lim * lim) {
+          T sf = lim / M<T>::sqrt(m2);
+          s1 *= sf; s2 *= sf;
+        }
+        T r1 = (s1 - lam[1]) * A[1][1], r2 = (s2 - lam[2]) * A[2][2];
+        lam[1] = s1; lam[2] = s2;
+        if (r1 * r1 > resid) resid = r1 * r1;
+        if (r2 * r2 > resid) resid = r2 * r2;
+      }
+      if (resid <= sc.solver_residual) break;
+    }
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      T ju = u[0][i] * lam[0] + u[1][i] * lam[1] + u[2][i] * lam[2];
+      bv[i] += ju * inv_mb;
+      rv[i] -= ju * inv_mr;
+      bw[i] += (rbxu[0][i] * lam[0] + rbxu[1][i] * lam[1] + rbxu[2][i] * lam[2]) * inv_ib;
+      wl[i] -= li[0][i] * lam[0] + li[1][i] * lam[1] + li[2][i] * lam[2];
+    }
+    // Bullet's +-max_coord_vel clamp after the solve (world coordinates of omega): far away in practice, exact when not
+    bool over = near_limit(dot3(wl, wl), sc.vmax2_hi);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) over = over | near_limit(bv[i], sc.vmax_hi) | near_limit(bw[i], sc.vmax_hi) | near_limit(rv[i], sc.vmax_hi);
+    if (TB_UNLIKELY(over)) {
+      T w[3];
+      mat_vec(R, wl, w);
+      clamp_velocities(bv, bw, rv, w, sc.max_coord_vel, sc.vmax_hi);
+      matT_vec(R, w, wl);
+    }
+  }
+  // ---- (4) poses, as in ff_substep
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    Lp->bp[i] = bp[i] + dt * bv[i];
+    Lp->rp[i] = rp[i] + dt * rv[i];
+    Lp->bv[i] = bv[i]; Lp->bw[i] = bw[i]; Lp->rv[i] = rv[i]; Lp->wl[i] = wl[i];
+  }
+  {
+    T sinc, cw;
+    sinc_cos_x2(sc.ff_qx2 * dot3(wl, wl), &sinc, &cw);
+    T k = (T)0.5 * dt * sinc;
+    T ax = wl[0] * k, ay = wl[1] * k, az = wl[2] * k;
+    T x = cw * rq[0] + ax * rq[3] + az * rq[1] - ay * rq[2];
+    T y = cw * rq[1] + ay * rq[3] + ax * rq[2] - az * rq[0];
+    T z = cw * rq[2] + az * rq[3] + ay * rq[0] - ax * rq[1];
+    T w = cw * rq[3] - ax * rq[0] - ay * rq[1] - az * rq[2];
+    T n2 = x * x + y * y + z * z + w * w;
+    T inv = (T)1.5 - (T)0.5 * n2;
+    if (TB_UNLIKELY(M<T>::abs(n2 - 1) > (T)1e-4)) inv = fast_rsqrt(n2);
+    Lp->rq[0] = x * inv; Lp->rq[1] = y * inv; Lp->rq[2] = z * inv; Lp->rq[3] = w * inv;
+  }
+  // ---- env logic (swingracket_env.py:109-133): no court or goal contact and no time-out is possible here
+  Lp->step += 1;
+  Lp->events |= bits;
+  Lp->sb = norm3(bw);
+  *last = bits;
+  return ff_classify(sc, *Lp);
 }
 
 // Reward of the env step a fast-forward ended with, from the contact bits of its last substep (swingracket_env.py:111-126;

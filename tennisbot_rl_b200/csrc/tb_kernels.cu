@@ -125,7 +125,14 @@ struct StepIO {
   unsigned *epoch;                   // two device words: [0] steps completed (read by step_kernel, advanced by ff_kernel),
                                      // [1] = [0] + 1 written by step_kernel = the tag of this step's queue slots
   int prefetch_ahead;                // step_kernel: CTAs resident at a time (the L2 prefetch distance), 0 = none
-  unsigned long long *fault;         // sticky: non-zero once a wait inside ff_kernel has timed out (tb_read_stats fails then)
+  unsigned long long *fault;         // sticky: non-zero once a wait inside ff_kernel has timed out (every later call on the
+                                     // context fails); fault_host: the same word in mapped host memory, read by the host
+                                     // without synchronising
+  volatile unsigned long long *fault_host;
+  long long spin_limit;              // clock cycles any wait inside ff_kernel may take before the launch gives up
+  int server_sm_stride;              // ff_kernel: > 0 = every warp on an SM whose id is a multiple of this is a server warp and
+                                     // all others are flight warps (full persistent grids); 0 = one server warp per
+                                     // kServerStride CTAs
   unsigned long long *queue_ctrs;    // two sets of kCtrWords counters (kC* below) used by alternate steps: [0] front,
                                      // [1] back entries appended by the step's step_kernel, the rest ff_kernel's.  Which set
                                      // a step uses is decided on the device (ctr_sets), so captured CUDA graphs of any
@@ -205,8 +212,14 @@ constexpr int kCFullClaim0 = 6;   // claimed entries of queue_full (ff_kernel's 
 constexpr int kCFullTail = 16, kCFullHead = 17;  // dq_full: reserved by producers / claimed by servers
 constexpr int kCLateTail = 32, kCLateHead = 33;  // dq_late: reserved by servers / claimed by flight lanes
 constexpr int kCCtl = 13;         // entries of queue_ctl
-constexpr int kCBarrier = 96;     // ff_kernel's grid barrier (own line)
-constexpr int kCLanded = 64;      // envs whose env step is over (own line: everybody polls it at the end)
+constexpr int kCCtlClaim = 14;    // claimed entries of queue_ctl (ff_kernel's prologue, 32 per warp)
+constexpr int kCLanded = 64;      // envs whose env step is over (own line, with the two words below: idle warps poll them)
+constexpr int kCCtlDone = 65;     // entries of queue_ctl that have been stepped (their flights, if any, are published)
+constexpr int kCDynTotal = 66;    // flights that were queued by the prologue (on top of step_kernel's three lists)
+constexpr int kCFinDone = 67;     // finishing pass 1: tiles of 32 envs that have been looked at
+constexpr int kCRetryTail = 68;   // ... envs that were still in flight then (listed in queue_ctl, finished in pass 2)
+constexpr int kCFinClaim = 7;     // finishing pass 1: claimed tiles
+constexpr int kCRetryClaim = 8;   // finishing pass 2: claimed entries of the retry list
 
 struct WarpStats {
   unsigned long long *acc;  // this warp's row of the CTA's shared accumulators
@@ -544,39 +557,28 @@ constexpr int kIdle = 4, kWait = 5, kRetired = 6;  // lane states 0..3 = kFfFree
 #define TB_FF_MAX_VISITS 3
 #endif
 constexpr int kFfMaxVisits = TB_FF_MAX_VISITS;  // an env that comes to the servers this often finishes its flight there
-constexpr long long kSpinLimit = 1LL << 33;  // clock cycles (~4 s) any wait may take before the launch gives up
-
 __device__ __forceinline__ unsigned long long ld_ctr(const unsigned long long *p) { return *reinterpret_cast<const volatile unsigned long long *>(p); }
-// All CTAs of the (co-resident) grid meet.  Returns false if the barrier could not complete (a time-out, or another CTA
-// gave up): the launch then ends without finishing its envs instead of hanging the device.
-__device__ __forceinline__ bool grid_barrier(unsigned long long *ctr) {
-  __shared__ int s_ok;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    __threadfence();
-    atomicAdd(ctr + kCBarrier, 1ULL);
-    int ok = 1;
-    long long t0 = clock64();
-    while (ld_ctr(ctr + kCBarrier) < (unsigned long long)gridDim.x) {
-      __nanosleep(100);
-      if (clock64() - t0 > kSpinLimit) {
-        atomicExch(ctr + kCError, 6ULL);
-        ok = 0;
-        break;
-      }
-    }
-    __threadfence();
-    s_ok = ok;
-  }
-  __syncthreads();
-  return s_ok != 0;
-}
 __device__ __forceinline__ unsigned long long global_ns() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
   return t;
 }
-
+// Has every flight of this launch landed?  total0 = entries of step_kernel's three lists; the prologue adds the flights
+// of the deferred envs it steps (kCDynTotal) and counts the entries it is through with (kCCtlDone) after publishing them,
+// so once kCCtlDone has reached nctl the sum is final.
+__device__ __forceinline__ bool ff_all_landed(const unsigned long long *ctr, long long nctl, long long total0) {
+  if (ld_ctr(ctr + kCCtlDone) < (unsigned long long)nctl) return false;
+  if (ld_ctr(ctr + kCLanded) < (unsigned long long)total0 + ld_ctr(ctr + kCDynTotal)) return false;
+  __threadfence();  // (kCDynTotal is final once kCCtlDone has reached nctl: read it again behind the fence)
+  return ld_ctr(ctr + kCLanded) >= (unsigned long long)total0 + ld_ctr(ctr + kCDynTotal);
+}
+// a wait gave up: mark the launch (every role leaves when it sees the mark) and the context
+__device__ __forceinline__ void ff_give_up(const StepIO &io, unsigned long long *ctr, unsigned long long code) {
+  atomicExch(ctr + kCError, code);
+  atomicExch(io.fault, code);
+  *io.fault_host = code;
+  __threadfence_system();
+}
 
 // warp-aggregated reservation of slots in a dynamic queue + tagged publication of `me` (for lanes with pred).  The
 // env's state must have been stored before the call.
@@ -668,6 +670,11 @@ template <typename T> __device__ __forceinline__ void ff_store(T *base, int64_t 
   p5[0] = L.bw[1]; p5[1] = L.bw[2];
   p7[1] = int_as(T(), L.step); p7[2] = int_as(T(), flags);
 }
+// The landed mark of an env whose state ff_store has written, after a fence: the finishing pass may look at the env at any time
+// and takes the mark as "the state is complete".
+template <typename T> __device__ __forceinline__ void ff_mark_landed(T *base, int64_t n, int64_t me, int flags) {
+  base[((int64_t)7 * n + me) * 4 + 2] = int_as(T(), flags | kFlagLanded);
+}
 
 #ifdef TB_FF_DIAG
 // log of the last ~100 envs to land: final step count, substeps of the last leg, visits to the servers, where it ended
@@ -680,11 +687,119 @@ __device__ __forceinline__ void ff_diag_late(unsigned long long *ctr, int step, 
   }
 }
 #endif
-// A flight warp.  n0 / qfront: step_kernel's queue (front / back layout); total: envs in flight in this launch.
+
+// The finishing pass for 32 envs (a tile of consecutive envs in pass 1, entries of the retry list in pass 2): complete the
+// env step of those whose flight has landed - reward (swingracket_env.py:111-126, from the contact bits of the final
+// substep), statistics, terminal observation, outputs, auto-reset - coalesced like step_kernel.  Warps run it whenever
+// they have no flight to integrate, so it overlaps the tail of the launch instead of following it.  Pass 1 visits every
+// tile once and lists the envs that were still in flight (collect); pass 2, after the last landing, visits exactly those.
+template <typename T>
+__device__ __noinline__ void ff_finish_dense(const Scene<T> &sc, const StepIO &io, unsigned long long *ctr, int64_t me, bool valid, bool collect,
+                                             WarpStats *wsp) {
+  constexpr int KIND = TB_ENV_SWING;
+  const unsigned full = 0xffffffffu;
+  T *base = static_cast<T *>(io.state);
+  bool fin = false, retry = false;
+  St<T> s;
+  s.step = 0; s.ret = 0;
+  int events = 0;
+  float reward = 0.0f;
+  if (valid) {
+    Pack<T> p7 = ldcg_pack(base, io.n, 7, me);
+    int flags = (int)as_int(p7.z);
+    // pass 2 runs once every landing has been counted; a mark may still be on its way (it is written next to the count)
+    for (int spin = 0; !collect && !(flags & kFlagLanded) && spin < (1 << 20); ++spin) {
+      p7 = ldcg_pack(base, io.n, 7, me);
+      flags = (int)as_int(p7.z);
+    }
+    if (flags & kFlagLanded) {
+      fin = true;
+      __threadfence();  // the mark was written after the state (ff_store)
+      Pack<T> p0 = ldcg_pack(base, io.n, 0, me), p1 = ldcg_pack(base, io.n, 1, me), p2 = ldcg_pack(base, io.n, 2, me),
+              p3 = ldcg_pack(base, io.n, 3, me), p4 = ldcg_pack(base, io.n, 4, me), p5 = ldcg_pack(base, io.n, 5, me),
+              p6 = ldcg_pack(base, io.n, 6, me);
+      s.rp[0] = p0.x; s.rp[1] = p0.y; s.rp[2] = p0.z; s.bp[0] = p0.w;
+      s.rq[0] = p1.x; s.rq[1] = p1.y; s.rq[2] = p1.z; s.rq[3] = p1.w;
+      s.rv[0] = p2.x; s.rv[1] = p2.y; s.rv[2] = p2.z; s.bp[1] = p2.w;
+      s.rw[0] = p3.x; s.rw[1] = p3.y; s.rw[2] = p3.z; s.bp[2] = p3.w;
+      s.bv[0] = p4.x; s.bv[1] = p4.y; s.bv[2] = p4.z; s.bw[0] = p4.w;
+      s.bw[1] = p5.x; s.bw[2] = p5.y; s.aux[0] = p5.z; s.aux[1] = p5.w;
+      s.aux[2] = p6.x; s.goal[0] = p6.y; s.goal[1] = p6.z; s.d0 = p6.w;
+      s.step = (int)as_int(p7.y);
+      s.episode = (uint32_t)as_int(p7.w);
+      events = (flags >> kFlagEventShift) & 0xff;
+      reward = ff_reward(s, (flags >> kFlagLastShift) & 0xff);
+      s.ret = p7.x + (T)reward;
+      s.flags = flags & kFlagDone;  // drop every in-flight mark
+    } else {
+      retry = (flags & kFlagInFlight) != 0;
+    }
+  }
+  account<T>(*wsp, fin, true, 0, events, s.step, s.ret);
+  if (fin) {
+    finish_api<T, KIND>(sc, io, me, s, reward, true, events);
+    store_state(base, io.n, me, s);
+    if (io.pid && io.auto_reset) {
+      T z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      store_pid(static_cast<T *>(io.pid), io.n, me, z);
+    }
+  }
+  if (collect) {
+    const unsigned rm = __ballot_sync(full, retry);
+    if (rm) {
+      unsigned long long at = 0;
+      if (wsp->lane == 0) at = atomicAdd(ctr + kCRetryTail, (unsigned long long)__popc(rm));
+      at = __shfl_sync(full, at, 0);
+      if (retry) io.queue_ctl[at + __popc(rm & ((1u << wsp->lane) - 1u))] = (int)me;
+    }
+  }
+}
+
+// What a warp does when it has no flight to integrate: a piece of the finishing pass.  Returns 0 = nothing to do right
+// now (the caller backs off), 1 = did some, 2 = the launch is complete (every env finished): leave.
+template <typename T>
+__device__ __forceinline__ int ff_finishing_duty(const Scene<T> &sc, const StepIO &io, unsigned long long *ctr, long long nctl, long long total0,
+                                                 WarpStats &ws, bool &pass1_over) {
+  const unsigned full = 0xffffffffu;
+  const int lane = ws.lane;
+  const long long ntiles = (io.n + 31) >> 5;
+  if (!pass1_over) {
+    // (the retry list lives in queue_ctl: not before the prologue has read all of it)
+    if (ld_ctr(ctr + kCCtlDone) < (unsigned long long)nctl) return 0;
+    long long t = 0;
+    if (lane == 0) t = (long long)atomicAdd(ctr + kCFinClaim, 1ULL);
+    t = __shfl_sync(full, t, 0);
+    if (t < ntiles) {
+      const int64_t me = (t << 5) + lane;
+      ff_finish_dense<T>(sc, io, ctr, me, me < io.n, true, &ws);
+      __threadfence();  // retry entries before the count
+      __syncwarp();
+      if (lane == 0) atomicAdd(ctr + kCFinDone, 1ULL);
+      return 1;
+    }
+    pass1_over = true;
+  }
+  if (!ff_all_landed(ctr, nctl, total0) || ld_ctr(ctr + kCFinDone) < (unsigned long long)ntiles) return 0;
+  __threadfence();
+  const long long nretry = (long long)ld_ctr(ctr + kCRetryTail);
+  for (;;) {
+    long long at = 0;
+    if (lane == 0) at = (long long)atomicAdd(ctr + kCRetryClaim, 32ULL);
+    at = __shfl_sync(full, at, 0);
+    if (at >= nretry) break;
+    const bool valid = at + lane < nretry;
+    const int64_t me = valid ? (int64_t)__ldcg(io.queue_ctl + at + lane) : 0;
+    ff_finish_dense<T>(sc, io, ctr, me, valid, false, &ws);
+  }
+  return 2;
+}
+
+// A flight warp.  n0 / qfront: step_kernel's queue (front / back layout); nctl, total0: see ff_all_landed.
 template <typename T>
 __device__ __forceinline__ void ff_flight_warp(const Scene<T> &sc, const StepIO &io, unsigned epoch, long long n0, long long qfront,
-                                               long long total, int lane, int &nsub) {
+                                               long long nctl, long long total0, WarpStats &ws, int &nsub) {
   const unsigned full = 0xffffffffu;
+  const int lane = ws.lane;
   T *base = static_cast<T *>(io.state);
   unsigned long long *ctr = ctr_set(io, epoch - 1u);
   FfLane<T> L;
@@ -697,7 +812,7 @@ __device__ __forceinline__ void ff_flight_warp(const Scene<T> &sc, const StepIO 
   int me = 0, st = kIdle, waited = 0, step0 = 0, visits = 0;
   long long ticket = 0;
   unsigned serves = 0;
-  bool exhausted0 = n0 == 0, first = false, first_pending = false;
+  bool exhausted0 = n0 == 0, first = false, first_pending = false, pass1_over = false;
   long long idle_since = 0;
   unsigned nap = 0;  // idle back-off: thousands of warps polling one cache line would starve the servers' atomics on it
   for (;;) {
@@ -723,32 +838,35 @@ __device__ __forceinline__ void ff_flight_warp(const Scene<T> &sc, const StepIO 
       if (!run_m || __popc(wait_m) >= kServeMin || waited >= kServeWait) break;
     }
     waited = 0;
-    // ---- lanes whose flight left ff_fast: state back to HBM; landed mark, or the full queue
+    // ---- lanes whose flight left ff_fast: state back to HBM; landed mark (ff_fast ends on the court's top face only), or
+    //      the servers' queue
     if (leave_m) {
-      const bool leaving = st == kFfFull || st == kFfDone;
-      if (leaving) {
+      const bool to_full = st == kFfFull, landed = st == kFfDone;
+      int flags = 0;
+      if (to_full || landed) {
         nsub += L.step - step0;
-        int flags = kFlagInFlight | (L.events << kFlagEventShift) | (visits << kFlagVisitShift);
-        if (st == kFfDone) flags |= kFlagLanded | (TB_EV_COURT_BALL << kFlagLastShift);  // ff_fast ends on the court's top face only
+        flags = kFlagInFlight | (L.events << kFlagEventShift) | (visits << kFlagVisitShift);
+        if (landed) flags |= TB_EV_COURT_BALL << kFlagLastShift;
 #ifdef TB_FF_DIAG
-        if (st == kFfDone && ld_ctr(ctr + kCLanded) + 100 >= (unsigned long long)total) ff_diag_late(ctr, L.step, L.step - step0, visits, 0);
+        if (landed && ld_ctr(ctr + kCLanded) + 100 >= (unsigned long long)total0 + ld_ctr(ctr + kCDynTotal)) ff_diag_late(ctr, L.step, L.step - step0, visits, 0);
 #endif
         ff_store(base, io.n, (int64_t)me, L, flags);
       }
-      dq_push(io.dq_full, io.dq_cap, ctr + kCFullTail, epoch, st == kFfFull, me, lane, ctr + kCError);
-      unsigned done_m = __ballot_sync(full, st == kFfDone);
+      dq_push(io.dq_full, io.dq_cap, ctr + kCFullTail, epoch, to_full, me, lane, ctr + kCError);
+      unsigned done_m = __ballot_sync(full, landed);
       if (done_m) {
-        __threadfence();  // landed states before the count
+        __threadfence();  // landed states before the marks and the count
+        if (landed) ff_mark_landed(base, io.n, (int64_t)me, flags);
         if (lane == 0) atomicAdd(ctr + kCLanded, (unsigned long long)__popc(done_m));
       }
-      if (leaving) st = kIdle;
+      if (to_full || landed) st = kIdle;
     }
 #ifdef TB_FF_DIAG
     if (blockIdx.x == 0 && threadIdx.x == 0) {
-      unsigned long long ld = ld_ctr(ctr + kCLanded), t = global_ns();
-      if (!ctr[kDPhase + 1] && ld * 2 >= (unsigned long long)total) ctr[kDPhase + 1] = t;
-      if (!ctr[kDPhase + 2] && ld * 10 >= (unsigned long long)total * 9) ctr[kDPhase + 2] = t;
-      if (!ctr[kDPhase + 3] && ld * 100 >= (unsigned long long)total * 99) ctr[kDPhase + 3] = t;
+      unsigned long long ld = ld_ctr(ctr + kCLanded), t = global_ns(), tot = (unsigned long long)total0 + ld_ctr(ctr + kCDynTotal);
+      if (!ctr[kDPhase + 1] && ld * 2 >= tot) ctr[kDPhase + 1] = t;
+      if (!ctr[kDPhase + 2] && ld * 10 >= tot * 9) ctr[kDPhase + 2] = t;
+      if (!ctr[kDPhase + 3] && ld * 100 >= tot * 99) ctr[kDPhase + 3] = t;
     }
 #endif
     // ---- lanes without an env: the next entries of step_kernel's queue (one atomic per warp); once that is empty, a
@@ -815,14 +933,21 @@ __device__ __forceinline__ void ff_flight_warp(const Scene<T> &sc, const StepIO 
     if (to_full) st = kIdle;
     first_pending = __any_sync(full, first);
     const int got_any = __any_sync(full, got);
-    // ---- nothing to run and nothing to claim: done when every env has landed, else wait for the servers
+    // ---- nothing to run and nothing to claim: a piece of the finishing pass; when there is none, wait for the servers
     if (!run_m && !got_any) {
-      if (ld_ctr(ctr + kCLanded) >= (unsigned long long)total) break;
-      long long now = clock64();
-      if (!idle_since) idle_since = now;
-      if (now - idle_since > kSpinLimit) { atomicExch(ctr + kCError, 4ULL); break; }
-      nap = nap ? min(nap * 2, 32000u) : 1000u;
-      __nanosleep(nap);
+      if (ld_ctr(ctr + kCError) != 0) break;
+      const int duty = ff_finishing_duty<T>(sc, io, ctr, nctl, total0, ws, pass1_over);
+      if (duty == 2) break;
+      if (duty == 1) {
+        idle_since = 0;
+        nap = 0;
+      } else {
+        long long now = clock64();
+        if (!idle_since) idle_since = now;
+        if (now - idle_since > io.spin_limit) { ff_give_up(io, ctr, 4ULL); break; }
+        nap = nap ? min(nap * 2, 32000u) : 1000u;
+        __nanosleep(nap);
+      }
     } else {
       idle_since = 0;
       nap = 0;
@@ -831,13 +956,14 @@ __device__ __forceinline__ void ff_flight_warp(const Scene<T> &sc, const StepIO 
 }
 
 // A server warp: every lane holds one parked env at a time and takes generic substeps with it until ff_fast applies again
-// (or, for an env that keeps coming back, until its env step is over); then it hands the env on and claims the next one.
-// Chains differ wildly in length (one contact step ... a ball rolling on the racket face for the rest of its flight), so
-// lanes are refilled one by one, not batch by batch.
+// (or, for an env that keeps coming back, until its env step is over); then it hands the env on, or completes its env
+// step (ff_finish), and claims the next one.  Chains differ wildly in length (one contact step ... a ball rolling on the
+// racket face for the rest of its flight), so lanes are refilled one by one, not batch by batch.
 template <typename T>
-__device__ __noinline__ void ff_server_warp(const Scene<T> &sc, const StepIO &io, unsigned epoch, long long nfull0, long long total, int lane,
-                                            int *nsub) {
+__device__ __noinline__ void ff_server_warp(const Scene<T> &sc, const StepIO &io, unsigned epoch, long long nfull0, long long nctl,
+                                            long long total0, WarpStats *wsp, int *nsub) {
   const unsigned full = 0xffffffffu;
+  const int lane = wsp->lane;
   T *base = static_cast<T *>(io.state);
   unsigned long long *ctr = ctr_set(io, epoch - 1u);
   bool exhausted0 = nfull0 == 0, busy = false, to_end = false, waiting = false;
@@ -847,6 +973,12 @@ __device__ __noinline__ void ff_server_warp(const Scene<T> &sc, const StepIO &io
   int chain = 0;
 #endif
   FfLane<T> L;
+  {
+    T *z = reinterpret_cast<T *>(&L);
+#pragma unroll
+    for (int i = 0; i < (int)(offsetof(FfLane<T>, step) / sizeof(T)); ++i) z[i] = 0;
+    L.step = 0; L.events = 0;
+  }
   int me = 0, r = kFfDone, phase = 2, last = 0, visits = 0, step0 = 0;
 #ifdef TB_FF_DIAG
   const unsigned long long ts0 = global_ns();
@@ -885,6 +1017,9 @@ __device__ __noinline__ void ff_server_warp(const Scene<T> &sc, const StepIO &io
         if (((cand >> lane) & 1u) && t < io.dq_cap) { ticket = t; waiting = true; }
       }
     }
+#ifdef TB_FF_DIAG
+    const long long tl0 = clock64();
+#endif
     if (got) {
       int flags = ff_load(base, io.n, (int64_t)me, L);
       phase = (flags & kFlagFirst) ? 1 : 2;
@@ -897,12 +1032,15 @@ __device__ __noinline__ void ff_server_warp(const Scene<T> &sc, const StepIO &io
       last = 0;
       r = ff_classify(sc, L);  // fills the lane's squared speeds; kFfFull, rounding apart
       busy = true;
+#ifdef TB_FF_DIAG
+      atomicAdd(ctr + 108, 1ULL); atomicAdd(ctr + 109, (unsigned long long)(clock64() - tl0));
+#endif
     }
-    if (!__any_sync(full, busy)) {  // nothing to do: done when every env has landed
-      if (ld_ctr(ctr + kCLanded) >= (unsigned long long)total) break;
+    if (!__any_sync(full, busy)) {  // nothing to do: done when every flight has landed
+      if (ff_all_landed(ctr, nctl, total0) || ld_ctr(ctr + kCError) != 0) break;
       long long now = clock64();
       if (!idle_since) idle_since = now;
-      if (now - idle_since > kSpinLimit) { atomicExch(ctr + kCError, 5ULL); break; }
+      if (now - idle_since > io.spin_limit) { ff_give_up(io, ctr, 5ULL); break; }
       nap = nap ? min(nap * 2, 4000u) : 500u;
       __nanosleep(nap);
       continue;
@@ -911,6 +1049,7 @@ __device__ __noinline__ void ff_server_warp(const Scene<T> &sc, const StepIO &io
     nap = 0;
     // ---- one substep per busy lane
     bool leave = false;
+    int lflags = 0;
 #ifdef TB_FF_DIAG
     long long tb0 = clock64();
     if (busy) ++chain;
@@ -920,7 +1059,30 @@ __device__ __noinline__ void ff_server_warp(const Scene<T> &sc, const StepIO &io
       atomicAdd(ctr + kDPhase + (r == kFfFull ? 4 : 5), 1ULL);
 #endif
       if (r == kFfFull) {
-        r = ff_full<T>(sc, &L, phase, &last);
+#ifdef TB_FF_DIAG
+        const long long tc0 = clock64();
+#endif
+#ifndef TB_FF_NO_LEAN
+        int rl = ff_contact_lean<T>(sc, &L, phase, &last);  // ball against a racket face, high above the court: the short cut
+#else
+        int rl = -1;
+#endif
+#ifdef TB_FF_DIAG
+        const long long tc1 = clock64();
+        atomicAdd(ctr + (rl < 0 ? 102 : 100), 1ULL); atomicAdd(ctr + (rl < 0 ? 103 : 101), (unsigned long long)(tc1 - tc0));
+#endif
+        if (rl < 0) {
+          rl = ff_full<T>(sc, &L, phase, &last);
+#ifdef TB_FF_DIAG
+          atomicAdd(ctr + 104, (unsigned long long)(clock64() - tc1));
+          if (last & TB_EV_RACKET_BALL) atomicAdd(ctr + 105, 1ULL);
+          if (last & ~(TB_EV_RACKET_BALL | TB_EV_RACKET_LOW)) atomicAdd(ctr + 106, 1ULL);
+#endif
+        }
+#ifdef TB_FF_DIAG
+        else if (last & TB_EV_RACKET_BALL) atomicAdd(ctr + 107, 1ULL);
+#endif
+        r = rl;
       } else {  // (to_end, or a rounding-level disagreement with the classification that queued the env)
         if (phase == 1) {  // the force-free first substep (see ff_flight_warp)
           const T t0 = L.tgt[0], t1 = L.tgt[1], t2 = L.tgt[2];
@@ -929,8 +1091,7 @@ __device__ __noinline__ void ff_server_warp(const Scene<T> &sc, const StepIO &io
           L.tgt[0] = t0; L.tgt[1] = t1; L.tgt[2] = t2;
         } else {
           // an env that is finished here (to_end) takes its contact-free substeps in one go: a server iteration lasts as
-          // long as the slowest generic substep among the warp's lanes (15-40 us), and the last env of a launch used
-          // to crawl through the end of its flight at one substep per iteration (0.4 ms of a 2.4 ms launch)
+          // long as the slowest generic substep among the warp's lanes
           do r = ff_fast<T>(sc, L, r); while (to_end && r <= kFfLand);
         }
         last = TB_EV_COURT_BALL;  // if this was the last one: ff_fast ends on the court's top face only
@@ -939,12 +1100,12 @@ __device__ __noinline__ void ff_server_warp(const Scene<T> &sc, const StepIO &io
       leave = r == kFfDone || (r != kFfFull && !to_end);
       if (leave) {
         *nsub += L.step - step0;
-        int flags = kFlagInFlight | (L.events << kFlagEventShift) | (visits << kFlagVisitShift);
-        if (r == kFfDone) flags |= kFlagLanded | (last << kFlagLastShift);
 #ifdef TB_FF_DIAG
-        if (r == kFfDone && ld_ctr(ctr + kCLanded) + 100 >= (unsigned long long)total) ff_diag_late(ctr, L.step, L.step - step0, visits, 1 + (to_end ? 1 : 0));
+        if (r == kFfDone && ld_ctr(ctr + kCLanded) + 100 >= (unsigned long long)total0 + ld_ctr(ctr + kCDynTotal)) ff_diag_late(ctr, L.step, L.step - step0, visits, 1 + (to_end ? 1 : 0));
 #endif
-        ff_store(base, io.n, (int64_t)me, L, flags);
+        lflags = kFlagInFlight | (L.events << kFlagEventShift) | (visits << kFlagVisitShift);
+        if (r == kFfDone) lflags |= last << kFlagLastShift;
+        ff_store(base, io.n, (int64_t)me, L, lflags);
         busy = false;
 #ifdef TB_FF_DIAG
         atomicMax(ctr + kDPhase + 8, (unsigned long long)chain);
@@ -968,114 +1129,119 @@ __device__ __noinline__ void ff_server_warp(const Scene<T> &sc, const StepIO &io
       }
     }
 #endif
+    const bool landed = leave && r == kFfDone;
     dq_push(io.dq_late, io.dq_cap, ctr + kCLateTail, epoch, leave && r != kFfDone, me, lane, ctr + kCError);
-    unsigned done_m = __ballot_sync(full, leave && r == kFfDone);
+    unsigned done_m = __ballot_sync(full, landed);
     if (done_m) {
-      __threadfence();
+      __threadfence();  // landed states before the marks and the count
+      if (landed) ff_mark_landed(base, io.n, (int64_t)me, lflags);
       if (lane == 0) atomicAdd(ctr + kCLanded, (unsigned long long)__popc(done_m));
     }
   }
 }
 
-// The finishing pass for one warp-tile of 32 consecutive envs: complete the env step of those that landed.
+// ff_kernel's prologue: the control-phase substeps step_kernel deferred (ball within reach of something, PID mode, ...)
+// through the generic path, 32 entries of queue_ctl per warp at a time (claimed, so a CTA that becomes resident late
+// finds nothing left and no CTA waits for another).  An env whose 26th step this was joins the flights through the
+// dynamic queues.  Out of line: the generic step's registers and spills stay out of the flight loop.
 template <typename T>
-__device__ __noinline__ void ff_phase_finish(const Scene<T> &sc, const StepIO &io, int64_t tile0, WarpStats *wsp) {
+__device__ __noinline__ void ff_prologue(const Scene<T> &sc, const StepIO &io, unsigned epoch, unsigned long long *ctr, long long nctl, WarpStats *wsp) {
   constexpr int KIND = TB_ENV_SWING;
+  const unsigned full = 0xffffffffu;
+  const int lane = wsp->lane;
   T *base = static_cast<T *>(io.state);
-  const int64_t me = tile0 + wsp->lane;
-  bool fin = false;
-  St<T> s;
-  s.step = 0; s.ret = 0;
-  int events = 0;
-  float reward = 0.0f;
-  if (me < io.n) {
-    Pack<T> p7 = ldcg_pack(base, io.n, 7, me);
-    int flags = (int)as_int(p7.z);
-    if (flags & kFlagLanded) {
-      fin = true;
-      Pack<T> p0 = ldcg_pack(base, io.n, 0, me), p1 = ldcg_pack(base, io.n, 1, me), p2 = ldcg_pack(base, io.n, 2, me),
-              p3 = ldcg_pack(base, io.n, 3, me), p4 = ldcg_pack(base, io.n, 4, me), p5 = ldcg_pack(base, io.n, 5, me),
-              p6 = ldcg_pack(base, io.n, 6, me);
-      s.rp[0] = p0.x; s.rp[1] = p0.y; s.rp[2] = p0.z; s.bp[0] = p0.w;
-      s.rq[0] = p1.x; s.rq[1] = p1.y; s.rq[2] = p1.z; s.rq[3] = p1.w;
-      s.rv[0] = p2.x; s.rv[1] = p2.y; s.rv[2] = p2.z; s.bp[1] = p2.w;
-      s.rw[0] = p3.x; s.rw[1] = p3.y; s.rw[2] = p3.z; s.bp[2] = p3.w;
-      s.bv[0] = p4.x; s.bv[1] = p4.y; s.bv[2] = p4.z; s.bw[0] = p4.w;
-      s.bw[1] = p5.x; s.bw[2] = p5.y; s.aux[0] = p5.z; s.aux[1] = p5.w;
-      s.aux[2] = p6.x; s.goal[0] = p6.y; s.goal[1] = p6.z; s.d0 = p6.w;
-      s.step = (int)as_int(p7.y);
-      s.episode = (uint32_t)as_int(p7.w);
-      events = (flags >> kFlagEventShift) & 0xff;
-      reward = ff_reward(s, (flags >> kFlagLastShift) & 0xff);
-      s.ret = p7.x + (T)reward;
-      s.flags = flags & kFlagDone;  // drop every in-flight mark
-    }
-  }
-  account<T>(*wsp, fin, true, 0, events, s.step, s.ret);
-  if (fin) {
-    finish_api<T, KIND>(sc, io, me, s, reward, true, events);
-    store_state(base, io.n, me, s);
-    if (io.pid && io.auto_reset) {
-      T z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-      store_pid(static_cast<T *>(io.pid), io.n, me, z);
-    }
-  }
-}
-
-// ff_kernel's prologue for one CTA (out of line: the generic step's registers and spills stay out of the flight loop)
-template <typename T>
-__device__ __noinline__ void ff_prologue(const Scene<T> &sc, const StepIO &io, unsigned long long *ctr, long long nctl, WarpStats *wsp,
-                                         int *s_cnt, unsigned long long *s_base, float *s_dummy) {
-  for (long long b0 = (long long)blockIdx.x * kBlock; b0 < nctl; b0 += (long long)gridDim.x * kBlock) {
-    const long long idx = b0 + threadIdx.x;
-    const bool valid = idx < nctl;
-    const int64_t me = valid ? (int64_t)io.queue_ctl[idx] : 0;
+  for (;;) {
+    long long at = 0;
+    if (lane == 0) at = (long long)atomicAdd(ctr + kCCtlClaim, 32ULL);
+    at = __shfl_sync(full, at, 0);
+    if (at >= nctl) break;
+    const bool valid = at + lane < nctl;
+    const int me = valid ? __ldcg(io.queue_ctl + at + lane) : 0;
     St<T> s;
-    float a[8];
+    s.step = 0; s.ret = 0;
+    StepCtl c = {0, 0, 0, 0.0f, false, 0};
+    bool fin = false;
+    T spin1 = 0, spin2 = 0;
+    uint32_t episode0 = 0;
     if (valid) {
-      load_state(static_cast<const T *>(io.state), io.n, me, s);
-      load_action<TB_ENV_SWING>(io.actions, me, a);
+      float a[8];
+      load_state(static_cast<const T *>(io.state), io.n, (int64_t)me, s);
+      load_action<KIND>(io.actions, (int64_t)me, a);
+      spin1 = s.bw[1]; spin2 = s.bw[2]; episode0 = s.episode;
+      c.done = s.flags & kFlagDone;
+      if (TB_UNLIKELY(io.pid != nullptr)) {
+        T pid[8];
+        load_pid(static_cast<const T *>(io.pid), io.n, (int64_t)me, pid);
+        fin = env_substep<T, KIND>(sc, s, a, c, pid);
+        if (fin && c.done && io.auto_reset) {  // reset() builds a new Racket, hence fresh controllers
+#pragma unroll
+          for (int j = 0; j < 8; ++j) pid[j] = 0;
+        }
+        store_pid(static_cast<T *>(io.pid), io.n, (int64_t)me, pid);
+      } else {
+        fin = env_substep<T, KIND>(sc, s, a, c);
+      }
+      if (fin) s.ret += (T)c.reward;
     }
-    step_tile<T, TB_ENV_SWING, false, false>(sc, io, ctr, 0, me, 0, valid, s, a, *wsp, s_cnt, s_base, s_dummy);
+    const unsigned valid_m = __ballot_sync(full, valid);
+    if (lane == 0) wsp->acc[TB_STAT_PHYSICS_STEPS] += __popc(valid_m);
+    account<T>(*wsp, fin, c.done, c.hit, c.events, s.step, s.ret);
+    if (valid && fin) finish_api<T, KIND>(sc, io, (int64_t)me, s, c.reward, c.done, c.events);
+    // an env that enters the fast-forward here: to the servers if its first substep is a full one, else to the flights
+    const bool queued = valid && !fin;
+    bool to_full = false;
+    if (queued) {
+      to_full = ff_classify_state(sc, s) == kFfFull;
+      s.flags = (s.flags & ~(0xff << kFlagEventShift)) | kFlagInFlight | kFlagFirst | (c.events << kFlagEventShift);
+    }
+    if (valid) {
+      const bool restarted = s.episode != episode0;
+      store_state_changed(base, io.n, (int64_t)me, s, restarted || s.bw[1] != spin1 || s.bw[2] != spin2, restarted);
+    }
+    dq_push(io.dq_full, io.dq_cap, ctr + kCFullTail, epoch, to_full, me, lane, ctr + kCError);
+    dq_push(io.dq_late, io.dq_cap, ctr + kCLateTail, epoch, queued && !to_full, me, lane, ctr + kCError);
+    const unsigned queued_m = __ballot_sync(full, queued);
+    __threadfence();  // results and queue entries before the counts
+    if (lane == 0) {
+      if (queued_m) atomicAdd(ctr + kCDynTotal, (unsigned long long)__popc(queued_m));
+      __threadfence();
+      atomicAdd(ctr + kCCtlDone, (unsigned long long)__popc(valid_m));
+    }
   }
 }
 
 template <typename T>
 __global__ void __launch_bounds__(kBlock, MinBlocks<T>::v) ff_kernel(const __grid_constant__ Scene<T> sc, const __grid_constant__ StepIO io) {
   __shared__ unsigned long long sacc[kBlock / 32][TB_NUM_STATS];
-  __shared__ int s_cnt[3 * (kBlock / 32)];
-  __shared__ unsigned long long s_base[3];
-  __shared__ float s_dummy[4];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   pdl_wait();
   const unsigned epoch = io.epoch[1];  // this step's tag, written by its step_kernel; the step's index is epoch - 1
   if (blockIdx.x == 0 && threadIdx.x == 0) io.epoch[0] = epoch == kEpochLast ? 0u : epoch;  // (read by the next step_kernel only)
   unsigned long long *ctr = ctr_set(io, epoch - 1u);
-  const long long nctl = (long long)ctr[kCCtl];  // (written by step_kernel, same stream)
-  if (nctl == 0 && ctr[kCFront] + ctr[kCBack] + ctr[kCFull0] == 0) return;
+  // (all four written by step_kernel, same stream)
+  const long long nctl = (long long)ctr[kCCtl], qfront = (long long)ctr[kCFront], qn0 = qfront + (long long)ctr[kCBack], nfull0 = (long long)ctr[kCFull0];
+  const long long total0 = qn0 + nfull0;
+  if (nctl == 0 && total0 == 0) return;
   WarpStats ws;
   ws.init(sacc[wib], lane);
-  // ---- prologue: the control-phase substeps step_kernel deferred (ball within reach of something, PID mode, ...),
-  //      gathered into dense warps and taken through the generic path; those that were an env's 26th step join the
-  //      queues below, hence the grid barrier
-  if (nctl) {
-    ff_prologue<T>(sc, io, ctr, nctl, &ws, s_cnt, s_base, s_dummy);
-    if (!grid_barrier(ctr)) {
-      if (threadIdx.x == 0) atomicExch(io.fault, 6ULL);
-      ws.flush(io.stats);
-      return;
-    }
-  }
-  const long long qfront = (long long)ld_ctr(ctr + kCFront);  // queued envs
-  const long long qn0 = qfront + (long long)ld_ctr(ctr + kCBack), nfull0 = (long long)ld_ctr(ctr + kCFull0);
-  const long long total = qn0 + nfull0;
-  if (total == 0) { ws.flush(io.stats); return; }
+  // No CTA ever waits for a particular other CTA: all work - deferred control substeps, flights, parked envs - is claimed
+  // from counters and queues, so the launch completes whichever CTAs are resident when (another stream may hold SMs).
+  if (nctl) ff_prologue<T>(sc, io, epoch, ctr, nctl, &ws);
   int nsub = 0;  // substeps this lane integrated
   const bool diag = blockIdx.x == 0 && threadIdx.x == 0;  // times as this CTA's first warp sees them
   unsigned long long t_mark = diag ? global_ns() : 0;
-  const bool server = wib == kBlock / 32 - 1 && blockIdx.x % kServerStride == 0;
-  if (server) ff_server_warp<T>(sc, io, epoch, nfull0, total, lane, &nsub);
-  else ff_flight_warp<T>(sc, io, epoch, qn0, qfront, total, lane, nsub);
+  // Roles.  The generic substep is ~3000 instructions of code and constants that no flight warp needs, and a chain of
+  // dependent FP64 operations that crawls when it shares a scheduler with three flight warps that keep the FP64 pipe full.
+  // A full persistent grid therefore gives whole SMs to the servers (every warp of every CTA that runs there), chosen by
+  // %smid; a grid that does not fill the device keeps one server warp per kServerStride CTAs.
+  bool server = wib == kBlock / 32 - 1 && blockIdx.x % kServerStride == 0;
+  if (io.server_sm_stride > 0) {
+    unsigned smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    server = smid % (unsigned)io.server_sm_stride == 0;
+  }
+  if (server) ff_server_warp<T>(sc, io, epoch, nfull0, nctl, total0, &ws, &nsub);
+  else ff_flight_warp<T>(sc, io, epoch, qn0, qfront, nctl, total0, ws, nsub);
   if (diag) {
     unsigned long long t = global_ns();
 #ifdef TB_FF_DIAG
@@ -1084,19 +1250,12 @@ __global__ void __launch_bounds__(kBlock, MinBlocks<T>::v) ff_kernel(const __gri
     ctr[kDPhase + 11] = ctr[kDPhase + 11] ? ctr[kDPhase + 11] - t_mark : 0;
 #endif
     ctr[kDPhase] = t - t_mark;
-    t_mark = t;
     ctr[kDRounds] = 1;
     ctr[kDFullEnvs] = ld_ctr(ctr + kCFullTail) + (unsigned long long)nfull0;
+    ctr[kDFinish] = 0;
   }
-  if (ld_ctr(ctr + kCError) != 0 && threadIdx.x == 0) atomicExch(io.fault, ld_ctr(ctr + kCError));
-  if (ld_ctr(ctr + kCError) == 0) {  // every env has landed, and their states are visible (fence before the count)
-    __threadfence();
-    nsub = __reduce_add_sync(0xffffffffu, nsub);
-    if (lane == 0) ws.acc[TB_STAT_PHYSICS_STEPS] += nsub;
-    const int64_t stride = (int64_t)gridDim.x * kBlock;
-    for (int64_t tile0 = (int64_t)blockIdx.x * kBlock + wib * 32; tile0 < io.n; tile0 += stride) ff_phase_finish<T>(sc, io, tile0, &ws);
-    if (diag) ctr[kDFinish] = global_ns() - t_mark;
-  }
+  nsub = __reduce_add_sync(0xffffffffu, nsub);
+  if (lane == 0) ws.acc[TB_STAT_PHYSICS_STEPS] += nsub;
   ws.flush(io.stats);
 }
 
@@ -1273,18 +1432,94 @@ static void params_default(Params &p) {
   p.pid_hit_z = 1.5;     // tennisbot_env.py:106
 }
 
-template <typename T, int NE> static void build_prism(Prism<T, NE> &pr, const double (*v)[2], double half_thick) {
-  double r2 = 0;
+// quad_edges: indices of the two outline edges that bound the quadrilateral of prism_inside_fast (its other two sides
+// are the lines v = the lower and the upper end of those edges), or nullptr.  Both regions are verified against every edge
+// line here and dropped if they do not clear them all.
+template <typename T, int NE> static void build_prism(Prism<T, NE> &pr, const double (*v)[2], double half_thick, const int *quad_edges) {
+  double r2 = 0, nx[NE], ny[NE];
   for (int i = 0; i < NE; ++i) {
     const double *a = v[i], *b = v[(i + 1) % NE];
     double ex = b[0] - a[0], ey = b[1] - a[1], l2 = ex * ex + ey * ey, il = 1.0 / std::sqrt(l2);
     pr.e[i].ax = (T)a[0]; pr.e[i].ay = (T)a[1]; pr.e[i].ex = (T)ex; pr.e[i].ey = (T)ey;
     pr.e[i].inv_len2 = (T)(1.0 / l2); pr.e[i].nx = (T)(ey * il); pr.e[i].ny = (T)(-ex * il);
+    nx[i] = ey * il; ny[i] = -ex * il;
     double d2 = a[0] * a[0] + a[1] * a[1] + half_thick * half_thick;
     if (d2 > r2) r2 = d2;
   }
   pr.half_thick = (T)half_thick;
   pr.bound_radius = (T)std::sqrt(r2);
+  const double shrink = sizeof(T) == 8 ? 1.0 - 1e-9 : 1.0 - 1e-4;
+  {
+    // ellipse: centred where the outline is widest (above the quadrilateral, if there is one), semi-axes out to the widest
+    // point and up to the top, then scaled about its centre until it lies inside every edge's half plane
+    double vlo = -1e30;
+    if (quad_edges) vlo = std::fmax(std::fmax(v[quad_edges[0]][1], v[(quad_edges[0] + 1) % NE][1]), std::fmax(v[quad_edges[1]][1], v[(quad_edges[1] + 1) % NE][1]));
+    double a0 = 0, c = 0, top = -1e30;
+    for (int i = 0; i < NE; ++i) {
+      if (v[i][1] < vlo) continue;
+      if (std::fabs(v[i][0]) > a0) { a0 = std::fabs(v[i][0]); c = v[i][1]; }
+      top = std::fmax(top, v[i][1]);
+    }
+    double b0 = top - c, s = 1e30;
+    if (!(b0 > 0)) { b0 = a0; c = 0; }  // (a polygon symmetric about u as well, e.g. the goal's 32-gon: a circle)
+    for (int i = 0; i < NE; ++i) {
+      double off = (v[i][0] - 0.0) * nx[i] + (v[i][1] - c) * ny[i];
+      double sup = std::sqrt(a0 * nx[i] * a0 * nx[i] + b0 * ny[i] * b0 * ny[i]);
+      s = std::fmin(s, off / sup);
+    }
+    if (s > 0) {
+      pr.in_c = (T)c; pr.in_inv_a = (T)(1.0 / (a0 * s * shrink)); pr.in_inv_b = (T)(1.0 / (b0 * s * shrink));
+    } else {  // never inside
+      pr.in_c = 0; pr.in_inv_a = (T)1e30; pr.in_inv_b = (T)1e30;
+    }
+    // the containing ellipse of the vertices at or above vlo (same centre and aspect), for prism_outside_fast
+    double so = 0;
+    for (int i = 0; i < NE; ++i) {
+      if (v[i][1] < vlo) continue;
+      double du = v[i][0] / a0, dv = (v[i][1] - c) / b0;
+      so = std::fmax(so, std::sqrt(du * du + dv * dv));
+    }
+    pr.out_a = (T)(a0 * so / shrink); pr.out_b = (T)(b0 * so / shrink);
+    pr.out_v = (T)vlo; pr.out_lo = (T)-1e30;
+    pr.out_inv_a = pr.out_inv_b = 0;  // (set by build_scene once the rim is known)
+  }
+  pr.tz_lo = 1; pr.tz_hi = 0;
+  for (int k = 0; k < 2; ++k) { pr.t_ax[k] = pr.t_ay[k] = 0; pr.t_nx[k] = pr.t_ny[k] = 0; }
+  if (quad_edges) {
+    const int e0 = quad_edges[0], e1 = quad_edges[1];
+    double lo = std::fmax(std::fmin(v[e0][1], v[(e0 + 1) % NE][1]), std::fmin(v[e1][1], v[(e1 + 1) % NE][1]));
+    double hi = std::fmin(std::fmax(v[e0][1], v[(e0 + 1) % NE][1]), std::fmax(v[e1][1], v[(e1 + 1) % NE][1]));
+    const double eps = (hi - lo) * (1.0 - shrink);
+    lo += eps; hi -= eps;
+    // corners of the region: where the two edge lines meet v = lo and v = hi; all four must lie inside every edge line
+    bool ok = hi > lo;
+    for (int k = 0; k < 2 && ok; ++k) {
+      const int e = quad_edges[k];
+      for (int j = 0; j < 2 && ok; ++j) {
+        const double vv = j ? hi : lo;
+        if (std::fabs(nx[e]) < 1e-12) { ok = false; break; }
+        const double uu = v[e][0] - (vv - v[e][1]) * ny[e] / nx[e];  // on the edge's line
+        for (int i = 0; i < NE; ++i) ok = ok && (uu - v[i][0]) * nx[i] + (vv - v[i][1]) * ny[i] <= 1e-12;
+      }
+    }
+    if (!ok) {  // no usable quadrilateral: the ellipse has to contain every vertex
+      double so = 0;
+      const double a0 = (double)pr.out_a, b0 = (double)pr.out_b, c = (double)pr.in_c;
+      for (int i = 0; i < NE; ++i) {
+        double du = v[i][0] / a0, dv = (v[i][1] - c) / b0;
+        so = std::fmax(so, std::sqrt(du * du + dv * dv));
+      }
+      if (so > 1) { pr.out_a = (T)(a0 * so / shrink); pr.out_b = (T)(b0 * so / shrink); }
+    }
+    if (ok) {
+      pr.out_lo = (T)std::fmin(std::fmin(v[e0][1], v[(e0 + 1) % NE][1]), std::fmin(v[e1][1], v[(e1 + 1) % NE][1]));
+      pr.tz_lo = (T)lo; pr.tz_hi = (T)hi;
+      for (int k = 0; k < 2; ++k) {
+        const int e = quad_edges[k];
+        pr.t_ax[k] = (T)v[e][0]; pr.t_ay[k] = (T)v[e][1]; pr.t_nx[k] = (T)nx[e]; pr.t_ny[k] = (T)ny[e];
+      }
+    }
+  }
 }
 
 struct HostScene {  // double-precision master copy; Scene<T> is derived from it
@@ -1350,7 +1585,12 @@ template <typename T> static void build_scene(const Params &p, Scene<T> &sc) {
   sc.floor_h[0] = (T)TB_FLOOR_HX; sc.floor_h[1] = (T)TB_FLOOR_HY; sc.floor_h[2] = (T)TB_FLOOR_HZ;
   sc.net_h[0] = (T)TB_NET_HX; sc.net_h[1] = (T)TB_NET_HY; sc.net_h[2] = (T)TB_NET_HZ;
   sc.goal_r = (T)TB_GOAL_RADIUS; sc.goal_hz = (T)TB_GOAL_HALF_Z;
-  build_prism<T, kRacketEdges>(sc.racket, h.racket_v, h.racket_half_x);
+  {
+    // the racket's throat: the two long straight outline edges that run from the handle end up to the head (the edges
+    // after vertex 0 and before the last vertex in the CCW outline, tb_scene_data.h)
+    const int quad[2] = {0, kRacketEdges - 2};
+    build_prism<T, kRacketEdges>(sc.racket, h.racket_v, h.racket_half_x, quad);
+  }
   {
     double ay = 0, zlo = 1e30, zhi = -1e30;
     for (int i = 0; i < kRacketEdges; ++i) {
@@ -1364,7 +1604,7 @@ template <typename T> static void build_scene(const Params &p, Scene<T> &sc) {
     double zm = std::fmax(std::fabs(zlo), std::fabs(zhi));
     sc.racket_obb_radius = (T)(std::sqrt(h.racket_half_x * h.racket_half_x + ay * ay + zm * zm) * (1 + 1e-6));
   }
-  build_prism<T, kGoalEdges>(sc.goal, h.goal_v, TB_GOAL_HALF_Z);
+  build_prism<T, kGoalEdges>(sc.goal, h.goal_v, TB_GOAL_HALF_Z, nullptr);
   {
     // fast-forward substep constants (ff_substep).  The three rejects are grown a little: they may only send a
     // substep into the exact tests for nothing, never past them.
@@ -1405,6 +1645,8 @@ template <typename T> static void build_scene(const Params &p, Scene<T> &sc) {
     sc.ffp_box[0] = (T)((double)sc.racket_box[0] + reach_r + grow); sc.ffp_box[1] = (T)((double)sc.racket_box[1] - reach_r - grow);
     sc.ffp_box[2] = (T)((double)sc.racket_box[2] + reach_r + grow);
     sc.ffp_rim = (T)(reach_r + grow);
+    sc.racket.out_inv_a = (T)((1.0 - 1e-9) / ((double)sc.racket.out_a + (double)sc.ffp_rim));
+    sc.racket.out_inv_b = (T)((1.0 - 1e-9) / ((double)sc.racket.out_b + (double)sc.ffp_rim));
     sc.ffl_inv_dt = (T)(1.0 / p.dt); sc.ffl_erp_dt = (T)(p.contact_erp / p.dt); sc.ffl_m = (T)TB_BALL_MASS;
     sc.ffl_jinv_t = (T)(1.0 / (1.0 / TB_BALL_MASS + TB_BALL_RADIUS * TB_BALL_RADIUS / (0.4 * TB_BALL_MASS * TB_BALL_RADIUS * TB_BALL_RADIUS)));
     sc.ffp_court[0] = sc.floor_h[0] + 1; sc.ffp_court[1] = sc.floor_h[1] + 1;
@@ -1450,8 +1692,12 @@ struct tb_ctx {
   long long dq_cap = 0;
   unsigned *epoch = nullptr;                 // device word, see StepIO
   unsigned long long *fault = nullptr;       // device word, see StepIO
+  unsigned long long *h_fault = nullptr;     // the same word in mapped host memory (checked on entry of every call, no sync)
+  unsigned long long *h_fault_dev = nullptr; // its device alias
+  long long spin_limit = 0;                  // clock cycles, see StepIO (TB_FF_SPIN_LIMIT_MS, default 4000 ms)
   unsigned long long *queue_ctrs = nullptr;  // two counter sets (kCtrWords each) used by alternate steps
   unsigned ff_grid = 0;                      // persistent grid of ff_kernel
+  int ff_server_sm_stride = 0;               // see StepIO (set with the grid size; TB_FF_SERVER_SM_STRIDE overrides, 0 = per-CTA roles)
   int step_resident = -1;                    // resident CTAs of step_kernel (its L2 prefetch distance)
   bool one_wave4 = false;                    // Tennisbot-v0: launch the 4-CTAs-per-SM build of step_kernel (see its MINB)
   bool pdl = std::getenv("TB_NO_PDL") == nullptr;  // programmatic dependent launch of the step's kernels
@@ -1475,6 +1721,15 @@ struct DeviceGuard {
   DeviceGuard guard_((ctx)->cfg.device);                         \
   if (!guard_.ok) return fail("%s", "cudaSetDevice failed")
 
+// A fast-forward launch of this context gave up on a wait (ff_give_up): its batch state is incomplete.  Sticky; every
+// later call fails loudly instead of handing stale observations on.
+static int check_fault(tb_ctx *c, const char *who) {
+  const unsigned long long f = c->h_fault ? *reinterpret_cast<volatile unsigned long long *>(c->h_fault) : 0ULL;
+  if (!f) return 0;
+  std::snprintf(g_err, sizeof g_err, "%s: an earlier fast-forward launch of this context timed out waiting on its work queues (code %llu); "
+                "the batch state is incomplete - destroy the context", who, f);
+  return 1;
+}
 static void rebuild(tb_ctx *c) {
   build_scene<float>(c->params, c->sc32);
   build_scene<double>(c->params, c->sc64);
@@ -1520,6 +1775,11 @@ template <typename T> static int ff_grid_size(tb_ctx *c, unsigned *grid) {
   int64_t resident = (int64_t)sms * (per_sm > 0 ? per_sm : 1);
   int64_t need = (c->cfg.num_envs + kBlock - 1) / kBlock;
   *grid = (unsigned)(need < resident ? need : resident);
+  {
+    const char *e = std::getenv("TB_FF_SERVER_SM_STRIDE");
+    int stride = e ? std::atoi(e) : 8;
+    c->ff_server_sm_stride = (need >= resident && stride > 0 && stride <= sms) ? stride : 0;
+  }
   return 0;
 }
 // CTAs of step_kernel that are resident at a time = how far ahead its L2 prefetch reaches.
@@ -1549,7 +1809,8 @@ static cudaError_t launch_pdl(bool pdl, void (*kernel)(KArgs...), unsigned grid,
 // One env step = step_kernel (+ ff_kernel for SwingRacket) on `stream`.
 static int launch_step(tb_ctx *c, StepIO &io, cudaStream_t stream, bool stage = false) {
   io.queue = c->queue; io.queue_full = c->queue_full; io.queue_ctl = c->queue_ctl;
-  io.fault = c->fault;
+  io.fault = c->fault; io.fault_host = c->h_fault_dev; io.spin_limit = c->spin_limit;
+  io.server_sm_stride = c->ff_server_sm_stride;
   io.dq_full = c->dq; io.dq_late = c->dq ? c->dq + c->dq_cap : nullptr; io.dq_cap = c->dq_cap;
   io.epoch = c->epoch;  // (a slot written 2^32 steps ago with the same tag would have to survive untouched)
   io.queue_ctrs = c->queue_ctrs;
@@ -1585,9 +1846,11 @@ static int launch_step(tb_ctx *c, StepIO &io, cudaStream_t stream, bool stage = 
   if (swing) {
     if (c->cfg.precision == TB_F64) {
       if (!c->ff_grid && ff_grid_size<double>(c, &c->ff_grid)) return 1;
+      io.server_sm_stride = c->ff_server_sm_stride;
       CU(launch_pdl(c->pdl, ff_kernel<double>, c->ff_grid, stream, c->sc64, io));
     } else {
       if (!c->ff_grid && ff_grid_size<float>(c, &c->ff_grid)) return 1;
+      io.server_sm_stride = c->ff_server_sm_stride;
       CU(launch_pdl(c->pdl, ff_kernel<float>, c->ff_grid, stream, c->sc32, io));
     }
     c->launches++;
@@ -1632,6 +1895,21 @@ int tb_scene_constant(const char *name, int index, double *value) {
   if (!std::strcmp(name, "racket_outline_z") && index >= 0 && index < kRacketEdges) { *value = TB_RACKET_OUTLINE[index][1]; return 0; }
   if (!std::strcmp(name, "goal_vertex_x") && index >= 0 && index < kGoalEdges) { *value = h.goal_v[index][0]; return 0; }
   if (!std::strcmp(name, "goal_vertex_y") && index >= 0 && index < kGoalEdges) { *value = h.goal_v[index][1]; return 0; }
+  {  // regions of prism_inside_fast (COM frame), for the unit test that checks them against the outline
+    static Scene<double> sd;  // (4 KB: not on the stack)
+    build_scene<double>(p, sd);
+    const double in_r[5] = {sd.racket.in_c, 1.0 / sd.racket.in_inv_a, 1.0 / sd.racket.in_inv_b, sd.racket.tz_lo, sd.racket.tz_hi};
+    const double in_g[5] = {sd.goal.in_c, 1.0 / sd.goal.in_inv_a, 1.0 / sd.goal.in_inv_b, sd.goal.tz_lo, sd.goal.tz_hi};
+    const double out_r[4] = {sd.racket.out_a, sd.racket.out_b, sd.racket.out_v, sd.racket.out_lo};
+    if (!std::strcmp(name, "racket_outside") && index >= 0 && index < 4) { *value = out_r[index]; return 0; }
+    if (!std::strcmp(name, "racket_inside") && index >= 0 && index < 5) { *value = in_r[index]; return 0; }
+    if (!std::strcmp(name, "goal_inside") && index >= 0 && index < 5) { *value = in_g[index]; return 0; }
+    if (!std::strcmp(name, "racket_quad_edge") && index >= 0 && index < 8) {
+      const double q[8] = {sd.racket.t_ax[0], sd.racket.t_ay[0], sd.racket.t_nx[0], sd.racket.t_ny[0], sd.racket.t_ax[1], sd.racket.t_ay[1], sd.racket.t_nx[1], sd.racket.t_ny[1]};
+      *value = q[index];
+      return 0;
+    }
+  }
   return fail("tb_scene_constant: unknown name or index '%s'", name);
 }
 
@@ -1679,6 +1957,14 @@ int tb_create(const tb_config *cfg, tb_ctx **out) {
   if (e == cudaSuccess) e = cudaMemsetAsync(c->queue_ctrs, 0, 2 * kCtrWords * sizeof(unsigned long long), c->own_stream);
   if (e == cudaSuccess) e = cudaMalloc(&c->fault, sizeof(unsigned long long));
   if (e == cudaSuccess) e = cudaMemsetAsync(c->fault, 0, sizeof(unsigned long long), c->own_stream);
+  if (e == cudaSuccess) e = cudaHostAlloc((void **)&c->h_fault, sizeof(unsigned long long), cudaHostAllocMapped);
+  if (e == cudaSuccess) { *c->h_fault = 0; e = cudaHostGetDevicePointer((void **)&c->h_fault_dev, c->h_fault, 0); }
+  {
+    const char *ms = std::getenv("TB_FF_SPIN_LIMIT_MS");
+    double limit_ms = ms ? std::atof(ms) : 4000.0;
+    if (!(limit_ms > 0)) limit_ms = 4000.0;
+    c->spin_limit = (long long)(limit_ms * 1e-3 * (double)prop.clockRate * 1e3);  // clockRate is in kHz
+  }
   if (e == cudaSuccess) e = cudaMalloc(&c->epoch, 2 * sizeof(unsigned));
   if (e == cudaSuccess) e = cudaMemsetAsync(c->epoch, 0, 2 * sizeof(unsigned), c->own_stream);
   if (e == cudaSuccess && c->dq) e = cudaMemsetAsync(c->dq, 0, (size_t)c->dq_cap * 2 * sizeof(unsigned long long), c->own_stream);  // tag 0 = no epoch
@@ -1718,6 +2004,7 @@ int tb_destroy(tb_ctx *c) {
   if (c->own_stream) { cudaStreamSynchronize(c->own_stream); cudaStreamDestroy(c->own_stream); }
   for (int i = 0; i < 3; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
   cudaFree(c->state); cudaFree(c->stats); cudaFree(c->queue_ctrs); cudaFree(c->queue); cudaFree(c->dq); cudaFree(c->epoch); cudaFree(c->fault); cudaFree(c->queue_full); cudaFree(c->queue_ctl); cudaFree(c->pid);
+  if (c->h_fault) cudaFreeHost(c->h_fault);
   cudaFree(c->d_actions); cudaFree(c->d_obs); cudaFree(c->d_reward); cudaFree(c->d_term);
   cudaFree(c->d_done); cudaFree(c->d_events); cudaFree(c->d_mask);
   delete c;
@@ -1745,6 +2032,7 @@ int tb_get_param(tb_ctx *c, const char *name, double *value) {
 
 static int reset_impl(tb_ctx *c, const double *d_init, const uint8_t *d_mask, float *d_obs, void *stream) {
   GUARD(c);
+  if (check_fault(c, "tb_reset")) return 1;
   StepIO io = make_io(c);
   io.obs = d_obs;
   DISPATCH(reset_kernel, grid_for(io.n, kBlock), kBlock, (cudaStream_t)stream, io, d_init, d_mask);
@@ -1761,6 +2049,7 @@ static int step_impl(tb_ctx *c, const float *d_actions, float *d_obs, float *d_r
                      float *d_terminal_obs, uint8_t *d_events, void *stream, bool stage) {
   GUARD(c);
   if (!d_actions || !d_obs || !d_reward || !d_done) return fail("%s", "tb_step: actions, obs, reward and done are required");
+  if (check_fault(c, "tb_step")) return 1;
   StepIO io = make_io(c);
   io.actions = d_actions; io.obs = d_obs; io.reward = d_reward; io.done = d_done; io.term_obs = d_terminal_obs;
   io.events = d_events;
@@ -1876,7 +2165,7 @@ int tb_step_host(tb_ctx *c, const float *h_actions, float *h_obs, float *h_rewar
     if (za && zo && zr && zd && (zt || !h_terminal_obs) && (ze || !h_events)) {
       if (step_impl(c, za, zo, zr, zd, zt, ze, s, true)) return 1;
       CU(cudaStreamSynchronize(s));
-      return 0;
+      return check_fault(c, "tb_step_host");
     }
   }
   if (ensure_staging(c)) return 1;
@@ -1890,7 +2179,7 @@ int tb_step_host(tb_ctx *c, const float *h_actions, float *h_obs, float *h_rewar
   if (h_terminal_obs) CU(cudaMemcpyAsync(h_terminal_obs, c->d_term, n * od * sizeof(float), cudaMemcpyDeviceToHost, s));
   if (h_events) CU(cudaMemcpyAsync(h_events, c->d_events, n, cudaMemcpyDeviceToHost, s));
   CU(cudaStreamSynchronize(s));
-  return 0;
+  return check_fault(c, "tb_step_host");
 }
 
 int tb_set_kernel_timing(tb_ctx *c, int enabled) {
@@ -1929,6 +2218,10 @@ int tb_ff_diagnostics(tb_ctx *c, int64_t *h_out) {
       std::fprintf(stderr, "server iterations with %d..%d lanes: %llu, mean %llu cycles; after 1.5 ms: %llu, mean %llu cycles\n", b ? (1 << (b - 1)) + 1 : 1,
                    1 << b, s[112 + 2 * b], s[112 + 2 * b] ? s[113 + 2 * b] / s[112 + 2 * b] : 0ULL, s[80 + 2 * b],
                    s[80 + 2 * b] ? s[81 + 2 * b] / s[80 + 2 * b] : 0ULL);
+  if (std::getenv("TB_FF_DIAG_DUMP"))
+    std::fprintf(stderr, "server substeps: lean %llu (mean %llu cycles, %llu with contact), handed to ff_full %llu (lean part mean %llu cycles, ff_full mean %llu cycles; "
+                 "%llu with racket contact, %llu with another event); loads %llu (mean %llu cycles)\n", s[100], s[100] ? s[101] / s[100] : 0ULL, s[107], s[102],
+                 s[102] ? s[103] / s[102] : 0ULL, s[102] ? s[104] / s[102] : 0ULL, s[105], s[106], s[108], s[108] ? s[109] / s[108] : 0ULL);
   if (std::getenv("TB_FF_DIAG_DUMP")) {
     unsigned long long tmax = 0;
     for (int i = 0; i < 100 && i < (int)s[299]; ++i) tmax = s[301 + 2 * i] > tmax ? s[301 + 2 * i] : tmax;
