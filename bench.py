@@ -13,9 +13,15 @@ step), so the timed region must cover whole episodes to weight the two kinds of 
 Episodes run in lock step (all envs reset together, as a VecEnv starts).  With --steps a multiple of 26 (default
 1040 = 40 episodes, ~0.4 s) the timed region spans K/26 whole episodes.  For any other K the region is placed so
 that it ENDS right after a fast-forward step and therefore contains ceil(K/26) of them: the expensive step is then
-weighted at least as heavily as in whole episodes and the number can only come out pessimistic.  `--stagger on`
-instead offsets the episode phases per 128-env group (g mod 26) so that every launch carries the same 25:1 mix
-(slower: each launch then waits for its own 800-substep time-out flights).
+weighted at least as heavily as in whole episodes and the number can only come out pessimistic.  The NCCL all-reduce
+of the episode statistics follows every fast-forward step of the timed region, so any K contains ceil(K/26) reductions.
+`--stagger on` instead offsets the episode phases per 128-env group (g mod 26) so that every launch carries the same
+25:1 mix (slower: each launch then waits for its own 800-substep time-out flights).
+
+Actions: a ring of 32 pre-drawn U(-1,1) batches in HBM, i.e. i.i.d. within every 26-step episode.
+`extras` (N = 1 only): the other BASELINE.json configs measured in the same process - Tennisbot-v0 at 65 536 envs with a
+scripted ball-tracking policy (config 3 with racket-ball contact), the TennisVecEnv host loop at 16 384 envs (config 4's
+env side), the fused tb_rollout at K = 26 and the policy rollout the PPO trainer uses.
 """
 import argparse
 import json
@@ -37,8 +43,11 @@ ALGO_BYTES = {  # action + obs + reward + done + state read + st
     ("Tennisbot-v0", "f32"): 8 + 48 + 4 + 1 + 128 + 128,
     ("Tennisbot-v0", "f64"): 8 + 48 + 4 + 1 + 256 + 256,
 }
+ALGO_BYTES_F32_STATE = {"SwingRacket-v0": 24 + 24 + 4 + 1 + 128 + 128, "Tennisbot-v0": 8 + 48 + 4 + 1 + 128 + 128}  # BASELINE.md's yardstick
 EPISODE_STEPS = 26
 GROUP = 128
+RING = 32  # pre-drawn action batches: >= 26, so the actions of an episode are i.i.d. (a ring of 4 repeats every 4 steps and
+           # drives the racket in one direction: many more racket-ball contacts than action_space.sample() gives)
 
 
 def parse():
@@ -55,6 +64,8 @@ def parse():
     ap.add_argument("--stagger", default="off", choices=["on", "off"],
                     help="episode phases: off = lock-step (all envs reset together), on = staggered per 128-env group")
     ap.add_argument("--skip-cpu-baseline", action="store_true")
+    ap.add_argument("--extras", default="auto", choices=["auto", "on", "off"],
+                    help="measure the other BASELINE configs too (auto: at N = 1)")
     return ap.parse_args()
 
 

@@ -83,6 +83,9 @@ extern "C" {
 
 /* in-kernel action sources for tb_rollout */
 #define TB_ACT_RANDOM 0 /* U(-1,1) = action_space.sample(); Philox stream keyed (env, episode, step) */
+#define TB_ACT_TRACK 1  /* Tennisbot-v0 only: scripted ball tracker, a0 = 0.2 U(-1,1), a1 = clip(4 (ball_y - racket_y) - 1.5
+                           racket_vy, -1, 1) in float32 on the observation entries: BASELINE config 3 "with racket-ball
+                           contact" (uniform actions meet the ball in ~2 % of episodes) */
 
 typedef struct tb_ctx tb_ctx;
 
@@ -143,6 +146,29 @@ int tb_step(tb_ctx *ctx, const float *d_actions, float *d_obs, float *d_reward, 
  * d_obs: observation after the last step; d_reward_sum float32 [N]; d_done_count int32 [N] (any may be NULL). */
 int tb_rollout(tb_ctx *ctx, int action_mode, int k_steps, float *d_obs, float *d_reward_sum, int32_t *d_done_count,
                void *stream);
+
+/* ---- policy rollout: what SB3's collect_rollouts does around env.step (train_swing.py:83-122), kept on the
+ * device.  The policy is the one the reference trains: SB3 MlpPolicy with net_arch pi = vf = [32, 64, 32], tanh, a Gaussian
+ * head with state-independent log_std (train_swing.py:80-91; backup_models/ppo_swing.zip).  Parameters, float32, each
+ * tensor row-major [out][in] and padded to a multiple of 4 floats:
+ *   pi tower: W1[32x6] b1[32] W2[64x32] b2[64] W3[32x64] b3[32] action_net W[6x32] b[6 -> 8]                (4616 floats)
+ *   vf tower: W1 b1 W2 b2 W3 b3 (same shapes) value_net W[1x32] b[1 -> 4]                                   (4452 floats)
+ *   log_std[6 -> 8]                                                                                          (8 floats) */
+#define TB_POLICY_FLOATS 9076
+int tb_set_policy(tb_ctx *ctx, const float *d_params, int64_t count, void *stream);
+/* K env steps with actions sampled from the policy: per step one policy_kernel launch (forward, Philox Gaussian noise,
+ * log-density, value) followed by tb_step's launches, all on `stream`, nothing synchronises - capturable in a CUDA graph.
+ * d_obs float32 [K, N, 6]: d_obs[0] must hold the current observation (from tb_reset or the previous rollout's
+ * d_last_obs); d_obs[t] receives the observation step t acted on.  d_actions float32 [K, N, 6]: the sampled, UNCLIPPED
+ * action (env.step gets it clipped to the Box, as SB3 does); d_logp, d_value float32 [K, N]; d_reward float32 [K, N];
+ * d_done uint8 [K, N]; d_last_obs float32 [N, 6] and d_last_value float32 [N]: observation after the last step and its
+ * value (GAE bootstrap).  d_actions, d_logp, d_value, d_last_value may be NULL.  deterministic = 1: action = mean
+ * (model.predict(deterministic=True)); else stochastic, as validate_swing.py:35 rolls the policy.  The noise streams
+ * are keyed (noise_seed, global env id, the context's env-step counter, a device word): independent of the env's own streams
+ * and of the sharding, and fresh on every replay of a captured graph. */
+int tb_policy_rollout(tb_ctx *ctx, int k_steps, int deterministic, uint64_t noise_seed, float *d_obs, float *d_actions,
+                      float *d_logp, float *d_value, float *d_reward, uint8_t *d_done, float *d_last_obs,
+                      float *d_last_value, void *stream);
 
 /* ---- state dump / injection for the parity harness: double [N, TB_STATE_WORDS] */
 int tb_get_state(tb_ctx *ctx, double *d_state, void *stream);

@@ -943,7 +943,7 @@ typedef struct {
   uint8_t *done, *events;
   double *margin, *obs64;
   /* rollout */
-  int rollout, k_steps;
+  int rollout, k_steps, action_mode;
   float *reward_sum;
   int32_t *done_count;
   int64_t stats[TBO_NUM_STATS], nphys;
@@ -973,6 +973,14 @@ static void *job_run(void *arg) {
         tbo_philox4x32(c->seed, (uint64_t)(c->id_offset + i), (uint32_t)s[S_EPISODE],
                        word3(STREAM_ACTION, (uint32_t)s[S_STEP], (uint32_t)b), r);
         for (int q = 0; q < 4; ++q) a[b * 4 + q] = (float)(2.0 * u01(r[q]) - 1.0);
+      }
+      if (j->action_mode == 1) {
+        /* scripted ball tracker for the incoming-ball env (random actions meet the ball in ~2 % of episodes):
+         * small random drive along x, PD law on ball y - racket y, all in float32 on the float32 observation entries */
+        const float ry = (float)s[S_RP + 1], vy = (float)s[S_RV + 1], by = (float)s[S_BP + 1];
+        float u = 4.0f * (by - ry) - 1.5f * vy;
+        a[0] = 0.2f * a[0];
+        a[1] = u < -1.0f ? -1.0f : (u > 1.0f ? 1.0f : u);
       }
       float rw = 0;
       uint8_t dn = 0;
@@ -1028,10 +1036,10 @@ int tbo_step(tbo_ctx *c, const float *actions, float *obs, float *reward, uint8_
 
 int tbo_rollout(tbo_ctx *c, int action_mode, int k_steps, float *obs, float *reward_sum, int32_t *done_count) {
   if (!c || k_steps < 0) return fail("tbo_rollout: bad argument");
-  if (action_mode != 0) return fail("tbo_rollout: unknown action mode");
+  if (action_mode != 0 && !(action_mode == 1 && c->kind == TBO_ENV_HIT)) return fail("tbo_rollout: unknown action mode");
   job_t j;
   memset(&j, 0, sizeof j);
-  j.c = c; j.rollout = 1; j.k_steps = k_steps; j.obs = obs; j.reward_sum = reward_sum; j.done_count = done_count;
+  j.c = c; j.rollout = 1; j.k_steps = k_steps; j.action_mode = action_mode; j.obs = obs; j.reward_sum = reward_sum; j.done_count = done_count;
   return run_jobs(c, &j);
 }
 

@@ -13,7 +13,8 @@ LIB_PATH = Path(os.environ.get("TB_LIB_PATH", PKG / "libtennisbot_b200.so"))  # 
 ENV_SWING, ENV_HIT = 0, 1
 F32, F64 = 0, 1
 STATE_WORDS, INIT_WORDS, NUM_STATS = 32, 8, 10
-ACT_RANDOM = 0
+ACT_RANDOM, ACT_TRACK = 0, 1
+POLICY_FLOATS = 9076
 CONTROL_FORCE, CONTROL_PID = 0, 1
 
 EV_RACKET_BALL, EV_COURT_BALL, EV_GOAL_BALL, EV_TIMEOUT, EV_BALL_PASSED, EV_NET_BALL, EV_RACKET_LOW = 1, 2, 4, 8, 16, 32, 64
@@ -26,6 +27,7 @@ EXPORTS = (
     "tb_scene_constant", "tb_create", "tb_destroy", "tb_set_param", "tb_get_param", "tb_set_control_mode", "tb_reset", "tb_reset_from",
     "tb_step", "tb_rollout", "tb_get_state", "tb_set_state", "tb_stats_device_ptr", "tb_read_stats",
     "tb_reset_host", "tb_step_host", "tb_launch_count", "tb_ff_diagnostics", "tb_set_kernel_timing", "tb_get_kernel_timing",
+    "tb_set_policy", "tb_policy_rollout",
 )
 
 
@@ -77,6 +79,9 @@ def load():
     L.tb_launch_count.argtypes = [vp, C.POINTER(i64)]
     if hasattr(L, "tb_ff_diagnostics"):  # absent from older builds loaded through TB_LIB_PATH for comparisons
         L.tb_ff_diagnostics.argtypes = [vp, C.POINTER(i64)]
+    if hasattr(L, "tb_set_policy"):
+        L.tb_set_policy.argtypes = [vp, vp, i64, vp]
+        L.tb_policy_rollout.argtypes = [vp, i32, i32, C.c_uint64, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     L.tb_set_kernel_timing.argtypes = [vp, i32]
     L.tb_get_kernel_timing.argtypes = [vp, C.POINTER(dbl), C.POINTER(dbl), C.POINTER(i64)]
     _lib = L

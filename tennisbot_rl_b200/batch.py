@@ -120,6 +120,23 @@ class TennisBatch:
         _lib.check(self.lib.tb_rollout(self.h, int(action_mode), int(k_steps), *args, self._stream()))
         return (self.obs, self._rsum, self._dcount) if want_outputs else None
 
+    # ------------------------------------------------------------------ policy rollout (tb_set_policy / tb_policy_rollout)
+    def set_policy(self, params):
+        """params: float32 CUDA tensor [POLICY_FLOATS] in the layout of include/tennisbot_b200.h (pack_policy builds it)."""
+        p = params.to(device=self.device, dtype=torch.float32).contiguous()
+        if p.numel() != _lib.POLICY_FLOATS:
+            raise ValueError(f"policy parameter vector must have {_lib.POLICY_FLOATS} floats")
+        _lib.check(self.lib.tb_set_policy(self.h, _dptr(p), p.numel(), self._stream()))
+
+    def policy_rollout(self, obs, reward, done, last_obs, actions=None, logp=None, value=None, last_value=None,
+                       deterministic=False, noise_seed=0):
+        """K = obs.shape[0] env steps with actions sampled in-kernel from the policy set by set_policy.  obs[0] must hold
+        the current observation.  All buffers are float32 CUDA tensors ([K, N, 6] / [K, N]; done uint8)."""
+        k = int(obs.shape[0])
+        _lib.check(self.lib.tb_policy_rollout(self.h, k, int(bool(deterministic)), int(noise_seed) & (2 ** 64 - 1), _dptr(obs),
+                                              _dptr(actions), _dptr(logp), _dptr(value), _dptr(reward), _dptr(done), _dptr(last_obs),
+                                              _dptr(last_value), self._stream()))
+
     def get_state(self):
         s = torch.empty((self.num_envs, _lib.STATE_WORDS), dtype=torch.float64, device=self.device)
         _lib.check(self.lib.tb_get_state(self.h, _dptr(s), self._stream()))

@@ -109,7 +109,7 @@ struct StepIO {
   void *state;
   int64_t n, id_offset;
   uint64_t seed;
-  int auto_reset, k_steps;
+  int auto_reset, k_steps, action_mode;
   const float *actions;
   float *obs, *reward, *term_obs, *reward_sum;
   uint8_t *done, *events;
@@ -1259,6 +1259,20 @@ __global__ void __launch_bounds__(kBlock, MinBlocks<T>::v) ff_kernel(const __gri
   ws.flush(io.stats);
 }
 
+// In-kernel action sources of the fused rollout.  TB_ACT_RANDOM: U(-1,1) = action_space.sample().  TB_ACT_TRACK (Tennisbot-v0):
+// a scripted ball tracker - a small random drive along x and a PD law on ball y - racket y, formed in float32 on the
+// observation's own float32 entries - so that racket-ball contacts actually occur (BASELINE config 3).
+template <typename T, int KIND>
+__device__ __forceinline__ void rollout_action(const StepIO &io, int64_t me, const St<T> &s, float *a) {
+  random_action<KIND>(io.seed, (uint64_t)(io.id_offset + me), s.episode, s.step, a);
+  if (KIND == TB_ENV_HIT && io.action_mode == TB_ACT_TRACK) {
+    const float ry = (float)s.rp[1], vy = (float)s.rv[1], by = (float)s.bp[1];
+    const float u = 4.0f * (by - ry) - 1.5f * vy;
+    a[0] = 0.2f * a[0];
+    a[1] = u < -1.0f ? -1.0f : (u > 1.0f ? 1.0f : u);
+  }
+}
+
 // Fused rollout: K env steps per env in one launch with in-kernel Philox actions; one thread per env, the state
 // stays in registers for the whole rollout (the fast-forward runs in line).
 template <typename T, int KIND>
@@ -1278,7 +1292,7 @@ __global__ void __launch_bounds__(kBlock) rollout_kernel(const __grid_constant__
   if (me < io.n) load_state(base, io.n, me, s);
   if (active) {
     left = io.k_steps;
-    random_action<KIND>(io.seed, (uint64_t)(io.id_offset + me), s.episode, s.step, a);
+    rollout_action<T, KIND>(io, me, s, a);
     c.done = s.flags & kFlagDone;
   }
 #pragma unroll 1
@@ -1306,7 +1320,7 @@ __global__ void __launch_bounds__(kBlock) rollout_kernel(const __grid_constant__
       rsum += c.reward;
       dcount += c.done ? 1 : 0;
       if (--left > 0) {
-        random_action<KIND>(io.seed, (uint64_t)(io.id_offset + me), s.episode, s.step, a);
+        rollout_action<T, KIND>(io, me, s, a);
         c.phase = 0; c.events = 0; c.hit = 0; c.reward = 0.0f; c.done = s.flags & kFlagDone;
       } else {
         active = false;
@@ -1322,6 +1336,135 @@ __global__ void __launch_bounds__(kBlock) rollout_kernel(const __grid_constant__
     store_state(base, io.n, me, s);
   }
   ws.flush(io.stats);
+}
+
+// ------------------------------------------------------------------------------------------------ policy rollout
+// the policy of train_swing.py:80-91 (SB3 MlpPolicy, net_arch pi = vf = [32, 64, 32], tanh, Gaussian head with
+// a state-independent log_std) evaluated on the device, so that a rollout is K x (policy_kernel, step_kernel, ff_kernel) on
+// one stream: observations, actions and the per-step records PPO needs never leave HBM and no host code runs between steps.
+// One thread per env; the 9 076 parameters (36 KB, layout TB_POLICY_* in the header) sit in shared memory and are read as
+// broadcast float4; activations stay in registers (every loop is unrolled).  float32 throughout, like the torch policy.
+constexpr int kPolW1 = 0, kPolB1 = 192, kPolW2 = 224, kPolB2 = 2272, kPolW3 = 2336, kPolB3 = 4384, kPolHead = 4416;
+constexpr int kPolPiTower = 4616, kPolVfTower = 4452, kPolLogStd = kPolPiTower + kPolVfTower;
+static_assert(kPolLogStd + 8 == TB_POLICY_FLOATS, "policy layout / header mismatch");
+
+// tanh(x) = 1 - 2 / (exp(2x) + 1) on the fast exponential: ~1e-6 absolute, a quarter of tanhf's instructions (a thread takes
+// 256 of them per step)
+__device__ __forceinline__ float tanh_fast(float x) {
+  const float e = __expf(2.0f * fminf(fmaxf(x, -15.0f), 15.0f));
+  return 1.0f - __fdividef(2.0f, e + 1.0f);
+}
+// y = tanh(W x + b): four outputs at a time, i.e. four independent accumulation chains per thread (at 16 384 envs there is
+// one warp per scheduler: a single chain would run at the FMA latency)
+template <int IN, int OUT>
+__device__ __forceinline__ void dense_tanh(const float *__restrict__ W, const float *__restrict__ b, const float *x, float *y) {
+  static_assert(OUT % 4 == 0, "outputs are taken four at a time");
+#pragma unroll
+  for (int o = 0; o < OUT; o += 4) {
+    float acc[4] = {b[o], b[o + 1], b[o + 2], b[o + 3]};
+    if (IN % 4 == 0) {
+#pragma unroll
+      for (int i = 0; i < IN / 4; ++i) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float4 w = reinterpret_cast<const float4 *>(W + (o + k) * IN)[i];
+          acc[k] = fmaf(w.x, x[4 * i], acc[k]); acc[k] = fmaf(w.y, x[4 * i + 1], acc[k]);
+          acc[k] = fmaf(w.z, x[4 * i + 2], acc[k]); acc[k] = fmaf(w.w, x[4 * i + 3], acc[k]);
+        }
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < IN; ++i)
+#pragma unroll
+        for (int k = 0; k < 4; ++k) acc[k] = fmaf(W[(o + k) * IN + i], x[i], acc[k]);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) y[o + k] = tanh_fast(acc[k]);
+  }
+}
+// the three tanh layers of one tower: 6 -> 32 -> 64 -> 32
+__device__ __forceinline__ void tower(const float *P, const float *x, float *h3) {
+  float h1[32], h2[64];
+  dense_tanh<6, 32>(P + kPolW1, P + kPolB1, x, h1);
+  dense_tanh<32, 64>(P + kPolW2, P + kPolB2, h1, h2);
+  dense_tanh<64, 32>(P + kPolW3, P + kPolB3, h2, h3);
+}
+constexpr uint32_t kStreamPolicy = 2u;
+struct PolicyIO {
+  const float *params;     // TB_POLICY_FLOATS floats in HBM
+  const float *obs;        // [N, 6] observation the action is computed from
+  float *act_raw;          // [N, 6] mean + std * eps, NOT clipped (what PPO's ratio is formed with), may be nullptr
+  float *act_env;          // [N, 6] clipped to the Box (what env.step gets: SB3 clips before stepping), may be nullptr
+  float *logp, *value;     // [N] log-density of act_raw; value estimate (either may be nullptr)
+  int64_t n, id_offset;
+  uint64_t seed;           // noise streams are keyed (seed, global env id, tick): independent of the env's own streams
+  const unsigned *tick;    // device word that advances with every env step (StepIO::epoch[0]): a rollout captured in a CUDA
+                           // graph draws fresh noise on every replay
+  int deterministic;       // 1: act_raw = mean (validate_swing.py's predict(deterministic=True) counterpart)
+};
+// grid (ceil(N / 128), 2): blockIdx.y = 0 the policy tower (action, log-density), 1 the value tower
+__global__ void __launch_bounds__(kBlock) policy_kernel(const __grid_constant__ PolicyIO io) {
+  __shared__ __align__(16) float P[kPolPiTower + 8];
+  const bool vf = blockIdx.y != 0;
+  pdl_wait();
+  if (vf ? io.value == nullptr : (!io.act_raw && !io.act_env && !io.logp)) return;
+  {
+    const float4 *src = reinterpret_cast<const float4 *>(io.params + (vf ? kPolPiTower : 0));
+    const int nv = (vf ? kPolVfTower : kPolPiTower) / 4;
+    for (int i = threadIdx.x; i < nv; i += kBlock) reinterpret_cast<float4 *>(P)[i] = src[i];
+    if (!vf && threadIdx.x < 2) reinterpret_cast<float4 *>(P + kPolPiTower)[threadIdx.x] = reinterpret_cast<const float4 *>(io.params + kPolLogStd)[threadIdx.x];
+  }
+  __syncthreads();
+  const int64_t me = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+  if (me < io.n) {
+    float x[6];
+    {
+      const float2 *p = reinterpret_cast<const float2 *>(io.obs + me * 6);
+      const float2 a = p[0], b = p[1], c = p[2];
+      x[0] = a.x; x[1] = a.y; x[2] = b.x; x[3] = b.y; x[4] = c.x; x[5] = c.y;
+    }
+    float h[32];
+    tower(P, x, h);
+    if (!vf) {
+      const float *Wa = P + kPolHead, *ba = P + kPolHead + 192, *ls = P + kPolPiTower;
+      uint32_t r0[4], r1[4];
+      const uint32_t tick = *io.tick;
+      philox4x32(io.seed, (uint64_t)(io.id_offset + me), tick, stream_word(kStreamPolicy, 0, 0), r0);
+      philox4x32(io.seed, (uint64_t)(io.id_offset + me), tick, stream_word(kStreamPolicy, 0, 1), r1);
+      const uint32_t rr[8] = {r0[0], r0[1], r0[2], r0[3], r1[0], r1[1], r1[2], r1[3]};
+      float raw[6], lp = 0.0f;
+#pragma unroll
+      for (int o = 0; o < 6; ++o) {
+        float mu = ba[o];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) mu = fmaf(Wa[o * 32 + i], h[i], mu);
+        // Box-Muller on a pair of uniforms: component o takes the cosine (o even) or sine (o odd) branch of pair o / 2
+        const float u1 = ((float)(rr[2 * (o / 2)] >> 8) + 0.5f) * (1.0f / 16777216.0f), u2 = (float)(rr[2 * (o / 2) + 1] >> 8) * (1.0f / 16777216.0f);
+        const float rad = sqrtf(-2.0f * logf(u1)), ang = 6.283185307179586f * u2;
+        const float eps = io.deterministic ? 0.0f : rad * ((o & 1) ? sinf(ang) : cosf(ang));
+        raw[o] = fmaf(expf(ls[o]), eps, mu);
+        lp += -0.5f * eps * eps - ls[o] - 0.9189385332046727f;
+      }
+      if (io.act_raw) {
+        float2 *q = reinterpret_cast<float2 *>(io.act_raw + me * 6);
+        q[0] = make_float2(raw[0], raw[1]); q[1] = make_float2(raw[2], raw[3]); q[2] = make_float2(raw[4], raw[5]);
+      }
+      if (io.act_env) {
+        float2 *q = reinterpret_cast<float2 *>(io.act_env + me * 6);
+#pragma unroll
+        for (int o = 0; o < 6; ++o) raw[o] = fminf(fmaxf(raw[o], -1.0f), 1.0f);
+        q[0] = make_float2(raw[0], raw[1]); q[1] = make_float2(raw[2], raw[3]); q[2] = make_float2(raw[4], raw[5]);
+      }
+      if (io.logp) io.logp[me] = lp;
+    } else {
+      const float *Wv = P + kPolHead;
+      float v = Wv[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v = fmaf(Wv[i], h[i], v);
+      io.value[me] = v;
+    }
+  }
+  pdl_trigger();
 }
 
 template <typename T, int KIND>
@@ -1704,6 +1847,8 @@ struct tb_ctx {
   int control_mode = TB_CONTROL_FORCE;
   void *pid = nullptr;                       // controller memory, allocated by tb_set_control_mode(TB_CONTROL_PID)
   bool zero_copy = std::getenv("TB_HOST_STAGING") == nullptr;  // tb_step_host: address pinned host buffers from the kernels
+  float *policy = nullptr;                   // TB_POLICY_FLOATS parameters (tb_set_policy)
+  float *pol_act = nullptr;                  // [N, 6] clipped actions handed from policy_kernel to step_kernel
   bool timing = false;                       // tb_set_kernel_timing
   cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
   double ms_step = 0, ms_ff = 0;
@@ -1797,9 +1942,9 @@ template <typename T, int KIND> static int step_resident_ctas(tb_ctx *c) {
   return 0;
 }
 template <typename... KArgs, typename... Args>
-static cudaError_t launch_pdl(bool pdl, void (*kernel)(KArgs...), unsigned grid, cudaStream_t stream, Args &&...args) {
+static cudaError_t launch_pdl(bool pdl, void (*kernel)(KArgs...), dim3 grid, cudaStream_t stream, Args &&...args) {
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kBlock); cfg.dynamicSmemBytes = 0; cfg.stream = stream;
+  cfg.gridDim = grid; cfg.blockDim = dim3(kBlock); cfg.dynamicSmemBytes = 0; cfg.stream = stream;
   cudaLaunchAttribute at[1];
   at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   at[0].val.programmaticStreamSerializationAllowed = 1;
@@ -2003,7 +2148,7 @@ int tb_destroy(tb_ctx *c) {
   DeviceGuard g(c->cfg.device);
   if (c->own_stream) { cudaStreamSynchronize(c->own_stream); cudaStreamDestroy(c->own_stream); }
   for (int i = 0; i < 3; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
-  cudaFree(c->state); cudaFree(c->stats); cudaFree(c->queue_ctrs); cudaFree(c->queue); cudaFree(c->dq); cudaFree(c->epoch); cudaFree(c->fault); cudaFree(c->queue_full); cudaFree(c->queue_ctl); cudaFree(c->pid);
+  cudaFree(c->state); cudaFree(c->stats); cudaFree(c->queue_ctrs); cudaFree(c->queue); cudaFree(c->dq); cudaFree(c->epoch); cudaFree(c->fault); cudaFree(c->queue_full); cudaFree(c->queue_ctl); cudaFree(c->pid); cudaFree(c->policy); cudaFree(c->pol_act);
   if (c->h_fault) cudaFreeHost(c->h_fault);
   cudaFree(c->d_actions); cudaFree(c->d_obs); cudaFree(c->d_reward); cudaFree(c->d_term);
   cudaFree(c->d_done); cudaFree(c->d_events); cudaFree(c->d_mask);
@@ -2062,12 +2207,59 @@ int tb_step(tb_ctx *c, const float *d_actions, float *d_obs, float *d_reward, ui
 
 int tb_rollout(tb_ctx *c, int action_mode, int k_steps, float *d_obs, float *d_reward_sum, int32_t *d_done_count, void *stream) {
   GUARD(c);
-  if (action_mode != TB_ACT_RANDOM) return fail("%s", "tb_rollout: unknown action mode");
+  if (action_mode != TB_ACT_RANDOM && !(action_mode == TB_ACT_TRACK && c->cfg.env_kind == TB_ENV_HIT))
+    return fail("%s", "tb_rollout: unknown action mode (TB_ACT_TRACK is Tennisbot-v0's)");
   if (c->control_mode != TB_CONTROL_FORCE) return fail("%s", "tb_rollout: in-kernel random actions need TB_CONTROL_FORCE");
   if (k_steps < 0) return fail("%s", "tb_rollout: k_steps must be >= 0");
   StepIO io = make_io(c);
-  io.k_steps = k_steps; io.obs = d_obs; io.reward_sum = d_reward_sum; io.done_count = d_done_count;
+  io.k_steps = k_steps; io.action_mode = action_mode; io.obs = d_obs; io.reward_sum = d_reward_sum; io.done_count = d_done_count;
   DISPATCH(rollout_kernel, grid_for(io.n, kBlock), kBlock, (cudaStream_t)stream, io);
+  CU(cudaGetLastError());
+  return 0;
+}
+
+int tb_set_policy(tb_ctx *c, const float *d_params, int64_t count, void *stream) {
+  GUARD(c);
+  if (c->cfg.env_kind != TB_ENV_SWING) return fail("%s", "tb_set_policy: the in-kernel policy is SwingRacket-v0's (6 -> 6)");
+  if (!d_params || count != TB_POLICY_FLOATS) return fail("%s", "tb_set_policy: expected TB_POLICY_FLOATS floats in device memory");
+  if (!c->policy) CU(cudaMalloc(&c->policy, TB_POLICY_FLOATS * sizeof(float)));
+  if (!c->pol_act) CU(cudaMalloc(&c->pol_act, (size_t)c->cfg.num_envs * 6 * sizeof(float)));
+  CU(cudaMemcpyAsync(c->policy, d_params, TB_POLICY_FLOATS * sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  return 0;
+}
+
+int tb_policy_rollout(tb_ctx *c, int k_steps, int deterministic, uint64_t noise_seed, float *d_obs, float *d_actions, float *d_logp,
+                      float *d_value, float *d_reward, uint8_t *d_done, float *d_last_obs, float *d_last_value, void *stream) {
+  GUARD(c);
+  if (!c->policy) return fail("%s", "tb_policy_rollout: no policy (tb_set_policy)");
+  if (c->control_mode != TB_CONTROL_FORCE) return fail("%s", "tb_policy_rollout: the policy's actions are forces (TB_CONTROL_FORCE)");
+  if (k_steps < 1 || !d_obs || !d_reward || !d_done || !d_last_obs) return fail("%s", "tb_policy_rollout: k_steps >= 1, obs, reward, done and last_obs are required");
+  if (check_fault(c, "tb_policy_rollout")) return 1;
+  const int64_t n = c->cfg.num_envs;
+  cudaStream_t s = (cudaStream_t)stream;
+  PolicyIO pio;
+  std::memset(&pio, 0, sizeof pio);
+  pio.params = c->policy; pio.n = n; pio.id_offset = c->cfg.env_id_offset; pio.seed = noise_seed; pio.deterministic = deterministic;
+  pio.act_env = c->pol_act; pio.tick = c->epoch;
+  const unsigned grid = grid_for(n, kBlock);
+  for (int t = 0; t < k_steps; ++t) {
+    pio.obs = d_obs + (size_t)t * n * 6;
+    pio.act_raw = d_actions ? d_actions + (size_t)t * n * 6 : nullptr;
+    pio.logp = d_logp ? d_logp + (size_t)t * n : nullptr;
+    pio.value = d_value ? d_value + (size_t)t * n : nullptr;
+    CU(launch_pdl(c->pdl, policy_kernel, dim3(grid, 2), s, pio));
+    c->launches++;
+    StepIO io = make_io(c);
+    io.actions = c->pol_act;
+    io.obs = t + 1 < k_steps ? d_obs + (size_t)(t + 1) * n * 6 : d_last_obs;
+    io.reward = d_reward + (size_t)t * n; io.done = d_done + (size_t)t * n;
+    if (launch_step(c, io, s)) return 1;
+  }
+  if (d_last_value) {  // bootstrap value of the observation the rollout ends with
+    pio.obs = d_last_obs; pio.act_raw = nullptr; pio.act_env = nullptr; pio.logp = nullptr; pio.value = d_last_value;
+    CU(launch_pdl(c->pdl, policy_kernel, dim3(grid, 2), s, pio));
+    c->launches++;
+  }
   CU(cudaGetLastError());
   return 0;
 }

@@ -4,11 +4,12 @@ The reference trains with SB3 PPO (`train_swing.py:80-91`: MlpPolicy, net_arch p
 0.002, gamma .99, gae_lambda .95, clip .2, n_epochs 10, vf_coef .5, max_grad_norm .5) on ONE env, 1100 steps per
 update.  SB3 is not installed here, so this is a plain-torch PPO with the same policy architecture and
 hyper-parameters; only the batch geometry changes (N envs x 26 steps = one whole episode per env per update) and
-the learning rate is the reference's 3e-4 default.  Observations and actions never leave HBM: the rollout calls
-TennisBatch.step with CUDA tensors, and the whole 26-step rollout (policy forward, sampling, env step) is captured
-once as a CUDA graph and replayed per update - the env step is graph-safe (no host synchronisation inside tb_step; the
-queue tags of ff_kernel advance on the device).  Target: the mean episodic return stored in
-backup_models/ppo_swing.zip, 31.5.
+the learning rate is the reference's 3e-4 default.  Observations and actions never leave HBM, and the rollout runs no
+torch code at all: tb_policy_rollout evaluates the policy in a CUDA kernel of the library (forward, Philox Gaussian noise,
+log-density, value), so the 26-step episode is 26 x (policy_kernel, step_kernel, ff_kernel) issued by one C call; the call
+is captured once as a CUDA graph and replayed per update (nothing in it synchronises; the queue tags of ff_kernel advance
+on the device).  `fused_policy=False` keeps the eager torch policy of round 1 for comparison.  Target: the mean episodic
+return stored in backup_models/ppo_swing.zip, 31.5.
 """
 import math
 import time
@@ -16,6 +17,7 @@ import time
 import torch
 import torch.nn as nn
 
+from . import _lib
 from .batch import TennisBatch
 
 EPISODE = 26  # agent steps per SwingRacket-v0 episode (swingracket_env.py:85-86: 25 control steps + the fast-forward step)
@@ -52,12 +54,37 @@ class ActorCritic(nn.Module):
     def value(self, obs):
         return self.v(self.vf(obs)).squeeze(-1)
 
+    def packed(self):
+        lin = lambda seq: [(m.weight, m.bias) for m in seq if isinstance(m, nn.Linear)]  # noqa: E731
+        return pack_policy(lin(self.pi), (self.mu.weight, self.mu.bias), lin(self.vf), (self.v.weight, self.v.bias), self.log_std)
+
+
+def pack_policy(pi, mu, vf, v, log_std):
+    """Flat float32 parameter vector in tb_set_policy's layout from (weight, bias) lists of the two towers: pi, vf = three
+    (W [out, in], b) pairs each; mu, v = the heads; every tensor padded to a multiple of 4 floats."""
+    def pad(t):
+        t = t.detach().reshape(-1).to(torch.float32)
+        r = (-t.numel()) % 4
+        return t if r == 0 else torch.cat([t, t.new_zeros(r)])
+    parts = []
+    for tower, head in ((pi, mu), (vf, v)):
+        for W, b in tower:
+            parts += [pad(W), pad(b)]
+        parts += [pad(head[0]), pad(head[1])]
+    parts.append(pad(log_std))
+    out = torch.cat(parts)
+    assert out.numel() == _lib.POLICY_FLOATS, out.numel()
+    return out
+
 
 class SwingPPO:
     """PPO learner whose rollouts run on the B200 env batch.  use_graph: replay the rollout as one CUDA graph."""
 
-    def __init__(self, num_envs=16384, precision="f64", seed=0, lr=3e-4, epochs=10, minibatches=8, device=0, use_graph=True):
+    def __init__(self, num_envs=16384, precision="f64", seed=0, lr=3e-4, epochs=10, minibatches=8, device=0, use_graph=True,
+                 fused_policy=True):
         torch.manual_seed(seed)
+        self.fused_policy = fused_policy
+        self.seed = seed
         self.dev = torch.device("cuda", device)
         self.n = n = int(num_envs)
         self.env = TennisBatch("SwingRacket-v0", n, device=device, seed=seed, precision=precision)
@@ -68,6 +95,8 @@ class SwingPPO:
         z = lambda *s: torch.zeros(s, device=self.dev)  # noqa: E731
         self.obs_buf, self.act_buf = z(EPISODE, n, 6), z(EPISODE, n, 6)
         self.logp_buf, self.rew_buf, self.done_buf, self.val_buf = z(EPISODE, n), z(EPISODE, n), z(EPISODE, n), z(EPISODE + 1, n)
+        self.done_u8 = torch.zeros((EPISODE, n), dtype=torch.uint8, device=self.dev)
+        self.params = z(_lib.POLICY_FLOATS)
         self.obs = self.env.reset().clone()
         self.graph = None
         self.use_graph = use_graph
@@ -81,6 +110,15 @@ class SwingPPO:
     # ------------------------------------------------------------------ rollout
     def _rollout_body(self):
         ac, env = self.ac, self.env
+        if self.fused_policy:
+            # parameters -> the library's buffer (device to device, inside the graph: every replay sees the current weights)
+            self.params.copy_(ac.packed())
+            env.set_policy(self.params)
+            self.obs_buf[0].copy_(self.obs)
+            env.policy_rollout(self.obs_buf, self.rew_buf, self.done_u8, self.obs, actions=self.act_buf, logp=self.logp_buf,
+                               value=self.val_buf[:EPISODE], last_value=self.val_buf[EPISODE], noise_seed=self.seed + 1)
+            self.done_buf.copy_(self.done_u8)
+            return
         for t in range(EPISODE):
             mu = ac.mean(self.obs)
             a = mu + ac.log_std.exp() * torch.randn_like(mu)
@@ -149,6 +187,9 @@ class SwingPPO:
                     self._minibatch_step()
                     continue
                 if self.upd_graph is None:
+                    # warm-up steps are real Adam updates: take them on a snapshot and put model and optimiser back, so
+                    # that the graph path trains exactly like the eager one (capture itself executes nothing)
+                    snap_m = {k: v.clone() for k, v in self.ac.state_dict().items()}
                     s = torch.cuda.Stream(self.dev)
                     s.wait_stream(torch.cuda.current_stream(self.dev))
                     with torch.cuda.stream(s):
@@ -158,8 +199,14 @@ class SwingPPO:
                     self.upd_graph = torch.cuda.CUDAGraph()
                     with torch.cuda.graph(self.upd_graph):
                         self._minibatch_step()
-                else:
-                    self.upd_graph.replay()
+                    with torch.no_grad():  # back to "no update taken yet": weights, Adam moments and step counts
+                        for k, v in self.ac.state_dict().items():
+                            v.copy_(snap_m[k])
+                        for st in self.opt.state.values():
+                            for v in st.values():
+                                if torch.is_tensor(v):
+                                    v.zero_()
+                self.upd_graph.replay()
 
     def _minibatch_step(self):
         ac = self.ac

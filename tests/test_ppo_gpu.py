@@ -82,11 +82,31 @@ def test_odd_number_of_steps_per_graph_replays():
     np.testing.assert_array_equal(state_g, state_e)
 
 
-def test_ppo_learns_on_the_gpu_env():
+@pytest.mark.parametrize("fused", [True, False])
+def test_ppo_learns_on_the_gpu_env(fused):
+    """Short run on 4096 envs with the in-kernel policy rollout (fused) and with round 1's eager torch policy."""
     from tennisbot_rl_b200.ppo import SwingPPO
 
-    ppo = SwingPPO(num_envs=4096, seed=1, use_graph=True)
+    ppo = SwingPPO(num_envs=4096, seed=1, use_graph=True, fused_policy=fused)
     s = ppo.train(iters=25, target=31.5)
     first, last = s["history"][0]["mean_return"], s["final_mean_return"]
     print(first, last, s["rollout_env_steps_per_s"])
     assert last > first + 2.0 and s["history"][-1]["hits_per_episode"] > 3 * max(s["history"][0]["hits_per_episode"], 0.02)
+
+
+def test_ppo_reaches_the_reference_return_at_config_4():
+    """BASELINE config 4 / north star: "SB3 PPO reaching the reference swing reward using the GPU env".  16 384 envs, the
+    reference's policy architecture and PPO hyper-parameters (train_swing.py:80-91), one whole episode per env per update.
+    Budget: 120 updates (51 M env steps; round 1 needed 66).  The mean episodic return of the stochastic policy must reach
+    31.5 - the mean of the last 100 training episodes stored in backup_models/ppo_swing.zip (tests/golden/
+    ppo_swing_monitor.json).  Rollout speed: >= 2e8 env-steps/s over the whole run (round 1's eager torch policy: 9.2e7).  At this
+    batch size the rollout is bound by the LATENCY of the 26th step once the policy hits the ball: flights of up to 775
+    dependent substeps (mean episode ~370 substeps) take ~0.7 ms whatever the batch, so 16 384 x 26 env steps cannot go
+    below ~0.75 ms (5.7e8 env-steps/s); measured 1.3 ms at iteration 0 (3.2e8) and 1.9 ms with a trained policy (2.2e8)."""
+    from tennisbot_rl_b200.ppo import SwingPPO
+
+    ppo = SwingPPO(num_envs=16384, seed=0, use_graph=True, fused_policy=True)
+    s = ppo.train(iters=120, target=31.5)
+    print({k: v for k, v in s.items() if k != "history"})
+    assert s["first_reached"] is not None and s["best_mean_return"] >= 31.5
+    assert s["rollout_env_steps_per_s"] >= 2e8

@@ -23,9 +23,11 @@ def main():
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--target", type=float, default=31.5)
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--eager-policy", action="store_true", help="torch policy in the rollout instead of tb_policy_rollout")
     ap.add_argument("--out", default="")
     args = ap.parse_args()
-    ppo = SwingPPO(args.envs, args.precision, args.seed, args.lr, args.epochs, args.minibatches, use_graph=not args.no_graph)
+    ppo = SwingPPO(args.envs, args.precision, args.seed, args.lr, args.epochs, args.minibatches, use_graph=not args.no_graph,
+                   fused_policy=not args.eager_policy)
     summary = ppo.train(args.iters, args.target, log=lambda s: print(s, flush=True))
     print(json.dumps({k: v for k, v in summary.items() if k != "history"}))
     if args.out:
