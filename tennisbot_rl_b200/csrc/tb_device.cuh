@@ -797,10 +797,17 @@ __device__ __forceinline__ void draw_init(uint64_t seed, uint64_t gid, uint32_t 
     in[7] = (T)1.0 + (T)0.5 * u01<T>(r2[3]);
   }
 }
+// Bits of the flags word that tell step_kernel which packs it need not load (the packs in HBM are always complete):
+//   kStDerived  the episode constants equal place(draw_init(seed, global env id, episode)): goal / d0 / spawn (swing) can be
+//               re-derived from the counter-based RNG instead of loaded; set by every RNG-placed episode start, not by
+//               explicit placements (tb_reset_from) or injected states (tb_set_state).  Tennisbot-v0: pack 6 holds only the
+//               constant z shoot force, so there the bit is set by every episode start
+//   kStSpin     the ball's spin has a y or z component (it has none until a frictional contact): pack 5 must be loaded
+constexpr int kStDerived = 1 << 24, kStSpin = 1 << 25;
 template <typename T, int KIND>
-__device__ __forceinline__ void start_episode(const Scene<T> &sc, St<T> &s, const T *in, uint32_t episode) {
+__device__ __forceinline__ void start_episode(const Scene<T> &sc, St<T> &s, const T *in, uint32_t episode, bool from_rng) {
   place<T, KIND>(sc, s, in);
-  s.ret = 0; s.step = 0; s.flags = 0; s.episode = episode;
+  s.ret = 0; s.step = 0; s.flags = (from_rng || KIND == TB_ENV_HIT) ? kStDerived : 0; s.episode = episode;
 }
 template <typename T, int KIND> __device__ __forceinline__ void pack_obs(const St<T> &s, float *o) {
   if (KIND == TB_ENV_SWING) {

@@ -73,15 +73,22 @@ template <typename T> __device__ __forceinline__ void load_state(const T *base, 
 }
 // Packs 5 and 6 hold episode constants (spawn / shoot force, goal, d0) next to the y, z spin of the ball, which is zero
 // until a frictional contact: step_kernel writes them back only when they changed (p5: spin or reset, p6: reset).
-template <typename T> __device__ __forceinline__ void store_state_changed(T *base, int64_t n, int64_t i, const St<T> &s, bool p5, bool p6) {
+template <typename T> __device__ __forceinline__ int flags_with_spin(const St<T> &s) {
+  return (s.flags & ~kStSpin) | ((s.bw[1] != 0 || s.bw[2] != 0) ? kStSpin : 0);
+}
+template <typename T> __device__ __forceinline__ void store_state_changed(T *base, int64_t n, int64_t i, const St<T> &s, bool p5, bool p6, bool have_aux = true) {
   st_pack(base, n, 0, i, Pack<T>{s.rp[0], s.rp[1], s.rp[2], s.bp[0]});
   st_pack(base, n, 1, i, Pack<T>{s.rq[0], s.rq[1], s.rq[2], s.rq[3]});
   st_pack(base, n, 2, i, Pack<T>{s.rv[0], s.rv[1], s.rv[2], s.bp[1]});
   st_pack(base, n, 3, i, Pack<T>{s.rw[0], s.rw[1], s.rw[2], s.bp[2]});
   st_pack(base, n, 4, i, Pack<T>{s.bv[0], s.bv[1], s.bv[2], s.bw[0]});
-  if (p5) st_pack(base, n, 5, i, Pack<T>{s.bw[1], s.bw[2], s.aux[0], s.aux[1]});
+  if (p5 && have_aux) st_pack(base, n, 5, i, Pack<T>{s.bw[1], s.bw[2], s.aux[0], s.aux[1]});
+  if (p5 && !have_aux) {  // (pack 5 was not loaded: its aux half stays as it is in HBM)
+    T *q = base + ((int64_t)5 * n + i) * 4;
+    q[0] = s.bw[1]; q[1] = s.bw[2];
+  }
   if (p6) st_pack(base, n, 6, i, Pack<T>{s.aux[2], s.goal[0], s.goal[1], s.d0});
-  st_pack(base, n, 7, i, Pack<T>{s.ret, int_as(T(), s.step), int_as(T(), s.flags), int_as(T(), (int64_t)s.episode)});
+  st_pack(base, n, 7, i, Pack<T>{s.ret, int_as(T(), s.step), int_as(T(), flags_with_spin(s)), int_as(T(), (int64_t)s.episode)});
 }
 template <typename T> __device__ __forceinline__ void store_state(T *base, int64_t n, int64_t i, const St<T> &s) {
   st_pack(base, n, 0, i, Pack<T>{s.rp[0], s.rp[1], s.rp[2], s.bp[0]});
@@ -91,7 +98,44 @@ template <typename T> __device__ __forceinline__ void store_state(T *base, int64
   st_pack(base, n, 4, i, Pack<T>{s.bv[0], s.bv[1], s.bv[2], s.bw[0]});
   st_pack(base, n, 5, i, Pack<T>{s.bw[1], s.bw[2], s.aux[0], s.aux[1]});
   st_pack(base, n, 6, i, Pack<T>{s.aux[2], s.goal[0], s.goal[1], s.d0});
-  st_pack(base, n, 7, i, Pack<T>{s.ret, int_as(T(), s.step), int_as(T(), s.flags), int_as(T(), (int64_t)s.episode)});
+  st_pack(base, n, 7, i, Pack<T>{s.ret, int_as(T(), s.step), int_as(T(), flags_with_spin(s)), int_as(T(), (int64_t)s.episode)});
+}
+
+// step_kernel's load: the packs a control step needs.  Packs 5 and 6 (ball spin y, z | episode constants) are loaded only
+// when the flags word says they carry something that cannot be had otherwise (kStSpin, kStDerived); the goal of an RNG-placed
+// SwingRacket episode is re-derived from the counter-based generator - the kernel is HBM-bound with issue slots to spare.
+// aux and d0 stay undefined then: a control step never reads them, and pack 5 / 6 are only written back by a lane that
+// loaded them (spin changed) or restarted the episode (all fields fresh).
+// Returns whether pack 5 was loaded (if not, its aux half is unknown and a lane whose spin changes writes the spin half only).
+template <typename T, int KIND>
+__device__ __forceinline__ bool load_state_ctl(const T *base, int64_t n, int64_t i, uint64_t seed, uint64_t gid, St<T> &s) {
+  Pack<T> p0 = ld_pack(base, n, 0, i), p1 = ld_pack(base, n, 1, i), p2 = ld_pack(base, n, 2, i),
+          p3 = ld_pack(base, n, 3, i), p4 = ld_pack(base, n, 4, i), p7 = ld_pack(base, n, 7, i);
+  s.rp[0] = p0.x; s.rp[1] = p0.y; s.rp[2] = p0.z; s.bp[0] = p0.w;
+  s.rq[0] = p1.x; s.rq[1] = p1.y; s.rq[2] = p1.z; s.rq[3] = p1.w;
+  s.rv[0] = p2.x; s.rv[1] = p2.y; s.rv[2] = p2.z; s.bp[1] = p2.w;
+  s.rw[0] = p3.x; s.rw[1] = p3.y; s.rw[2] = p3.z; s.bp[2] = p3.w;
+  s.bv[0] = p4.x; s.bv[1] = p4.y; s.bv[2] = p4.z; s.bw[0] = p4.w;
+  s.ret = p7.x; s.step = (int)as_int(p7.y); s.flags = (int)as_int(p7.z); s.episode = (uint32_t)as_int(p7.w);
+  const bool derived = (s.flags & kStDerived) != 0;
+  // Tennisbot-v0 reads the shoot force (aux x, y in pack 5) during the first frames of every episode
+  const bool need5 = (s.flags & kStSpin) != 0 || (KIND == TB_ENV_HIT && s.step < 5) || (KIND == TB_ENV_SWING && !derived);
+  s.bw[1] = 0; s.bw[2] = 0; s.aux[0] = 0; s.aux[1] = 0; s.aux[2] = 0; s.goal[0] = 0; s.goal[1] = 0; s.d0 = 0;
+  if (need5) {
+    Pack<T> p5 = ld_pack(base, n, 5, i);
+    s.bw[1] = p5.x; s.bw[2] = p5.y; s.aux[0] = p5.z; s.aux[1] = p5.w;
+  }
+  if (!derived) {
+    Pack<T> p6 = ld_pack(base, n, 6, i);
+    s.aux[2] = p6.x; s.goal[0] = p6.y; s.goal[1] = p6.z; s.d0 = p6.w;
+  } else if (KIND == TB_ENV_SWING) {
+    T in[TB_INIT_WORDS];
+    draw_init<T, KIND>(seed, gid, s.episode, in);
+    s.goal[0] = in[3]; s.goal[1] = in[4];
+  } else {
+    s.aux[2] = (T)(25.0 * 0.8);  // tennisbot_env.py:237: the z shoot force is a constant (place())
+  }
+  return need5;
 }
 
 // controller memory of TB_CONTROL_PID: two more packs per env in a separate array (allocated when the mode is set)
@@ -288,7 +332,7 @@ __device__ __forceinline__ void finish_api(const Scene<T> &sc, const StepIO &io,
       uint32_t ep = s.episode + 1;
       T in[TB_INIT_WORDS];
       draw_init<T, KIND>(io.seed, (uint64_t)(io.id_offset + me), ep, in);
-      start_episode<T, KIND>(sc, s, in, ep);
+      start_episode<T, KIND>(sc, s, in, ep, true);
       pack_obs<T, KIND>(s, ob);
     } else {
       s.flags |= kFlagDone;
@@ -343,7 +387,7 @@ __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.lau
 template <typename T, int KIND, bool STAGE, bool DEFER>
 __device__ __forceinline__ void step_tile(const Scene<T> &sc, const StepIO &io, unsigned long long *qctr, int64_t tile0, int64_t me, int rows,
                                           bool valid, St<T> &s, const float *a, WarpStats &ws, int *s_cnt, unsigned long long *s_base,
-                                          float *s_tile) {
+                                          float *s_tile, bool have5) {
   constexpr int OD = Dims<KIND>::obs;
   const unsigned full = 0xffffffffu;
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -444,7 +488,7 @@ __device__ __forceinline__ void step_tile(const Scene<T> &sc, const StepIO &io, 
   }
   if (valid) {
     const bool restarted = s.episode != episode0;
-    store_state_changed(base, io.n, me, s, restarted || s.bw[1] != spin1 || s.bw[2] != spin2, restarted);
+    store_state_changed(base, io.n, me, s, restarted || s.bw[1] != spin1 || s.bw[2] != spin2, restarted, have5 || restarted);
   }
 }
 
@@ -505,15 +549,17 @@ __global__ void __launch_bounds__(kBlock, MINB ? MINB : StepMinBlocks<T, KIND>::
       const T *b0 = static_cast<const T *>(io.state);
 #pragma unroll
       for (int p = 0; p < kPacks; ++p)
-        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(b0 + ((int64_t)p * io.n + e0) * 4), "r"((uint32_t)(kBlock * 4 * sizeof(T))) : "memory");
+        if (p != 5 && p != 6)  // (the two packs load_state_ctl usually skips)
+          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(b0 + ((int64_t)p * io.n + e0) * 4), "r"((uint32_t)(kBlock * 4 * sizeof(T))) : "memory");
       asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(io.actions + e0 * AD), "r"((uint32_t)(kBlock * AD * 4)) : "memory");
     }
   }
+  bool have5 = true;
   if (valid) {
-    load_state(static_cast<const T *>(io.state), io.n, me, s);
+    have5 = load_state_ctl<T, KIND>(static_cast<const T *>(io.state), io.n, me, io.seed, (uint64_t)(io.id_offset + me), s);
     if (!STAGE) load_action<KIND>(io.actions, me, a);
   }
-  step_tile<T, KIND, STAGE, KIND == TB_ENV_SWING>(sc, io, qctr, tile0, me, rows, valid, s, a, ws, s_cnt, s_base, s_tile);
+  step_tile<T, KIND, STAGE, KIND == TB_ENV_SWING>(sc, io, qctr, tile0, me, rows, valid, s, a, ws, s_cnt, s_base, s_tile, have5);
   ws.flush(io.stats);
   pdl_trigger();
 }
@@ -1311,7 +1357,7 @@ __global__ void __launch_bounds__(kBlock) rollout_kernel(const __grid_constant__
           uint32_t ep = s.episode + 1;
           T in[TB_INIT_WORDS];
           draw_init<T, KIND>(io.seed, (uint64_t)(io.id_offset + me), ep, in);
-          start_episode<T, KIND>(sc, s, in, ep);
+          start_episode<T, KIND>(sc, s, in, ep, true);
           pack_obs<T, KIND>(s, ob);
         } else {
           s.flags |= kFlagDone;
@@ -1484,7 +1530,7 @@ __global__ void __launch_bounds__(kBlock) reset_kernel(const __grid_constant__ S
   } else {
     draw_init<T, KIND>(io.seed, (uint64_t)(io.id_offset + i), ep, in);
   }
-  start_episode<T, KIND>(sc, s, in, ep);
+  start_episode<T, KIND>(sc, s, in, ep, init == nullptr);
   store_state(base, io.n, i, s);
   if (io.pid) {
     T z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -1511,7 +1557,7 @@ template <typename T> __global__ void get_state_kernel(const T *base, int64_t n,
   }
   for (int j = 0; j < 4; ++j) o[TB_S_RACKET_QUAT + j] = s.rq[j];
   o[TB_S_GOAL] = s.goal[0]; o[TB_S_GOAL + 1] = s.goal[1]; o[TB_S_D0] = s.d0; o[TB_S_RETURN] = s.ret;
-  o[TB_S_STEP] = s.step; o[TB_S_FLAGS] = s.flags; o[TB_S_EPISODE] = (double)(int32_t)s.episode;
+  o[TB_S_STEP] = s.step; o[TB_S_FLAGS] = s.flags & kFlagDone; o[TB_S_EPISODE] = (double)(int32_t)s.episode;
 }
 template <typename T> __global__ void set_state_kernel(T *base, int64_t n, const double *in) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1525,7 +1571,7 @@ template <typename T> __global__ void set_state_kernel(T *base, int64_t n, const
   }
   for (int j = 0; j < 4; ++j) s.rq[j] = (T)o[TB_S_RACKET_QUAT + j];
   s.goal[0] = (T)o[TB_S_GOAL]; s.goal[1] = (T)o[TB_S_GOAL + 1]; s.d0 = (T)o[TB_S_D0]; s.ret = (T)o[TB_S_RETURN];
-  s.step = (int)o[TB_S_STEP]; s.flags = (int)o[TB_S_FLAGS]; s.episode = (uint32_t)(int32_t)o[TB_S_EPISODE];
+  s.step = (int)o[TB_S_STEP]; s.flags = (int)o[TB_S_FLAGS] & kFlagDone; s.episode = (uint32_t)(int32_t)o[TB_S_EPISODE];
   store_state(base, n, i, s);
 }
 
