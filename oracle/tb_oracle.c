@@ -47,6 +47,8 @@ typedef struct {
   double pid_max_force;        /* racket.py:52: output (and integral) limits +-maxForce [C] */
   double pid_bias_z;           /* racket.py:110: constant z force of apply_pid_force_torque [C] */
   double pid_hit_z;            /* tennisbot_env.py:106 (commented call): z set-point appended to the 2-D hit action [C] */
+  double shoot_start;          /* first env step on which the ball's shoot force acts: 0 in tennisbot_env.py:118; playground.py:99 uses 11 */
+  double shoot_frames;         /* BALL_SHOOT_FRAMES = 5 (tennisbot_env.py:21); playground.py:16-17,99: 39 */
 } params_t;
 
 static const char *k_param_names[] = {
@@ -54,7 +56,7 @@ static const char *k_param_names[] = {
     "rest_ball_goal", "fric_ball_racket", "fric_ball_court", "fric_ball_goal", "contact_erp", "linear_slop",
     "rest_vel_threshold", "solver_iterations", "solver_residual", "contact_threshold", "hull_margin",
     "box_margin", "gyro_term", "racket_scale", "pid_kp", "pid_ki", "pid_kd", "pid_max_force", "pid_bias_z",
-    "pid_hit_z"};
+    "pid_hit_z", "shoot_start", "shoot_frames"};
 #define N_PARAMS ((int)(sizeof k_param_names / sizeof k_param_names[0]))
 
 static void params_default(params_t *p) {
@@ -85,6 +87,8 @@ static void params_default(params_t *p) {
   p->pid_max_force = 10.0;
   p->pid_bias_z = 4.0;
   p->pid_hit_z = 1.5;
+  p->shoot_start = 0;
+  p->shoot_frames = 5;
 }
 
 /* ------------------------------------------------------------------------------------------------ state */
@@ -758,7 +762,8 @@ static void hit_step(const tbo_ctx *c, double *s, double *pid, const float *a, s
   }
   int k = (int)s[S_STEP];
   double Fb[3] = {0, 0, 0};
-  if (k < 5) { Fb[0] = s[S_AUX]; Fb[1] = s[S_AUX + 1]; Fb[2] = s[S_AUX + 2]; }
+  const int shoot0 = (int)c->p.shoot_start, shoot_n = (int)c->p.shoot_frames;
+  if (k >= shoot0 && k < shoot0 + shoot_n) { Fb[0] = s[S_AUX]; Fb[1] = s[S_AUX + 1]; Fb[2] = s[S_AUX + 2]; }
   int bits = physics_step(c, s, F, zero, Fb, 0, &o->pb);
   o->nphys = 1;
   k++;
@@ -767,7 +772,7 @@ static void hit_step(const tbo_ctx *c, double *s, double *pid, const float *a, s
   o->events = bits;
   o->reward = 0;
   o->done = 0;
-  if (k < 5) return; /* returns False regardless of self.done (:138-139) */
+  if (k < shoot_n) return; /* returns False regardless of self.done (:138-139) */
   double dz = s[S_BP + 2] - s[S_RP + 2], dy = s[S_BP + 1] - s[S_RP + 1];
   double delta = sqrt(dz * dz + dy * dy);
   double reward = 0;

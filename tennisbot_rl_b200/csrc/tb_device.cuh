@@ -120,7 +120,7 @@ template <typename T, int NE> struct Prism {
   // every outline vertex at or above out_v (all of them when there is no quadrilateral); below out_v the outline lies
   // between the quadrilateral's two edge lines and above v = out_lo.
   T out_a, out_b, out_v, out_lo;
-  T out_inv_a, out_inv_b;  // 1 / (out_a + rim), 1 / (out_b + rim) for the racket's rim (ffp_rim), rounded down
+  T out_inv_a, out_inv_b;  // reciprocal semi-axes of the ellipse that contains the rim-neighbourhood of E(out_a, out_b), rim = ffp_rim
 };
 // true: (u, v) is strictly inside the outline (false says nothing)
 template <typename T, int NE> __device__ __forceinline__ bool prism_inside_fast(const Prism<T, NE> &pr, T u, T v) {
@@ -135,7 +135,7 @@ template <typename T> struct Scene {
   T dt, gravity_z, lin_damping, ang_damping, max_coord_vel;
   T rest_racket, rest_court, rest_goal, mu_racket, mu_court, mu_goal;
   T erp, slop, rest_vel_threshold, solver_residual, contact_threshold, hull_margin, box_margin, gyro;
-  int iters;
+  int iters, shoot_start, shoot_frames;  // Tennisbot-v0: env steps on which the ball's shoot force acts (tennisbot_env.py:21,118)
   unsigned vmax_hi;  // high 32 bits of max_coord_vel in T's format (clamp_velocities)
   T pid_kp, pid_ki, pid_kd, pid_lim, pid_bias_z, pid_hit_z;  // TB_CONTROL_PID (racket.py:47-64,103-122)
   T ball_r, ball_inv_m, ball_inv_i, racket_inv_m;
@@ -330,8 +330,9 @@ template <typename T> __device__ __forceinline__ void plane_space(const T *n, T 
 }
 
 // true: (u, v) is farther than `rim` from the outline for certain (false says nothing).  Far from the part at or above out_v:
-// outside the containing ellipse grown by rim (the parallel curve of an ellipse lies inside the ellipse with both semi-
-// axes grown by the offset).  Far from the part below out_v, which lies between two edge lines: beyond one of those lines,
+// outside an ellipse that contains everything within rim of the containing ellipse (out_inv_a, out_inv_b: the semi-axes
+// grown by rim AND scaled up on the host until they do - growing alone falls short between the axes).  Far from the part
+// below out_v, which lies between two edge lines: beyond one of those lines,
 // below out_lo or above out_v, each by more than rim.
 template <typename T, int NE> __device__ __forceinline__ bool prism_outside_fast(const Prism<T, NE> &pr, T u, T v, T rim) {
   T du = u * pr.out_inv_a, dv = (v - pr.in_c) * pr.out_inv_b;  // (rim == the rim the reciprocals were formed with)
@@ -908,7 +909,7 @@ __device__ __forceinline__ bool env_substep(const Scene<T> &sc, St<T> &s, const 
       pid_force(sc, pid, s.rp, sp, F);
     }
     T Fb[3] = {0, 0, 0};
-    if (s.step < 5) { Fb[0] = s.aux[0]; Fb[1] = s.aux[1]; Fb[2] = s.aux[2]; }
+    if (s.step >= sc.shoot_start && s.step < sc.shoot_start + sc.shoot_frames) { Fb[0] = s.aux[0]; Fb[1] = s.aux[1]; Fb[2] = s.aux[2]; }
 #ifdef TB_HIT_GENERIC  // (A/B builds only: the generic step in line, as before hit_fast existed)
     int bits = physics_step<T, false>(sc, s, F, zero, Fb);
 #else
@@ -916,7 +917,7 @@ __device__ __forceinline__ bool env_substep(const Scene<T> &sc, St<T> &s, const 
 #endif
     int k = ++s.step;
     c.events = bits;
-    if (k < 5) { c.done = false; return true; }  // returns False regardless of self.done (tennisbot_env.py:138-139)
+    if (k < sc.shoot_frames) { c.done = false; return true; }  // returns False regardless of self.done (tennisbot_env.py:138-139)
     T dz = s.bp[2] - s.rp[2], dy = s.bp[1] - s.rp[1];
     T delta = M<T>::sqrt(dz * dz + dy * dy);
     T reward = 0;

@@ -108,7 +108,7 @@ template <typename T> __device__ __forceinline__ void store_state(T *base, int64
 // loaded them (spin changed) or restarted the episode (all fields fresh).
 // Returns whether pack 5 was loaded (if not, its aux half is unknown and a lane whose spin changes writes the spin half only).
 template <typename T, int KIND>
-__device__ __forceinline__ bool load_state_ctl(const T *base, int64_t n, int64_t i, uint64_t seed, uint64_t gid, St<T> &s) {
+__device__ __forceinline__ bool load_state_ctl(const T *base, int64_t n, int64_t i, uint64_t seed, uint64_t gid, int shoot_end, St<T> &s) {
   Pack<T> p0 = ld_pack(base, n, 0, i), p1 = ld_pack(base, n, 1, i), p2 = ld_pack(base, n, 2, i),
           p3 = ld_pack(base, n, 3, i), p4 = ld_pack(base, n, 4, i), p7 = ld_pack(base, n, 7, i);
   s.rp[0] = p0.x; s.rp[1] = p0.y; s.rp[2] = p0.z; s.bp[0] = p0.w;
@@ -119,7 +119,7 @@ __device__ __forceinline__ bool load_state_ctl(const T *base, int64_t n, int64_t
   s.ret = p7.x; s.step = (int)as_int(p7.y); s.flags = (int)as_int(p7.z); s.episode = (uint32_t)as_int(p7.w);
   const bool derived = (s.flags & kStDerived) != 0;
   // Tennisbot-v0 reads the shoot force (aux x, y in pack 5) during the first frames of every episode
-  const bool need5 = (s.flags & kStSpin) != 0 || (KIND == TB_ENV_HIT && s.step < 5) || (KIND == TB_ENV_SWING && !derived);
+  const bool need5 = (s.flags & kStSpin) != 0 || (KIND == TB_ENV_HIT && s.step < shoot_end) || (KIND == TB_ENV_SWING && !derived);
   s.bw[1] = 0; s.bw[2] = 0; s.aux[0] = 0; s.aux[1] = 0; s.aux[2] = 0; s.goal[0] = 0; s.goal[1] = 0; s.d0 = 0;
   if (need5) {
     Pack<T> p5 = ld_pack(base, n, 5, i);
@@ -262,6 +262,8 @@ constexpr int kCCtlDone = 65;     // entries of queue_ctl that have been stepped
 constexpr int kCDynTotal = 66;    // flights that were queued by the prologue (on top of step_kernel's three lists)
 constexpr int kCFinDone = 67;     // finishing pass 1: tiles of 32 envs that have been looked at
 constexpr int kCRetryTail = 68;   // ... envs that were still in flight then (listed in queue_ctl, finished in pass 2)
+constexpr int kCStarted = 9;      // ff_kernel CTAs that have taken their role; kCServers: those that are servers (role by SM)
+constexpr int kCServers = 10;
 constexpr int kCFinClaim = 7;     // finishing pass 1: claimed tiles
 constexpr int kCRetryClaim = 8;   // finishing pass 2: claimed entries of the retry list
 
@@ -556,7 +558,7 @@ __global__ void __launch_bounds__(kBlock, MINB ? MINB : StepMinBlocks<T, KIND>::
   }
   bool have5 = true;
   if (valid) {
-    have5 = load_state_ctl<T, KIND>(static_cast<const T *>(io.state), io.n, me, io.seed, (uint64_t)(io.id_offset + me), s);
+    have5 = load_state_ctl<T, KIND>(static_cast<const T *>(io.state), io.n, me, io.seed, (uint64_t)(io.id_offset + me), sc.shoot_start + sc.shoot_frames, s);
     if (!STAGE) load_action<KIND>(io.actions, me, a);
   }
   step_tile<T, KIND, STAGE, KIND == TB_ENV_SWING>(sc, io, qctr, tile0, me, rows, valid, s, a, ws, s_cnt, s_base, s_tile, have5);
@@ -1282,9 +1284,22 @@ __global__ void __launch_bounds__(kBlock, MinBlocks<T>::v) ff_kernel(const __gri
   // %smid; a grid that does not fill the device keeps one server warp per kServerStride CTAs.
   bool server = wib == kBlock / 32 - 1 && blockIdx.x % kServerStride == 0;
   if (io.server_sm_stride > 0) {
-    unsigned smid;
-    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-    server = smid % (unsigned)io.server_sm_stride == 0;
+    __shared__ int s_server;
+    if (threadIdx.x == 0) {
+      unsigned smid;
+      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+      int srv = smid % (unsigned)io.server_sm_stride == 0;
+      // Liveness does not depend on where the CTAs land: every CTA registers, and if the last one to start finds that no CTA
+      // is a server (other work kept the server SMs away from this grid), it becomes one.  As with per-CTA roles, the launch
+      // completes once all of its CTAs have run, whatever the order.
+      if (srv) atomicAdd(ctr + kCServers, 1ULL);
+      __threadfence();
+      const unsigned long long started = atomicAdd(ctr + kCStarted, 1ULL) + 1ULL;
+      if (!srv && started == (unsigned long long)gridDim.x && ld_ctr(ctr + kCServers) == 0) srv = 1;
+      s_server = srv;
+    }
+    __syncthreads();
+    server = s_server != 0;
   }
   if (server) ff_server_warp<T>(sc, io, epoch, nfull0, nctl, total0, &ws, &nsub);
   else ff_flight_warp<T>(sc, io, epoch, qn0, qfront, nctl, total0, ws, nsub);
@@ -1580,14 +1595,14 @@ struct Params {  // order matches k_param_names
   double dt, gravity_z, lin_damping, ang_damping, max_coord_vel, rest_ball_racket, rest_ball_court, rest_ball_goal,
       fric_ball_racket, fric_ball_court, fric_ball_goal, contact_erp, linear_slop, rest_vel_threshold,
       solver_iterations, solver_residual, contact_threshold, hull_margin, box_margin, gyro_term, racket_scale, pid_kp,
-      pid_ki, pid_kd, pid_max_force, pid_bias_z, pid_hit_z;
+      pid_ki, pid_kd, pid_max_force, pid_bias_z, pid_hit_z, shoot_start, shoot_frames;
 };
 static const char *k_param_names[] = {
     "dt", "gravity_z", "lin_damping", "ang_damping", "max_coord_vel", "rest_ball_racket", "rest_ball_court",
     "rest_ball_goal", "fric_ball_racket", "fric_ball_court", "fric_ball_goal", "contact_erp", "linear_slop",
     "rest_vel_threshold", "solver_iterations", "solver_residual", "contact_threshold", "hull_margin",
     "box_margin", "gyro_term", "racket_scale", "pid_kp", "pid_ki", "pid_kd", "pid_max_force", "pid_bias_z",
-    "pid_hit_z"};
+    "pid_hit_z", "shoot_start", "shoot_frames"};
 constexpr int kNumParams = sizeof(k_param_names) / sizeof(k_param_names[0]);
 static_assert(sizeof(Params) == kNumParams * sizeof(double), "Params / name table mismatch");
 
@@ -1619,6 +1634,8 @@ static void params_default(Params &p) {
   p.pid_max_force = 10.0;
   p.pid_bias_z = 4.0;    // racket.py:110
   p.pid_hit_z = 1.5;     // tennisbot_env.py:106
+  p.shoot_start = 0;     // tennisbot_env.py:118 (playground.py:99 shoots on frames 11 .. 49)
+  p.shoot_frames = 5;    // BALL_SHOOT_FRAMES, tennisbot_env.py:21
 }
 
 // quad_edges: indices of the two outline edges that bound the quadrilateral of prism_inside_fast (its other two sides
@@ -1757,6 +1774,7 @@ template <typename T> static void build_scene(const Params &p, Scene<T> &sc) {
   sc.pid_kp = (T)p.pid_kp; sc.pid_ki = (T)p.pid_ki; sc.pid_kd = (T)p.pid_kd; sc.pid_lim = (T)p.pid_max_force;
   sc.pid_bias_z = (T)p.pid_bias_z; sc.pid_hit_z = (T)p.pid_hit_z;
   sc.iters = (int)p.solver_iterations;
+  sc.shoot_start = (int)p.shoot_start; sc.shoot_frames = (int)p.shoot_frames;
   {
     T v = (T)p.max_coord_vel;
     unsigned long long bits = 0;
@@ -1834,8 +1852,21 @@ template <typename T> static void build_scene(const Params &p, Scene<T> &sc) {
     sc.ffp_box[0] = (T)((double)sc.racket_box[0] + reach_r + grow); sc.ffp_box[1] = (T)((double)sc.racket_box[1] - reach_r - grow);
     sc.ffp_box[2] = (T)((double)sc.racket_box[2] + reach_r + grow);
     sc.ffp_rim = (T)(reach_r + grow);
-    sc.racket.out_inv_a = (T)((1.0 - 1e-9) / ((double)sc.racket.out_a + (double)sc.ffp_rim));
-    sc.racket.out_inv_b = (T)((1.0 - 1e-9) / ((double)sc.racket.out_b + (double)sc.ffp_rim));
+    {
+      // prism_outside_fast's ellipse must CONTAIN everything within `rim` of the containing ellipse E(a, b).  Growing both semi-
+      // axes by rim is not enough (by the triangle inequality E(a + rim, b + rim) lies INSIDE the offset body, touching it on
+      // the axes only): scale it by gamma = max over directions of (h_E + rim) / h_E', h = support function
+      const double a = (double)sc.racket.out_a, b = (double)sc.racket.out_b, rim = (double)sc.ffp_rim;
+      double gamma = 1.0;
+      for (int k = 0; k <= 20000; ++k) {
+        const double th = 1.5707963267948966 * k / 20000.0, c = std::cos(th), sn = std::sin(th);
+        const double h = std::sqrt(a * a * c * c + b * b * sn * sn) + rim, hp = std::sqrt((a + rim) * (a + rim) * c * c + (b + rim) * (b + rim) * sn * sn);
+        gamma = std::fmax(gamma, h / hp);
+      }
+      gamma *= 1.0 + 1e-6;  // (sampling of the maximum, conversion to T)
+      sc.racket.out_inv_a = (T)(1.0 / (gamma * (a + rim)));
+      sc.racket.out_inv_b = (T)(1.0 / (gamma * (b + rim)));
+    }
     sc.ffl_inv_dt = (T)(1.0 / p.dt); sc.ffl_erp_dt = (T)(p.contact_erp / p.dt); sc.ffl_m = (T)TB_BALL_MASS;
     sc.ffl_jinv_t = (T)(1.0 / (1.0 / TB_BALL_MASS + TB_BALL_RADIUS * TB_BALL_RADIUS / (0.4 * TB_BALL_MASS * TB_BALL_RADIUS * TB_BALL_RADIUS)));
     sc.ffp_court[0] = sc.floor_h[0] + 1; sc.ffp_court[1] = sc.floor_h[1] + 1;
@@ -1968,7 +1999,7 @@ template <typename T> static int ff_grid_size(tb_ctx *c, unsigned *grid) {
   *grid = (unsigned)(need < resident ? need : resident);
   {
     const char *e = std::getenv("TB_FF_SERVER_SM_STRIDE");
-    int stride = e ? std::atoi(e) : 8;
+    int stride = e ? std::atoi(e) : 12;  // measured on B200 (1 Mi envs, f64): 12 -> 2.46 ms per fast-forward launch, 8 -> 2.59, 16 -> 2.99, per-CTA roles 2.60
     c->ff_server_sm_stride = (need >= resident && stride > 0 && stride <= sms) ? stride : 0;
   }
   return 0;
@@ -2091,8 +2122,9 @@ int tb_scene_constant(const char *name, int index, double *value) {
     build_scene<double>(p, sd);
     const double in_r[5] = {sd.racket.in_c, 1.0 / sd.racket.in_inv_a, 1.0 / sd.racket.in_inv_b, sd.racket.tz_lo, sd.racket.tz_hi};
     const double in_g[5] = {sd.goal.in_c, 1.0 / sd.goal.in_inv_a, 1.0 / sd.goal.in_inv_b, sd.goal.tz_lo, sd.goal.tz_hi};
-    const double out_r[4] = {sd.racket.out_a, sd.racket.out_b, sd.racket.out_v, sd.racket.out_lo};
-    if (!std::strcmp(name, "racket_outside") && index >= 0 && index < 4) { *value = out_r[index]; return 0; }
+    const double out_r[6] = {sd.racket.out_a, sd.racket.out_b, sd.racket.out_v, sd.racket.out_lo, sd.racket.out_inv_a, sd.racket.out_inv_b};
+    if (!std::strcmp(name, "racket_outside") && index >= 0 && index < 6) { *value = out_r[index]; return 0; }
+    if (!std::strcmp(name, "racket_rim")) { *value = sd.ffp_rim; return 0; }
     if (!std::strcmp(name, "racket_inside") && index >= 0 && index < 5) { *value = in_r[index]; return 0; }
     if (!std::strcmp(name, "goal_inside") && index >= 0 && index < 5) { *value = in_g[index]; return 0; }
     if (!std::strcmp(name, "racket_quad_edge") && index >= 0 && index < 8) {

@@ -7,7 +7,9 @@ SB3 is not a dependency (it is absent from this image): when it is importable th
 Contract kept (SB3 1.8, the version recorded in backup_models/ppo_swing.zip):
   reset() -> float32 [N, obs];  step_async(actions[N, act]);  step_wait() -> (obs, rewards f32[N], dones bool[N], infos)
   auto-reset on done with infos[i]["terminal_observation"], infos[i]["episode"] = {"r", "l", "t"} (VecMonitor
-  semantics) and infos[i]["TimeLimit.truncated"] on the 800 / 1000-step time-outs.
+  semantics).  The reference registers both envs WITHOUT max_episode_steps and returns an empty info dict, so SB3 treats
+  the 800 / 1000-step time-outs as terminations (no bootstrap from the terminal value); infos[i]["TimeLimit.truncated"] is
+  therefore only emitted on request (report_truncation=True).  infos[i]["events"] always carries the event bits.
 Returned arrays are fresh copies (SB3 keeps `_last_obs` across the next step).
 """
 import time
@@ -49,8 +51,11 @@ except Exception:
 
 
 class TennisVecEnv(_VecEnvBase):
-    def __init__(self, env_id="SwingRacket-v0", num_envs=4096, device=0, seed=0, precision="f64", env_id_offset=0):
+    def __init__(self, env_id="SwingRacket-v0", num_envs=4096, device=0, seed=0, precision="f64", env_id_offset=0,
+                 report_truncation=False):
         obs_space, act_space = spaces_for(env_id)
+        self.report_truncation = bool(report_truncation)
+        self._pending_scale = None
         super().__init__(num_envs, obs_space, act_space)
         self.env_id = env_id
         self.batch = TennisBatch(env_id, num_envs, device=device, seed=seed, precision=precision, auto_reset=True,
@@ -64,6 +69,9 @@ class TennisVecEnv(_VecEnvBase):
 
     # ---------------------------------------------------------------- VecEnv API
     def reset(self):
+        if self._pending_scale is not None:
+            self.batch.set_param("racket_scale", self._pending_scale)
+            self._pending_scale = None
         obs = self.batch.reset_host()
         self._ep_ret[:] = 0
         self._ep_len[:] = 0
@@ -95,8 +103,9 @@ class TennisVecEnv(_VecEnvBase):
             rows = term[idx].copy()
             for k, (i, r, l, e, t) in enumerate(zip(idx.tolist(), self._ep_ret[idx].tolist(), self._ep_len[idx].tolist(),
                                                     evs.tolist(), trunc)):
-                infos[i] = {"terminal_observation": rows[k], "episode": {"r": r, "l": l, "t": now},
-                            "TimeLimit.truncated": t, "events": e}
+                infos[i] = {"terminal_observation": rows[k], "episode": {"r": r, "l": l, "t": now}, "events": e}
+                if self.report_truncation:
+                    infos[i]["TimeLimit.truncated"] = t
             self._ep_ret[idx] = 0
             self._ep_len[idx] = 0
         return obs, rew, dones, infos
@@ -129,10 +138,17 @@ class TennisVecEnv(_VecEnvBase):
         return None
 
     # ---------------------------------------------------------------- reference-specific hooks
-    def set_racket_scale(self, scale):
-        """TennisbotEnv.set_racket_scale for the whole batch (train.py:155-176 calls it through the env)."""
+    def set_racket_scale(self, scale, apply_now=False):
+        """TennisbotEnv.set_racket_scale for the whole batch (train.py:155-176 calls it through the env).  As in the reference
+        (tennisbot_env.py:213-215,234) the scale is only stored here and takes effect at the next reset(): the hull, its
+        inertia and the COM offset are scene-wide in the kernels, so applying it at once would change the geometry under
+        every episode in flight (apply_now=True does exactly that, for scripted use)."""
         self.racket_scale = float(scale)
-        self.batch.set_param("racket_scale", self.racket_scale)
+        if apply_now:
+            self.batch.set_param("racket_scale", self.racket_scale)
+            self._pending_scale = None
+        else:
+            self._pending_scale = self.racket_scale
 
     def episode_statistics(self, clear=False):
         return stats_dict(self.batch.read_stats(clear=clear))

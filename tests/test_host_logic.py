@@ -43,7 +43,7 @@ def vec(monkeypatch):
 @pytest.mark.parametrize("env_id", ["SwingRacket-v0", "Tennisbot-v0"])
 def test_vecenv_contract(vec, env_id):
     n = 16
-    env = vec.TennisVecEnv(env_id, n, seed=5)
+    env = vec.TennisVecEnv(env_id, n, seed=5, report_truncation=True)
     assert env.num_envs == n and env.observation_space.shape[0] == env.batch.obs_dim
     obs = env.reset()
     assert obs.shape == (n, env.batch.obs_dim) and obs.dtype == np.float32
@@ -79,6 +79,34 @@ def test_vecenv_contract(vec, env_id):
     assert env.env_is_wrapped(object) == [False] * n and env.get_attr("num_envs", [0, 1]) == [n, n]
     st = env.episode_statistics()
     assert st["episodes"] == seen_done and st["env_steps"] == n * horizon
+    env.close()
+
+
+def test_vecenv_reference_defaults(vec):
+    """Reference behaviour by default: the envs are registered without max_episode_steps and return {} as info, so no
+    TimeLimit.truncated key (SB3 would bootstrap from the terminal value otherwise); set_racket_scale takes effect at the
+    next reset(), not under the episodes in flight (tennisbot_env.py:213-215,234)."""
+    from tennisbot_rl_b200.playground import RacketScaleCurriculum, curriculum_scale
+
+    env = vec.TennisVecEnv("Tennisbot-v0", 8, seed=1)
+    env.reset()
+    rng = np.random.default_rng(0)
+    seen = 0
+    for t in range(1010):
+        _, _, dones, infos = env.step(rng.uniform(-1, 1, (8, 2)).astype(np.float32))
+        for i in np.nonzero(dones)[0]:
+            assert "TimeLimit.truncated" not in infos[i] and "events" in infos[i] and "episode" in infos[i]
+            seen += 1
+    assert seen >= 8
+    cur = RacketScaleCurriculum(env, total_timesteps=1000)
+    assert cur.on_rollout_start(0) == 3.0 and env.batch.get_param("racket_scale") == 1.0  # stored, not applied yet
+    env.reset()
+    assert env.batch.get_param("racket_scale") == 3.0
+    env.set_racket_scale(1.3, apply_now=True)
+    assert env.batch.get_param("racket_scale") == 1.3
+    # train.py:166-176: percent_thresh [3, 5, 10, 15, 25, 45, 70, 101] -> scale [3, 2.6, 2.3, 2.1, 1.9, 1.7, 1.3, 1]
+    assert [curriculum_scale(p * 10, 1000) for p in (0, 2, 3, 4, 5, 9, 10, 14, 15, 24, 25, 44, 45, 69, 70, 100)] == \
+        [3, 3, 2.6, 2.6, 2.3, 2.3, 2.1, 2.1, 1.9, 1.9, 1.7, 1.7, 1.3, 1.3, 1, 1]
     env.close()
 
 

@@ -290,3 +290,24 @@ def test_host_staging_fallback_matches(oracle_lib):
         np.testing.assert_array_equal(done, ref["done"])
         np.testing.assert_allclose(obs, ref["obs"], atol=TOL_F64_OUT)
         np.testing.assert_allclose(rew, ref["reward"], atol=TOL_F64_OUT)
+
+
+@pytest.mark.parametrize("env,n,steps,every,tol_state", [("SwingRacket-v0", 262144, 78, 13, TOL_F64_STATE),
+                                                         ("Tennisbot-v0", 65536, 1100, 100, 1e-6)])
+def test_f64_parity_at_config_sizes(oracle_lib, env, n, steps, every, tol_state):
+    """BASELINE.json's batch sizes against the oracle step by step (config 3: 65 536 incoming-ball envs over whole episodes
+    incl. the 1000-step time-out; SwingRacket: 262 144 envs x 3 episodes = 786 k episodes): every event byte and done flag
+    identical, statistics identical.  State bar: the 4096-env tests' 5e-8 for SwingRacket (observed 5e-15 on mid-episode
+    records); 1e-6 for Tennisbot-v0 - the maximum over 7e7 env steps sits in a ball-spin entry (rad/s, values up to ~50)
+    right after a bounce on the closed-form floor contact and has been seen at 2e-7 to 3e-7."""
+    b, o = _make(env, n, "f64", 101, oracle_lib)
+    o.close() if hasattr(o, "close") else None
+    o = oracle_lib.OracleEnv(env, n, seed=101, threads=16)
+    rng = np.random.default_rng(77)
+    init = reference_reset_params(o.kind, n, rng)
+    np.testing.assert_array_equal(b.reset(init=init).cpu().numpy(), o.reset(init=init))
+    rep, valid = run_parity(b, o, steps, lambda t, _obs: rng.uniform(-1, 1, (n, o.act_dim)), band=0.0, check_state_every=every)
+    print(env, n, steps, rep)
+    assert rep.event_mismatch_hard == 0 and rep.event_mismatch_near == 0 and rep.dropped == 0
+    assert rep.max_state_err < tol_state and rep.max_obs_err < TOL_F64_OUT and rep.max_reward_err < TOL_F64_OUT
+    np.testing.assert_array_equal(b.read_stats(), o.read_stats())
