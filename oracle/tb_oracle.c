@@ -49,6 +49,11 @@ typedef struct {
   double pid_hit_z;            /* tennisbot_env.py:106 (commented call): z set-point appended to the 2-D hit action [C] */
   double shoot_start;          /* first env step on which the ball's shoot force acts: 0 in tennisbot_env.py:118; playground.py:99 uses 11 */
   double shoot_frames;         /* BALL_SHOOT_FRAMES = 5 (tennisbot_env.py:21); playground.py:16-17,99: 39 */
+  double racket_court_contact; /* 1: model the racket's contact with the court's floor box (court.urdf:19-24): up to four support
+                                  corners of the hull's oriented bounding box against the floor's top face.  0 (default): the racket
+                                  falls through the court once the control phase is over (TBO_EV_RACKET_LOW marks it) */
+  double rest_racket_court;    /* 0.9*0.9: racket.py:43 x objects.py:29 */
+  double fric_racket_court;    /* 0.2*0.2: racket.py:44 x objects.py:30 */
 } params_t;
 
 static const char *k_param_names[] = {
@@ -56,7 +61,7 @@ static const char *k_param_names[] = {
     "rest_ball_goal", "fric_ball_racket", "fric_ball_court", "fric_ball_goal", "contact_erp", "linear_slop",
     "rest_vel_threshold", "solver_iterations", "solver_residual", "contact_threshold", "hull_margin",
     "box_margin", "gyro_term", "racket_scale", "pid_kp", "pid_ki", "pid_kd", "pid_max_force", "pid_bias_z",
-    "pid_hit_z", "shoot_start", "shoot_frames"};
+    "pid_hit_z", "shoot_start", "shoot_frames", "racket_court_contact", "rest_racket_court", "fric_racket_court"};
 #define N_PARAMS ((int)(sizeof k_param_names / sizeof k_param_names[0]))
 
 static void params_default(params_t *p) {
@@ -89,6 +94,9 @@ static void params_default(params_t *p) {
   p->pid_hit_z = 1.5;
   p->shoot_start = 0;
   p->shoot_frames = 5;
+  p->racket_court_contact = 0;
+  p->rest_racket_court = 0.9 * 0.9;
+  p->fric_racket_court = 0.2 * 0.2;
 }
 
 /* ------------------------------------------------------------------------------------------------ state */
@@ -333,6 +341,8 @@ static void build_shapes(tbo_ctx *c) {
 /* ------------------------------------------------------------------------------------------------ contacts */
 typedef struct {
   int dynamic_a;   /* 1: other body is the racket, 0: static */
+  int has_ball;    /* 1: the ball is the second body; 0: racket against a static body (then n points racket -> static body
+                      and the static body takes the ball's place in every row with zero inverse mass and zero velocity) */
   double n[3];     /* unit normal, other body -> ball, world */
   double d;        /* signed distance between the inflated surfaces */
   double ra[3];    /* racket-side contact point relative to racket COM (world axes) */
@@ -380,7 +390,7 @@ static int physics_step(const tbo_ctx *c, double *s, const double *f_racket, con
   const double dt = P->dt, T = P->contact_threshold, rb = TBO_BALL_RADIUS;
   double R[9];
   quat_to_mat(s + S_RQ, R);
-  contact_t ct[4];
+  contact_t ct[8];
   int nc = 0, bits = 0;
 
   /* ---- (1) detection */
@@ -396,6 +406,7 @@ static int physics_step(const tbo_ctx *c, double *s, const double *f_racket, con
       probe(pb, d - T);
       if (d <= T) {
         contact_t *k = &ct[nc++];
+        k->has_ball = 1;
         k->dynamic_a = 1;
         mat_vec(R, nl, k->n);
         double qs[3] = {ql[0] + P->hull_margin * nl[0], ql[1] + P->hull_margin * nl[1], ql[2] + P->hull_margin * nl[2]};
@@ -420,6 +431,7 @@ static int physics_step(const tbo_ctx *c, double *s, const double *f_racket, con
       probe(pb, d - T);
       if (d <= T) {
         contact_t *k = &ct[nc++];
+        k->has_ball = 1;
         k->dynamic_a = 0;
         memcpy(k->n, n, sizeof n);
         k->ra[0] = k->ra[1] = k->ra[2] = 0;
@@ -440,6 +452,7 @@ static int physics_step(const tbo_ctx *c, double *s, const double *f_racket, con
         probe(pb, d - T);
         if (d <= T) {
           contact_t *k = &ct[nc++];
+          k->has_ball = 1;
           k->dynamic_a = 0;
           k->n[0] = nl[1]; k->n[1] = nl[2]; k->n[2] = nl[0];
           k->ra[0] = k->ra[1] = k->ra[2] = 0;
@@ -457,8 +470,43 @@ static int physics_step(const tbo_ctx *c, double *s, const double *f_racket, con
     {
       double low = s[S_RP + 2] - fabs(R[6]) * c->racket.half_thick - fabs(R[7]) * c->racket_box[0] +
                    fmin(R[8] * c->racket_box[1], R[8] * c->racket_box[2]) - P->hull_margin;
-      if (low <= TBO_FLOOR_HZ + T && fabs(s[S_RP]) <= TBO_FLOOR_HX + 1 && fabs(s[S_RP + 1]) <= TBO_FLOOR_HY + 1)
+      if (low <= TBO_FLOOR_HZ + T && fabs(s[S_RP]) <= TBO_FLOOR_HX + 1 && fabs(s[S_RP + 1]) <= TBO_FLOOR_HY + 1) {
         bits |= TBO_EV_RACKET_LOW;
+        if (P->racket_court_contact != 0) {
+          /* Racket vs the floor box's top face: the corners of the hull's oriented bounding box (outline box x plate
+           * thickness, inflated by the hull margin) that are within the contact threshold of the face and over it, the four
+           * deepest if there are more (a manifold holds four points), in corner order.  Normal: racket -> floor = -z. */
+          double dz[8], cr[8][3];
+          int idx[8], m = 0;
+          for (int q = 0; q < 8; ++q) {
+            const double l[3] = {(q & 1) ? c->racket.half_thick : -c->racket.half_thick, (q & 2) ? c->racket_box[0] : -c->racket_box[0],
+                                 (q & 4) ? c->racket_box[2] : c->racket_box[1]};
+            double w[3];
+            mat_vec(R, l, w);
+            const double px = s[S_RP] + w[0], py = s[S_RP + 1] + w[1], pz = s[S_RP + 2] + w[2];
+            const double d = pz - P->hull_margin - TBO_FLOOR_HZ;
+            if (d <= T && fabs(px) <= TBO_FLOOR_HX && fabs(py) <= TBO_FLOOR_HY) {
+              dz[m] = d; cr[m][0] = w[0]; cr[m][1] = w[1]; cr[m][2] = w[2] - P->hull_margin; idx[m] = q; ++m;
+            }
+          }
+          while (m > 4) { /* drop the shallowest (first of equals) */
+            int worst = 0;
+            for (int q = 1; q < m; ++q) if (dz[q] > dz[worst]) worst = q;
+            for (int q = worst; q + 1 < m; ++q) { dz[q] = dz[q + 1]; idx[q] = idx[q + 1]; memcpy(cr[q], cr[q + 1], sizeof cr[q]); }
+            --m;
+          }
+          for (int q = 0; q < m; ++q) {
+            contact_t *k = &ct[nc++];
+            k->has_ball = 0;
+            k->dynamic_a = 1;
+            k->n[0] = 0; k->n[1] = 0; k->n[2] = -1;
+            memcpy(k->ra, cr[q], sizeof k->ra);
+            k->d = dz[q];
+            k->rest = P->rest_racket_court;
+            k->mu = P->fric_racket_court;
+          }
+        }
+      }
     }
   }
 
@@ -492,7 +540,7 @@ static int physics_step(const tbo_ctx *c, double *s, const double *f_racket, con
   /* ---- (3) contact solve (A.6): per contact a normal row and two friction rows coupled by a cone clamp */
   if (nc > 0) {
     const double ib = 0.4 * mb * rb * rb; /* sphere inertia recomputed from the shape, URDF's 1.0 ignored [R] */
-    row_t rows[4][3];
+    row_t rows[8][3];
     double dvb[3] = {0, 0, 0}, dwb[3] = {0, 0, 0}, dva[3] = {0, 0, 0}, dwa[3] = {0, 0, 0};
     for (int k = 0; k < nc; ++k) {
       contact_t *q = &ct[k];
@@ -503,9 +551,14 @@ static int physics_step(const tbo_ctx *c, double *s, const double *f_racket, con
       for (int r = 0; r < 3; ++r) {
         row_t *w = &rows[k][r];
         memcpy(w->u, dirs[r], sizeof w->u);
-        cross3(rbv, w->u, w->rbxu);
-        double denom = 1.0 / mb + dot3(w->rbxu, w->rbxu) / ib;
-        double rel = dot3(w->u, s + S_BV) + dot3(w->rbxu, s + S_BW);
+        double denom = 0, rel = 0;
+        if (q->has_ball) {
+          cross3(rbv, w->u, w->rbxu);
+          denom = 1.0 / mb + dot3(w->rbxu, w->rbxu) / ib;
+          rel = dot3(w->u, s + S_BV) + dot3(w->rbxu, s + S_BW);
+        } else {
+          w->rbxu[0] = w->rbxu[1] = w->rbxu[2] = 0;
+        }
         if (q->dynamic_a) {
           cross3(q->ra, w->u, w->raxu);
           double l[3], li[3];
@@ -543,8 +596,7 @@ static int physics_step(const tbo_ctx *c, double *s, const double *f_racket, con
         if (sum < 0) { dl = -w->lam; sum = 0; }
         w->lam = sum;
         for (int i = 0; i < 3; ++i) {
-          dvb[i] += w->u[i] * dl / mb;
-          dwb[i] += w->rbxu[i] * dl / ib;
+          if (ct[k].has_ball) { dvb[i] += w->u[i] * dl / mb; dwb[i] += w->rbxu[i] * dl / ib; }
           if (ct[k].dynamic_a) { dva[i] -= w->u[i] * dl / mr; dwa[i] -= w->ia_raxu[i] * dl; }
         }
         double rr = dl / w->jinv;
@@ -570,8 +622,7 @@ static int physics_step(const tbo_ctx *c, double *s, const double *f_racket, con
           double d = sum[r] - w->lam;
           w->lam = sum[r];
           for (int i = 0; i < 3; ++i) {
-            dvb[i] += w->u[i] * d / mb;
-            dwb[i] += w->rbxu[i] * d / ib;
+            if (ct[k].has_ball) { dvb[i] += w->u[i] * d / mb; dwb[i] += w->rbxu[i] * d / ib; }
             if (ct[k].dynamic_a) { dva[i] -= w->u[i] * d / mr; dwa[i] -= w->ia_raxu[i] * d; }
           }
           double rr = d / w->jinv;

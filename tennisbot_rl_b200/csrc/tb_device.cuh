@@ -136,6 +136,9 @@ template <typename T> struct Scene {
   T rest_racket, rest_court, rest_goal, mu_racket, mu_court, mu_goal;
   T erp, slop, rest_vel_threshold, solver_residual, contact_threshold, hull_margin, box_margin, gyro;
   int iters, shoot_start, shoot_frames;  // Tennisbot-v0: env steps on which the ball's shoot force acts (tennisbot_env.py:21,118)
+  int racket_court;                      // 1: racket vs the court's floor box is modelled (parameter racket_court_contact), on the
+                                         // generic path only: a state with TB_EV_RACKET_LOW never takes a straight-line substep then
+  T rest_racket_court, mu_racket_court;
   unsigned vmax_hi;  // high 32 bits of max_coord_vel in T's format (clamp_velocities)
   T pid_kp, pid_ki, pid_kd, pid_lim, pid_bias_z, pid_hit_z;  // TB_CONTROL_PID (racket.py:47-64,103-122)
   T ball_r, ball_inv_m, ball_inv_i, racket_inv_m;
@@ -343,9 +346,11 @@ template <typename T, int NE> __device__ __forceinline__ bool prism_outside_fast
   return far_head & far_quad;
 }
 // ------------------------------------------------------------------------------------------------ contacts
-constexpr int kMaxContacts = 4;
+constexpr int kMaxContacts = 8;  // the ball's (racket, floor, net, goal) + up to four racket-floor points
 template <typename T> struct Contact {
-  int dyn;
+  int dyn;   // the racket takes part (as the body the normal points away from)
+  int ball;  // the ball is the second body; 0: racket against a static body - the static body takes the ball's place in every
+             // row with zero inverse mass and zero velocity, and n points racket -> static body
   T n[3], d, ra[3], rest, mu;
 };
 template <typename T> struct Row {
@@ -364,7 +369,7 @@ template <typename T> struct SolveIO {
   T rq[4], bv[3], bw[3], rv[3], rw[3];  // in: pose + velocities after force integration
   T dvb[3], dwb[3], dva[3], dwa[3];     // out: velocity changes
 };
-constexpr int kNeedRacket = 1, kNeedFloor = 2, kNeedNet = 4, kNeedGoal = 8;
+constexpr int kNeedRacket = 1, kNeedFloor = 2, kNeedNet = 4, kNeedGoal = 8, kNeedRacketFloor = 16;
 
 // Projected Gauss-Seidel over the ball's contacts: per contact one normal row and a friction pair with an
 // implicit cone clamp, early exit on the squared-residual threshold (A.6).  Rare path (about one physics step
@@ -410,9 +415,14 @@ __device__ __forceinline__ void solve_impl(const Scene<T> &sc, const ContactSet<
     for (int r = 0; r < 3; ++r) {
       Row<S> &w = rows[k][r];
       w.u[0] = dirs[r][0]; w.u[1] = dirs[r][1]; w.u[2] = dirs[r][2];
-      cross3(rbv, w.u, w.rbxu);
-      S denom = inv_mb + dot3(w.rbxu, w.rbxu) * inv_ib;
-      S rel = dot3(w.u, bv) + dot3(w.rbxu, bw);
+      S denom = 0, rel = 0;
+      if (c.ball) {
+        cross3(rbv, w.u, w.rbxu);
+        denom = inv_mb + dot3(w.rbxu, w.rbxu) * inv_ib;
+        rel = dot3(w.u, bv) + dot3(w.rbxu, bw);
+      } else {
+        w.rbxu[0] = w.rbxu[1] = w.rbxu[2] = 0;
+      }
       if (c.dyn) {
         cross3(ra, w.u, w.raxu);
         S l[3], li[3];
@@ -453,8 +463,7 @@ __device__ __forceinline__ void solve_impl(const Scene<T> &sc, const ContactSet<
       w.lam = sum;
 #pragma unroll
       for (int i = 0; i < 3; ++i) {
-        dvb[i] += w.u[i] * dl * inv_mb;
-        dwb[i] += w.rbxu[i] * dl * inv_ib;
+        if (ct[k].ball) { dvb[i] += w.u[i] * dl * inv_mb; dwb[i] += w.rbxu[i] * dl * inv_ib; }
         if (ct[k].dyn) { dva[i] -= w.u[i] * dl * inv_mr; dwa[i] -= w.ia[i] * dl; }
       }
       S rr = dl * w.denom;  // (= dl / jinv to an ulp; feeds the early-exit test only: no division on the servers' critical path)
@@ -484,8 +493,7 @@ __device__ __forceinline__ void solve_impl(const Scene<T> &sc, const ContactSet<
         w.lam = sum[r];
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
-          dvb[i] += w.u[i] * d * inv_mb;
-          dwb[i] += w.rbxu[i] * d * inv_ib;
+          if (ct[k].ball) { dvb[i] += w.u[i] * d * inv_mb; dwb[i] += w.rbxu[i] * d * inv_ib; }
           if (ct[k].dyn) { dva[i] -= w.u[i] * d * inv_mr; dwa[i] -= w.ia[i] * d; }
         }
         S rr = d * w.denom;
@@ -513,7 +521,7 @@ __device__ __noinline__ int narrow_phase(const Scene<T> &sc, int need, const Nar
   int nc = 0, bits = 0;
   const T thr = sc.contact_threshold;
   T R[9];
-  if (need & kNeedRacket) quat_to_mat(in->rq, R);
+  if (need & (kNeedRacket | kNeedRacketFloor)) quat_to_mat(in->rq, R);
   if (need & kNeedRacket) {
     T rel[3] = {in->bp[0] - in->rp[0], in->bp[1] - in->rp[1], in->bp[2] - in->rp[2]}, pl[3];
     matT_vec(R, rel, pl);
@@ -527,7 +535,7 @@ __device__ __noinline__ int narrow_phase(const Scene<T> &sc, int need, const Nar
       T d = dc - (sc.ball_r + sc.hull_margin);
       if (d <= thr) {
         Contact<T> &k = cs->c[nc++];
-        k.dyn = 1;
+        k.dyn = 1; k.ball = 1;
         mat_vec(R, nl, k.n);
         T qs[3] = {ql[0] + sc.hull_margin * nl[0], ql[1] + sc.hull_margin * nl[1], ql[2] + sc.hull_margin * nl[2]};
         mat_vec(R, qs, k.ra);
@@ -545,7 +553,7 @@ __device__ __noinline__ int narrow_phase(const Scene<T> &sc, int need, const Nar
     T d = dc - (sc.ball_r + sc.box_margin);
     if (d <= thr) {
       Contact<T> &k = cs->c[nc++];
-      k.dyn = 0;
+      k.dyn = 0; k.ball = 1;
       k.n[0] = n[0]; k.n[1] = n[1]; k.n[2] = n[2];
       k.ra[0] = k.ra[1] = k.ra[2] = 0;
       k.d = d; k.rest = sc.rest_court; k.mu = sc.mu_court;
@@ -559,14 +567,56 @@ __device__ __noinline__ int narrow_phase(const Scene<T> &sc, int need, const Nar
     T d = dc - (sc.ball_r + sc.hull_margin);
     if (d <= thr) {
       Contact<T> &k = cs->c[nc++];
-      k.dyn = 0;
+      k.dyn = 0; k.ball = 1;
       k.n[0] = nl[1]; k.n[1] = nl[2]; k.n[2] = nl[0];
       k.ra[0] = k.ra[1] = k.ra[2] = 0;
       k.d = d; k.rest = sc.rest_goal; k.mu = sc.mu_goal;
       bits |= TB_EV_GOAL_BALL;
     }
   }
+  if (need & kNeedRacketFloor) {
+    // Racket vs the floor box's top face (court.urdf:19-24): the corners of the hull's oriented bounding box (outline box x
+    // plate thickness, inflated by the hull margin) that are within the contact threshold of the face and over it, the four
+    // deepest if there are more (a manifold holds four points), in corner order.  Normal: racket -> floor = -z.
+    T dz[8], cr[8][3];
+    int m = 0;
+#pragma unroll 1
+    for (int q = 0; q < 8; ++q) {
+      const T l[3] = {(q & 1) ? sc.racket.half_thick : -sc.racket.half_thick, (q & 2) ? sc.racket_obb[0] : -sc.racket_obb[0],
+                      (q & 4) ? sc.racket_obb[2] : sc.racket_obb[1]};
+      T w[3];
+      mat_vec(R, l, w);
+      const T px = in->rp[0] + w[0], py = in->rp[1] + w[1], pz = in->rp[2] + w[2];
+      const T d = pz - sc.hull_margin - sc.floor_h[2];
+      if (d <= thr && M<T>::abs(px) <= sc.floor_h[0] && M<T>::abs(py) <= sc.floor_h[1]) {
+        dz[m] = d; cr[m][0] = w[0]; cr[m][1] = w[1]; cr[m][2] = w[2] - sc.hull_margin; ++m;
+      }
+    }
+    while (m > 4) {  // drop the shallowest (first of equals)
+      int worst = 0;
+      for (int q = 1; q < m; ++q) if (dz[q] > dz[worst]) worst = q;
+      for (int q = worst; q + 1 < m; ++q) { dz[q] = dz[q + 1]; cr[q][0] = cr[q + 1][0]; cr[q][1] = cr[q + 1][1]; cr[q][2] = cr[q + 1][2]; }
+      --m;
+    }
+    for (int q = 0; q < m; ++q) {
+      Contact<T> &k = cs->c[nc++];
+      k.dyn = 1; k.ball = 0;
+      k.n[0] = 0; k.n[1] = 0; k.n[2] = -1;
+      k.ra[0] = cr[q][0]; k.ra[1] = cr[q][1]; k.ra[2] = cr[q][2];
+      k.d = dz[q]; k.rest = sc.rest_racket_court; k.mu = sc.mu_racket_court;
+    }
+  }
   return bits | (nc << 8);
+}
+
+// TB_EV_RACKET_LOW: the lowest corner of the hull's oriented bounding box (outline box x plate thickness, margin included) is
+// at or below the floor's contact threshold while the COM is over the court (same expression wherever it is evaluated)
+template <typename T> __device__ __forceinline__ bool racket_low(const Scene<T> &sc, const T *rp, const T *rq) {
+  const T x = rq[0], y = rq[1], z = rq[2], w = rq[3];
+  T r6 = 2 * (x * z - y * w), r7 = 2 * (y * z + x * w), r8 = 1 - 2 * (x * x + y * y);
+  T zlo = r8 * sc.racket_obb[1], zhi = r8 * sc.racket_obb[2];
+  T low = rp[2] - M<T>::abs(r6) * sc.racket.half_thick - M<T>::abs(r7) * sc.racket_obb[0] + (zlo < zhi ? zlo : zhi) - sc.hull_margin;
+  return (low <= sc.ffp_low) & (M<T>::abs(rp[0]) <= sc.ffp_court[0]) & (M<T>::abs(rp[1]) <= sc.ffp_court[1]);
 }
 
 // Half-angle factors of one substep's rotation, as even functions of |omega|: with x = |omega| dt / 2,
@@ -673,6 +723,7 @@ __device__ __forceinline__ int physics_step(const Scene<T> &sc, St<T> &s, const 
       bits |= (low <= sc.floor_h[2] + thr && M<T>::abs(s.rp[0]) <= sc.floor_h[0] + 1 && M<T>::abs(s.rp[1]) <= sc.floor_h[1] + 1)
                   ? TB_EV_RACKET_LOW : 0;
     }
+    if (sc.racket_court && (bits & TB_EV_RACKET_LOW)) need |= kNeedRacketFloor;
     if (TB_UNLIKELY(need)) {
       NarrowIn<T> in;
 #pragma unroll
@@ -1039,6 +1090,7 @@ template <typename T> __device__ __forceinline__ bool ff_substep(const Scene<T> 
       bits |= (low <= sc.floor_h[2] + thr && M<T>::abs(s.rp[0]) <= sc.floor_h[0] + 1 && M<T>::abs(s.rp[1]) <= sc.floor_h[1] + 1)
                   ? TB_EV_RACKET_LOW : 0;
     }
+    if (sc.racket_court && (bits & TB_EV_RACKET_LOW)) need |= kNeedRacketFloor;
     if (TB_UNLIKELY(need)) {
       NarrowIn<T> in;
 #pragma unroll
@@ -1196,6 +1248,7 @@ __device__ __forceinline__ int ff_classify_core(const Scene<T> &sc, const T *rp,
   const T ax = M<T>::abs(bp[0]), ay = M<T>::abs(bp[1]), az = M<T>::abs(bp[2]);
   bool full = racket | (!(ax > sc.ffp_net[0]) & !(az > sc.ffp_net[2]) & !(ay > sc.ffp_net[1])) |
               !(nb < sc.ffp_v2) | !(nr < sc.ffp_v2) | !(nw < sc.ffp_a2);
+  if (TB_UNLIKELY(sc.racket_court != 0)) full |= racket_low(sc, rp, rq);  // racket-court contact lives on the generic path
   if (WITH_GOAL) {  // SwingRacket: the goal disc and the 800-step time-out (Tennisbot-v0 has neither in its scene)
     T gx = bp[0] - goal[0], gy = bp[1] - goal[1];
     full |= (!(az > sc.ffp_goal_z) & !(gx * gx + gy * gy > sc.ffp_goal_r2)) | (step >= 800);
@@ -1595,6 +1648,7 @@ __device__ __noinline__ int ff_contact_lean(const Scene<T> &sc, FfLane<T> *Lp, i
     T zlo = R[8] * sc.racket_obb[1], zhi = R[8] * sc.racket_obb[2];
     T low = rp[2] - M<T>::abs(R[6]) * sc.racket.half_thick - M<T>::abs(R[7]) * sc.racket_obb[0] + (zlo < zhi ? zlo : zhi) - sc.hull_margin;
     bits |= (low <= sc.floor_h[2] + thr && M<T>::abs(rp[0]) <= sc.floor_h[0] + 1 && M<T>::abs(rp[1]) <= sc.floor_h[1] + 1) ? TB_EV_RACKET_LOW : 0;
+    if (sc.racket_court && bits) return -1;  // racket on the court: its contact points join the solve (generic path)
   }
   // ---- (2) velocities, as in ff_substep
   T bv[3] = {Lp->bv[0], Lp->bv[1], Lp->bv[2]}, bw[3] = {Lp->bw[0], Lp->bw[1], Lp->bw[2]};

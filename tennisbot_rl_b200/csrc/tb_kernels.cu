@@ -1595,14 +1595,15 @@ struct Params {  // order matches k_param_names
   double dt, gravity_z, lin_damping, ang_damping, max_coord_vel, rest_ball_racket, rest_ball_court, rest_ball_goal,
       fric_ball_racket, fric_ball_court, fric_ball_goal, contact_erp, linear_slop, rest_vel_threshold,
       solver_iterations, solver_residual, contact_threshold, hull_margin, box_margin, gyro_term, racket_scale, pid_kp,
-      pid_ki, pid_kd, pid_max_force, pid_bias_z, pid_hit_z, shoot_start, shoot_frames;
+      pid_ki, pid_kd, pid_max_force, pid_bias_z, pid_hit_z, shoot_start, shoot_frames, racket_court_contact, rest_racket_court,
+      fric_racket_court;
 };
 static const char *k_param_names[] = {
     "dt", "gravity_z", "lin_damping", "ang_damping", "max_coord_vel", "rest_ball_racket", "rest_ball_court",
     "rest_ball_goal", "fric_ball_racket", "fric_ball_court", "fric_ball_goal", "contact_erp", "linear_slop",
     "rest_vel_threshold", "solver_iterations", "solver_residual", "contact_threshold", "hull_margin",
     "box_margin", "gyro_term", "racket_scale", "pid_kp", "pid_ki", "pid_kd", "pid_max_force", "pid_bias_z",
-    "pid_hit_z", "shoot_start", "shoot_frames"};
+    "pid_hit_z", "shoot_start", "shoot_frames", "racket_court_contact", "rest_racket_court", "fric_racket_court"};
 constexpr int kNumParams = sizeof(k_param_names) / sizeof(k_param_names[0]);
 static_assert(sizeof(Params) == kNumParams * sizeof(double), "Params / name table mismatch");
 
@@ -1636,6 +1637,9 @@ static void params_default(Params &p) {
   p.pid_hit_z = 1.5;     // tennisbot_env.py:106
   p.shoot_start = 0;     // tennisbot_env.py:118 (playground.py:99 shoots on frames 11 .. 49)
   p.shoot_frames = 5;    // BALL_SHOOT_FRAMES, tennisbot_env.py:21
+  p.racket_court_contact = 0;        // 1: racket vs the court's floor box on the generic path (see Scene::racket_court)
+  p.rest_racket_court = 0.9 * 0.9;   // racket.py:43 x objects.py:29
+  p.fric_racket_court = 0.2 * 0.2;   // racket.py:44 x objects.py:30
 }
 
 // quad_edges: indices of the two outline edges that bound the quadrilateral of prism_inside_fast (its other two sides
@@ -1775,6 +1779,7 @@ template <typename T> static void build_scene(const Params &p, Scene<T> &sc) {
   sc.pid_bias_z = (T)p.pid_bias_z; sc.pid_hit_z = (T)p.pid_hit_z;
   sc.iters = (int)p.solver_iterations;
   sc.shoot_start = (int)p.shoot_start; sc.shoot_frames = (int)p.shoot_frames;
+  sc.racket_court = p.racket_court_contact != 0; sc.rest_racket_court = (T)p.rest_racket_court; sc.mu_racket_court = (T)p.fric_racket_court;
   {
     T v = (T)p.max_coord_vel;
     unsigned long long bits = 0;

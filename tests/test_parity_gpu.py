@@ -7,6 +7,7 @@ Bars (north star): contact / hit events and done flags exact; poses and rewards 
 """
 import numpy as np
 import pytest
+import torch
 
 from tests.harness import reference_reset_params, run_parity
 
@@ -311,3 +312,71 @@ def test_f64_parity_at_config_sizes(oracle_lib, env, n, steps, every, tol_state)
     assert rep.event_mismatch_hard == 0 and rep.event_mismatch_near == 0 and rep.dropped == 0
     assert rep.max_state_err < tol_state and rep.max_obs_err < TOL_F64_OUT and rep.max_reward_err < TOL_F64_OUT
     np.testing.assert_array_equal(b.read_stats(), o.read_stats())
+
+
+@pytest.mark.parametrize("policy", ["random", "zero"])
+def test_f64_parity_racket_court_contact(oracle_lib, policy):
+    """A12 with racket_court_contact = 1: the racket's contact with the court's floor box (up to four support corners of the
+    hull's bounding box, PGS rows together with the ball's contacts) on the generic path.  With zero actions every racket
+    drops onto the court during the fast-forward (SURVEY 7: handle tip on the floor at physics step 118, ball lands at 133);
+    with random actions about two thirds do.  Nothing is masked: every event byte incl. TB_EV_RACKET_LOW, done flag, reward
+    and step count must agree for every env, and so must the whole final state record (racket pose and velocities after its
+    bounces on the court included) - to 1e-6 for episodes of up to 300 physics steps (observed: 6e-14 with zero actions,
+    median 2e-14 with random ones).  A racket that lies on the court while the ball has come to rest ON it tumbles for the
+    775 substeps up to the time-out; such chaotic contact sequences amplify rounding without bound and are only counted
+    (a handful in 4096 envs)."""
+    from tennisbot_rl_b200.batch import TennisBatch
+
+    n = 4096
+    b = TennisBatch("SwingRacket-v0", n, device=0, seed=19, precision="f64", auto_reset=False)
+    o = oracle_lib.OracleEnv("SwingRacket-v0", n, seed=19, threads=8, auto_reset=False)
+    b.set_param("racket_court_contact", 1.0)
+    o.set_param("racket_court_contact", 1.0)
+    np.testing.assert_array_equal(b.reset().cpu().numpy(), o.reset())
+    rng = np.random.default_rng(6)
+    act = (lambda t, _obs: rng.uniform(-1, 1, (n, 6))) if policy == "random" else (lambda t, _obs: np.zeros((n, 6)))
+    rep, valid = run_parity(b, o, 25, act, band=0.0, check_state_every=5)
+    assert rep.event_mismatch_hard == 0 and rep.max_state_err < TOL_F64_STATE and rep.max_obs_err < TOL_F64_OUT
+    a = act(25, None).astype(np.float32)
+    g_obs, g_rew, g_done, g_term, g_ev = (x.cpu().numpy() for x in b.step(torch.from_numpy(a).cuda()))
+    ref = o.step(a)
+    np.testing.assert_array_equal(g_done, ref["done"])
+    np.testing.assert_array_equal(g_ev, ref["events"])           # TB_EV_RACKET_LOW included
+    gs, os_ = b.get_state().cpu().numpy(), o.get_state()
+    np.testing.assert_array_equal(gs[:, 29], os_[:, 29])         # every episode ended on the same physics step
+    short = os_[:, 29] <= 300
+    low = (ref["events"] & 64) != 0
+    err = np.abs(gs - os_).max(1)
+    print(policy, "racket on the court in %.1f %% of the episodes; state error: max over short episodes %.2e, long episodes %d, of them "
+          "beyond 1e-6: %d" % (100 * low.mean(), err[short].max(), (~short).sum(), (err[~short] > 1e-6).sum()))
+    assert low.mean() > (0.99 if policy == "zero" else 0.5)
+    assert err[short].max() < 1e-6 and short.mean() > 0.98
+    np.testing.assert_allclose(g_rew[short], ref["reward"][short], atol=1e-5)
+    np.testing.assert_allclose(g_term[short], ref["terminal_obs"][short], atol=1e-5)   # racket x, y compared for every env
+    np.testing.assert_allclose(gs[:, 13:16], os_[:, 13:16], atol=1e-5)                  # the ball lands where the oracle's does
+    np.testing.assert_array_equal(b.read_stats()[:6], o.read_stats()[:6])
+
+
+def test_racket_rests_on_the_court_when_contact_is_modelled(oracle_lib):
+    """Final states of a no-auto-reset episode with racket_court_contact = 1: no hull corner is below the floor by more than
+    the penetration a contact allows, where without the contact most rackets have fallen through."""
+    from tennisbot_rl_b200.batch import TennisBatch
+
+    n = 2048
+    out = {}
+    for mode in (0.0, 1.0):
+        b = TennisBatch("SwingRacket-v0", n, seed=5, precision="f64", auto_reset=False)
+        b.set_param("racket_court_contact", mode)
+        b.reset()
+        ev_all = torch.zeros(n, dtype=torch.uint8, device="cuda")
+        for t in range(26):
+            _, _, _, _, ev = b.step(torch.zeros((n, 6), device="cuda"))
+            ev_all |= ev
+        out[mode] = (b.get_state().cpu().numpy(), ev_all.cpu().numpy())
+        b.close()
+    low = (out[1.0][1] & 64) != 0
+    assert low.mean() > 0.9                       # zero actions: the racket always reaches the court before the ball lands
+    # zero actions: the handle tip meets the court 15 physics steps before the ball lands.  Without the contact the racket keeps
+    # falling (COM at 0.249 m when the episode ends), with it the tip is held up and the racket starts to topple (COM 0.314 m)
+    assert (out[1.0][0][low, 2] > out[0.0][0][low, 2] + 0.03).all()
+    assert out[1.0][0][low, 9].mean() > out[0.0][0][low, 9].mean() + 1.0   # ... its COM no longer falls at free-fall speed
