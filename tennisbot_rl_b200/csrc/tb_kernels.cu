@@ -9,6 +9,7 @@
 //   pack3 racket angvel xyz | ball pos z   pack7 return | step | flags | episode   (integers bit-cast)
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstddef>
 #include <cstdio>
@@ -174,6 +175,11 @@ struct StepIO {
                                      // without synchronising
   volatile unsigned long long *fault_host;
   long long spin_limit;              // clock cycles any wait inside ff_kernel may take before the launch gives up
+  int64_t env_lo, env_hi;            // step_kernel: the envs [env_lo, env_hi) of this launch (tb_step_host steps the batch in slices
+                                     // so that uploads, kernels and downloads overlap); the per-step bookkeeping belongs to the
+                                     // slice that starts at env 0
+  volatile unsigned *ff_ran_host;    // mapped host word ff_kernel sets when it had anything to do (it then wrote outputs of envs
+                                     // in any slice), or nullptr
   int server_sm_stride;              // ff_kernel: > 0 = every warp on an SM whose id is a multiple of this is a server warp and
                                      // all others are flight warps (full persistent grids); 0 = one server warp per
                                      // kServerStride CTAs
@@ -518,15 +524,15 @@ __global__ void __launch_bounds__(kBlock, MINB ? MINB : StepMinBlocks<T, KIND>::
   ws.init(sacc[wib], lane);
   const unsigned e = io.epoch[0];  // index of this step; constant while this grid runs (ff_kernel advances it)
   unsigned long long *qctr = ctr_set(io, e);
-  if (blockIdx.x == 0) {
+  if (blockIdx.x == 0 && io.env_lo == 0) {
     unsigned long long *next = ctr_set(io, e + 1u);
     for (int i = threadIdx.x; i < kCtrWords; i += kBlock) next[i] = 0;
     if (threadIdx.x == 0) io.epoch[1] = e + 1u;  // the tag of this step's queue slots, never 0
   }
 
-  const int64_t tile0 = (int64_t)blockIdx.x * kBlock + wib * 32, me = tile0 + lane;
-  const bool valid = me < io.n;
-  const int rows = io.n - tile0 >= 32 ? 32 : (io.n > tile0 ? (int)(io.n - tile0) : 0);
+  const int64_t tile0 = io.env_lo + (int64_t)blockIdx.x * kBlock + wib * 32, me = tile0 + lane;
+  const bool valid = me < io.env_hi;
+  const int rows = io.env_hi - tile0 >= 32 ? 32 : (io.env_hi > tile0 ? (int)(io.env_hi - tile0) : 0);
   St<T> s;
   float a[8];
   if (STAGE) {
@@ -546,8 +552,8 @@ __global__ void __launch_bounds__(kBlock, MINB ? MINB : StepMinBlocks<T, KIND>::
   // 15 % faster in float32 but slower in float64: two 35 KB stages x 3 CTAs leave almost no L1 for the rare paths'
   // local-memory records.  Measured on B200, see DESIGN.md.)
   if (!STAGE && threadIdx.x == 0 && io.prefetch_ahead > 0) {
-    const int64_t e0 = ((int64_t)blockIdx.x + io.prefetch_ahead) * kBlock;
-    if (e0 + kBlock <= io.n) {
+    const int64_t e0 = io.env_lo + ((int64_t)blockIdx.x + io.prefetch_ahead) * kBlock;
+    if (e0 + kBlock <= io.env_hi) {
       const T *b0 = static_cast<const T *>(io.state);
 #pragma unroll
       for (int p = 0; p < kPacks; ++p)
@@ -1270,6 +1276,7 @@ __global__ void __launch_bounds__(kBlock, MinBlocks<T>::v) ff_kernel(const __gri
   const long long nctl = (long long)ctr[kCCtl], qfront = (long long)ctr[kCFront], qn0 = qfront + (long long)ctr[kCBack], nfull0 = (long long)ctr[kCFull0];
   const long long total0 = qn0 + nfull0;
   if (nctl == 0 && total0 == 0) return;
+  if (io.ff_ran_host && blockIdx.x == 0 && threadIdx.x == 0) *io.ff_ran_host = 1u;
   WarpStats ws;
   ws.init(sacc[wib], lane);
   // No CTA ever waits for a particular other CTA: all work - deferred control substeps, flights, parked envs - is claimed
@@ -1929,6 +1936,11 @@ struct tb_ctx {
   int control_mode = TB_CONTROL_FORCE;
   void *pid = nullptr;                       // controller memory, allocated by tb_set_control_mode(TB_CONTROL_PID)
   bool zero_copy = std::getenv("TB_HOST_STAGING") == nullptr;  // tb_step_host: address pinned host buffers from the kernels
+  // tb_step_host's pipelined mode: the batch in slices, uploads / kernels / downloads of different slices overlapping
+  static constexpr int kMaxSlices = 8;
+  cudaStream_t s_up = nullptr, s_dn = nullptr;
+  cudaEvent_t ev_up[kMaxSlices] = {}, ev_k[kMaxSlices] = {};
+  unsigned *h_ffran = nullptr, *h_ffran_dev = nullptr;  // mapped host word, see StepIO::ff_ran_host
   float *policy = nullptr;                   // TB_POLICY_FLOATS parameters (tb_set_policy)
   float *pol_act = nullptr;                  // [N, 6] clipped actions handed from policy_kernel to step_kernel
   bool timing = false;                       // tb_set_kernel_timing
@@ -1967,6 +1979,7 @@ static StepIO make_io(tb_ctx *c) {
   std::memset(&io, 0, sizeof io);
   io.state = c->state; io.n = c->cfg.num_envs; io.id_offset = c->cfg.env_id_offset; io.seed = c->cfg.seed;
   io.auto_reset = c->cfg.auto_reset; io.stats = c->stats; io.k_steps = 1;
+  io.env_lo = 0; io.env_hi = c->cfg.num_envs;
   io.pid = c->control_mode == TB_CONTROL_PID ? c->pid : nullptr;
   return io;
 }
@@ -2034,16 +2047,18 @@ static cudaError_t launch_pdl(bool pdl, void (*kernel)(KArgs...), dim3 grid, cud
   return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
 }
 // One env step = step_kernel (+ ff_kernel for SwingRacket) on `stream`.
-static int launch_step(tb_ctx *c, StepIO &io, cudaStream_t stream, bool stage = false) {
+static void fill_io(tb_ctx *c, StepIO &io) {
   io.queue = c->queue; io.queue_full = c->queue_full; io.queue_ctl = c->queue_ctl;
   io.fault = c->fault; io.fault_host = c->h_fault_dev; io.spin_limit = c->spin_limit;
   io.server_sm_stride = c->ff_server_sm_stride;
   io.dq_full = c->dq; io.dq_late = c->dq ? c->dq + c->dq_cap : nullptr; io.dq_cap = c->dq_cap;
   io.epoch = c->epoch;  // (a slot written 2^32 steps ago with the same tag would have to survive untouched)
   io.queue_ctrs = c->queue_ctrs;
-  const unsigned grid = grid_for(io.n, kBlock);
+}
+// step_kernel for the envs [io.env_lo, io.env_hi) on `stream`
+static int launch_step_kernel(tb_ctx *c, StepIO &io, cudaStream_t stream, bool stage) {
+  const unsigned grid = grid_for(io.env_hi - io.env_lo, kBlock);
   const bool swing = c->cfg.env_kind == TB_ENV_SWING;
-  if (c->timing) CU(cudaEventRecord(c->ev[0], stream));
 #define TB_LAUNCH_STEP(T, K, SC)                                                                           \
   do {                                                                                                    \
     if (stage) {                                                                                          \
@@ -2069,20 +2084,31 @@ static int launch_step(tb_ctx *c, StepIO &io, cudaStream_t stream, bool stage = 
 #undef TB_LAUNCH_STEP
   c->launches++;
   CU(cudaGetLastError());
-  if (c->timing) CU(cudaEventRecord(c->ev[1], stream));
-  if (swing) {
-    if (c->cfg.precision == TB_F64) {
-      if (!c->ff_grid && ff_grid_size<double>(c, &c->ff_grid)) return 1;
-      io.server_sm_stride = c->ff_server_sm_stride;
-      CU(launch_pdl(c->pdl, ff_kernel<double>, c->ff_grid, stream, c->sc64, io));
-    } else {
-      if (!c->ff_grid && ff_grid_size<float>(c, &c->ff_grid)) return 1;
-      io.server_sm_stride = c->ff_server_sm_stride;
-      CU(launch_pdl(c->pdl, ff_kernel<float>, c->ff_grid, stream, c->sc32, io));
-    }
-    c->launches++;
-    CU(cudaGetLastError());
+  return 0;
+}
+// ff_kernel (SwingRacket-v0) for the whole batch on `stream`
+static int launch_ff_kernel(tb_ctx *c, StepIO &io, cudaStream_t stream) {
+  if (c->cfg.env_kind != TB_ENV_SWING) return 0;
+  if (c->cfg.precision == TB_F64) {
+    if (!c->ff_grid && ff_grid_size<double>(c, &c->ff_grid)) return 1;
+    io.server_sm_stride = c->ff_server_sm_stride;
+    CU(launch_pdl(c->pdl, ff_kernel<double>, c->ff_grid, stream, c->sc64, io));
+  } else {
+    if (!c->ff_grid && ff_grid_size<float>(c, &c->ff_grid)) return 1;
+    io.server_sm_stride = c->ff_server_sm_stride;
+    CU(launch_pdl(c->pdl, ff_kernel<float>, c->ff_grid, stream, c->sc32, io));
   }
+  c->launches++;
+  CU(cudaGetLastError());
+  return 0;
+}
+// One env step = step_kernel (+ ff_kernel for SwingRacket) on `stream`.
+static int launch_step(tb_ctx *c, StepIO &io, cudaStream_t stream, bool stage = false) {
+  fill_io(c, io);
+  if (c->timing) CU(cudaEventRecord(c->ev[0], stream));
+  if (launch_step_kernel(c, io, stream, stage)) return 1;
+  if (c->timing) CU(cudaEventRecord(c->ev[1], stream));
+  if (launch_ff_kernel(c, io, stream)) return 1;
   if (c->timing) {
     float a = 0, b = 0;
     CU(cudaEventRecord(c->ev[2], stream));
@@ -2233,6 +2259,10 @@ int tb_destroy(tb_ctx *c) {
   for (int i = 0; i < 3; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
   cudaFree(c->state); cudaFree(c->stats); cudaFree(c->queue_ctrs); cudaFree(c->queue); cudaFree(c->dq); cudaFree(c->epoch); cudaFree(c->fault); cudaFree(c->queue_full); cudaFree(c->queue_ctl); cudaFree(c->pid); cudaFree(c->policy); cudaFree(c->pol_act);
   if (c->h_fault) cudaFreeHost(c->h_fault);
+  if (c->h_ffran) cudaFreeHost(c->h_ffran);
+  if (c->s_up) cudaStreamDestroy(c->s_up);
+  if (c->s_dn) cudaStreamDestroy(c->s_dn);
+  for (int i = 0; i < tb_ctx::kMaxSlices; ++i) { if (c->ev_up[i]) cudaEventDestroy(c->ev_up[i]); if (c->ev_k[i]) cudaEventDestroy(c->ev_k[i]); }
   cudaFree(c->d_actions); cudaFree(c->d_obs); cudaFree(c->d_reward); cudaFree(c->d_term);
   cudaFree(c->d_done); cudaFree(c->d_events); cudaFree(c->d_mask);
   delete c;
@@ -2423,13 +2453,91 @@ static void *mapped_alias(const void *h) {
   return at.type == cudaMemoryTypeHost ? at.devicePointer : nullptr;
 }
 
+// tb_step_host for large batches and pinned buffers: the batch is stepped in slices.  The actions of every slice go up on
+// the upload stream (copy engine), each slice's step_kernel waits for its own upload, and its outputs go down on the
+// download stream (the other copy engine) while later slices are still uploading and stepping: both directions of the link
+// carry data at the same time (B200 box: 42 GB/s up and 53 GB/s down, 92 GB/s together) instead of the kernels reading and
+// writing host memory themselves (~60 GB/s in both directions together).  ff_kernel follows the last slice; when it had
+// anything to do (deferred control substeps, flights - it says so in a mapped host word) it wrote outputs of envs whose slice
+// may have gone down already, and all outputs are copied once more.
+static int step_host_pipelined(tb_ctx *c, const float *h_actions, float *h_obs, float *h_reward, uint8_t *h_done, float *h_terminal_obs,
+                               uint8_t *h_events, int slices) {
+  const int64_t n = c->cfg.num_envs;
+  const size_t od = (size_t)tb_obs_dim(c->cfg.env_kind), ad = (size_t)tb_act_dim(c->cfg.env_kind);
+  if (ensure_staging(c)) return 1;
+  if (!c->s_up) {
+    CU(cudaStreamCreateWithFlags(&c->s_up, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&c->s_dn, cudaStreamNonBlocking));
+    for (int i = 0; i < tb_ctx::kMaxSlices; ++i) {
+      CU(cudaEventCreateWithFlags(&c->ev_up[i], cudaEventDisableTiming));
+      CU(cudaEventCreateWithFlags(&c->ev_k[i], cudaEventDisableTiming));
+    }
+    CU(cudaHostAlloc((void **)&c->h_ffran, sizeof(unsigned), cudaHostAllocMapped));
+    CU(cudaHostGetDevicePointer((void **)&c->h_ffran_dev, c->h_ffran, 0));
+  }
+  cudaStream_t s = c->own_stream;
+  *c->h_ffran = 0;
+  StepIO io = make_io(c);
+  fill_io(c, io);
+  io.actions = c->d_actions; io.obs = c->d_obs; io.reward = c->d_reward; io.done = c->d_done;
+  io.term_obs = h_terminal_obs ? c->d_term : nullptr; io.events = h_events ? c->d_events : nullptr;
+  io.ff_ran_host = c->h_ffran_dev;
+  const int64_t per = ((n + slices - 1) / slices + kBlock - 1) / kBlock * kBlock;  // whole CTAs per slice
+  for (int k = 0; k < slices; ++k) {
+    const int64_t lo = std::min<int64_t>(n, k * per), hi = std::min<int64_t>(n, lo + per);
+    if (hi > lo) CU(cudaMemcpyAsync(c->d_actions + lo * ad, h_actions + lo * ad, (size_t)(hi - lo) * ad * sizeof(float), cudaMemcpyHostToDevice, c->s_up));
+    CU(cudaEventRecord(c->ev_up[k], c->s_up));
+  }
+  for (int k = 0; k < slices; ++k) {
+    const int64_t lo = std::min<int64_t>(n, k * per), hi = std::min<int64_t>(n, lo + per);
+    if (hi <= lo) continue;
+    CU(cudaStreamWaitEvent(s, c->ev_up[k], 0));
+    io.env_lo = lo; io.env_hi = hi;
+    if (launch_step_kernel(c, io, s, false)) return 1;
+    CU(cudaEventRecord(c->ev_k[k], s));
+    CU(cudaStreamWaitEvent(c->s_dn, c->ev_k[k], 0));
+    const size_t m = (size_t)(hi - lo);
+    CU(cudaMemcpyAsync(h_obs + lo * od, c->d_obs + lo * od, m * od * sizeof(float), cudaMemcpyDeviceToHost, c->s_dn));
+    CU(cudaMemcpyAsync(h_reward + lo, c->d_reward + lo, m * sizeof(float), cudaMemcpyDeviceToHost, c->s_dn));
+    CU(cudaMemcpyAsync(h_done + lo, c->d_done + lo, m, cudaMemcpyDeviceToHost, c->s_dn));
+    if (h_terminal_obs) CU(cudaMemcpyAsync(h_terminal_obs + lo * od, c->d_term + lo * od, m * od * sizeof(float), cudaMemcpyDeviceToHost, c->s_dn));
+    if (h_events) CU(cudaMemcpyAsync(h_events + lo, c->d_events + lo, m, cudaMemcpyDeviceToHost, c->s_dn));
+  }
+  io.env_lo = 0; io.env_hi = n;
+  if (launch_ff_kernel(c, io, s)) return 1;
+  CU(cudaStreamSynchronize(s));
+  CU(cudaStreamSynchronize(c->s_dn));
+  if (*reinterpret_cast<volatile unsigned *>(c->h_ffran)) {
+    const size_t m = (size_t)n;
+    CU(cudaMemcpyAsync(h_obs, c->d_obs, m * od * sizeof(float), cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(h_reward, c->d_reward, m * sizeof(float), cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(h_done, c->d_done, m, cudaMemcpyDeviceToHost, s));
+    if (h_terminal_obs) CU(cudaMemcpyAsync(h_terminal_obs, c->d_term, m * od * sizeof(float), cudaMemcpyDeviceToHost, s));
+    if (h_events) CU(cudaMemcpyAsync(h_events, c->d_events, m, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+  }
+  return check_fault(c, "tb_step_host");
+}
+
 int tb_step_host(tb_ctx *c, const float *h_actions, float *h_obs, float *h_reward, uint8_t *h_done, float *h_terminal_obs,
                  uint8_t *h_events) {
   GUARD(c);
   if (!h_actions || !h_obs || !h_reward || !h_done) return fail("%s", "tb_step_host: actions, obs, reward and done are required");
+  if (check_fault(c, "tb_step_host")) return 1;
   size_t n = (size_t)c->cfg.num_envs, od = (size_t)tb_obs_dim(c->cfg.env_kind), ad = (size_t)tb_act_dim(c->cfg.env_kind);
   cudaStream_t s = c->own_stream;
-  if (c->zero_copy) {
+  // mode: TB_HOST_MODE = zero_copy (default for pinned buffers) | pipeline | staging (pageable memory always takes it).
+  // Measured on the B200 box, 1 Mi SwingRacket envs, per step averaged over episodes: zero copy 0.95 ms, pipeline 1.19 ms,
+  // staging 1.24 ms.  The link alone allows 0.63 ms (42 GB/s up, 53 GB/s down, concurrently); the pipeline does not get there:
+  // its ~70 small copies, event records and waits per step cost more than the overlap wins, and every fast-forward step
+  // copies the outputs twice.
+  const char *mode = std::getenv("TB_HOST_MODE");
+  const bool pinned = mapped_alias(h_actions) && mapped_alias(h_obs) && mapped_alias(h_reward) && mapped_alias(h_done) &&
+                      (mapped_alias(h_terminal_obs) || !h_terminal_obs) && (mapped_alias(h_events) || !h_events);
+  const bool want_pipeline = mode && !std::strcmp(mode, "pipeline");
+  if (pinned && want_pipeline && c->timing == false)
+    return step_host_pipelined(c, h_actions, h_obs, h_reward, h_done, h_terminal_obs, h_events, n >= 262144 ? 8 : (n >= 65536 ? 4 : 2));
+  if (c->zero_copy && !(mode && !std::strcmp(mode, "staging"))) {
     // Pinned buffers: the kernels read the actions from and write the results to host memory themselves.  The
     // two PCIe directions then run concurrently and overlap with the compute, instead of H2D -> kernels -> D2H.
     const float *za = (const float *)mapped_alias(h_actions);

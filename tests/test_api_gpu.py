@@ -134,3 +134,29 @@ def test_full_size_properties(env_id, n, steps):
     st2, ndone2, rsum2, obs2, state2 = run()
     np.testing.assert_array_equal(st, st2)
     assert torch.equal(obs, obs2) and torch.equal(state, state2)  # bit-reproducible
+
+
+@pytest.mark.parametrize("mode", ["pipeline", "zero_copy", "staging"])
+def test_step_host_modes_match_oracle(oracle_lib, mode, monkeypatch):
+    """tb_step_host's three transports (sliced uploads / kernels / downloads on two copy engines; kernels addressing the pinned
+    host buffers; plain staging) give the oracle's results, through SwingRacket's fast-forward step and the auto-resets."""
+    from tennisbot_rl_b200.batch import TennisBatch
+
+    monkeypatch.setenv("TB_HOST_MODE", mode)
+    n = 5000  # not a multiple of the slice size
+    b = TennisBatch("SwingRacket-v0", n, seed=77)
+    o = oracle_lib.OracleEnv("SwingRacket-v0", n, seed=77, threads=8)
+    np.testing.assert_array_equal(b.reset_host(), o.reset())
+    rng = np.random.default_rng(8)
+    for t in range(54):
+        a = rng.uniform(-1, 1, (n, 6)).astype(np.float32)
+        hb = b.step_host(a)
+        ref = o.step(a)
+        np.testing.assert_array_equal(hb["done"], ref["done"])
+        np.testing.assert_array_equal(hb["events"], ref["events"])
+        np.testing.assert_allclose(hb["obs"], ref["obs"], atol=2e-6)
+        np.testing.assert_allclose(hb["reward"], ref["reward"], atol=2e-6)
+        d = ref["done"] != 0
+        np.testing.assert_allclose(hb["terminal_obs"][d], ref["terminal_obs"][d], atol=2e-6)
+    np.testing.assert_array_equal(b.read_stats(), o.read_stats())
+    b.close()
