@@ -178,8 +178,13 @@ int tb_set_state(tb_ctx *ctx, const double *d_state, void *stream);
 int tb_stats_device_ptr(tb_ctx *ctx, int64_t **d_stats); /* int64 [TB_NUM_STATS] in HBM: all-reduce this over NCCL */
 int tb_read_stats(tb_ctx *ctx, int64_t *h_stats, int clear, void *stream); /* synchronises `stream` */
 
-/* ---- host-buffer convenience (what a numpy VecEnv calls): H2D of the actions, the step kernel, D2H of the
- * results, on the context's own stream, synchronised before returning.  Pinned buffers make the copies DMA. */
+/* ---- host-buffer convenience (what a numpy VecEnv calls): one env step with the actions taken from and the results left in
+ * HOST arrays, on the context's own stream, synchronised before returning.  Transport, by default: when every buffer is
+ * pinned (cudaHostAlloc / torch pin_memory) the kernels address the host buffers themselves - actions are read and results
+ * written over PCIe while the step computes, both directions at once (zero copy); pageable buffers are staged (H2D copy,
+ * kernels, D2H copies).  TB_HOST_MODE = zero_copy | pipeline | staging selects one explicitly; `pipeline` steps the batch in
+ * slices whose uploads, kernels and downloads overlap on the two copy engines (measured slower than zero copy on the B200
+ * box).  A call fails if a fast-forward launch of the context has timed out (see tb_ff_diagnostics). */
 int tb_reset_host(tb_ctx *ctx, const uint8_t *h_mask, float *h_obs);
 int tb_step_host(tb_ctx *ctx, const float *h_actions, float *h_obs, float *h_reward, uint8_t *h_done,
                  float *h_terminal_obs, uint8_t *h_events);
@@ -190,9 +195,13 @@ int tb_launch_count(tb_ctx *ctx, int64_t *launches);
 /* Diagnostics of the most recent SwingRacket fast-forward (the launch of tb_step's second kernel on an env's 26th
  * step; read it before the next step): out[0] = 1 if one ran, out[1] = visits of envs to the generic full-substep path
  * (server warps), out[2] = nanoseconds until every flight had landed, out[3..13] = reserved (instrumented builds),
- * out[14] = nanoseconds of the finishing pass, out[15] = non-zero if a wait inside a fast-forward launch of this
- * context has ever timed out (sticky; that launch left envs unfinished instead of hanging the device, and
- * tb_read_stats fails from then on).  Synchronises the device.  h_out: 16 x int64. */
+ * out[14] = 0 (the finishing pass overlaps the flights since round 2), out[15] = non-zero if a wait inside a fast-forward
+ * launch of this context has ever timed out (sticky; that launch left envs unfinished instead of hanging the device, and
+ * EVERY later call on the context - tb_step, tb_step_host, tb_reset, tb_rollout, tb_read_stats - fails from then on: the
+ * fault word is mirrored in mapped host memory and checked on entry without synchronising).  A wait gives up after
+ * TB_FF_SPIN_LIMIT_MS (default 4000 ms).  ff_kernel has no grid barrier and claims all of its work from counters and queues,
+ * so it completes whatever else occupies SMs while it runs; the time-out is the backstop.  Synchronises the device.
+ * h_out: 16 x int64. */
 int tb_ff_diagnostics(tb_ctx *ctx, int64_t *h_out);
 
 /* Per-kernel device timing for roofline reports.  While enabled, every tb_step brackets its two kernels with CUDA

@@ -820,6 +820,8 @@ __device__ __forceinline__ int ff_finishing_duty(const Scene<T> &sc, const StepI
   if (!pass1_over) {
     // (the retry list lives in queue_ctl: not before the prologue has read all of it)
     if (ld_ctr(ctr + kCCtlDone) < (unsigned long long)nctl) return 0;
+    // a launch that only had deferred control substeps to take (no flight was queued): nothing to finish
+    if (total0 == 0 && ld_ctr(ctr + kCDynTotal) == 0) return 2;
     long long t = 0;
     if (lane == 0) t = (long long)atomicAdd(ctr + kCFinClaim, 1ULL);
     t = __shfl_sync(full, t, 0);

@@ -10,6 +10,9 @@ from tennisbot_rl_b200.batch import TennisBatch
 prec = sys.argv[1]; n = int(sys.argv[2]); eps = int(sys.argv[3]) if len(sys.argv) > 3 else 3
 env = sys.argv[4] if len(sys.argv) > 4 else "SwingRacket-v0"
 b = TennisBatch(env, n, precision=prec, seed=0)
+for kv in os.environ.get("TB_PARAMS", "").split(","):  # e.g. TB_PARAMS=racket_court_contact=1
+    if "=" in kv:
+        b.set_param(kv.split("=")[0], float(kv.split("=")[1]))
 b.reset()
 acts = [torch.empty((n, b.act_dim), device="cuda").uniform_(-1, 1) for _ in range(RING)]
 for t in range(26): b.step(acts[t % RING])
