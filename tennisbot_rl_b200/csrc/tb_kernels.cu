@@ -458,19 +458,26 @@ __device__ __forceinline__ void step_tile(const Scene<T> &sc, const StepIO &io, 
   // the tail of ff_kernel.  An env whose first fast-forward substep needs the full treatment (ball within reach of
   // the racket, mostly: a hit in progress) goes to the full queue, which ff_kernel serves before anything else.
   bool queued = valid && !fin;
+  int cls = 3;
+  if (KIND == TB_ENV_SWING && queued) {
+    // front of the queue as well: a ball that is closing in on the racket's plane and would cross it within ~0.6 s.
+    // If the racket is there when it does, the flight that follows is a long one, and it should not start last.
+    const T x = s.rq[0], y = s.rq[1], z = s.rq[2], w = s.rq[3];
+    const T nx = 1 - 2 * (y * y + z * z), ny = 2 * (x * y + z * w), nz = 2 * (x * z - y * w);
+    const T d = nx * (s.bp[0] - s.rp[0]) + ny * (s.bp[1] - s.rp[1]) + nz * (s.bp[2] - s.rp[2]);
+    const T vn = nx * (s.bv[0] - s.rv[0]) + ny * (s.bv[1] - s.rv[1]) + nz * (s.bv[2] - s.rv[2]);
+    const bool closing = d * vn < 0 && M<T>::abs(d) < (T)0.6 * M<T>::abs(vn);
+    cls = ff_classify_state(sc, s) == kFfFull ? 2 : ((dot3(s.bv, s.bv) > (T)9 || closing) ? 0 : 1);
+    s.flags = (s.flags & ~(0xff << kFlagEventShift)) | kFlagInFlight | kFlagFirst | (c.events << kFlagEventShift);
+  }
+  // the state goes back first: the bookkeeping below synchronises the CTA, and on 25 steps out of 26 it has nothing to do
+  if (valid) {
+    const bool restarted = s.episode != episode0;
+    store_state_changed(base, io.n, me, s, restarted || s.bw[1] != spin1 || s.bw[2] != spin2, restarted, have5 || restarted);
+  }
   if (KIND == TB_ENV_SWING) {
     constexpr int W = kBlock / 32;
-    int cls = 3;
-    if (queued) {
-      // front of the queue as well: a ball that is closing in on the racket's plane and would cross it within ~0.6 s.
-      // If the racket is there when it does, the flight that follows is a long one, and it should not start last.
-      const T x = s.rq[0], y = s.rq[1], z = s.rq[2], w = s.rq[3];
-      const T nx = 1 - 2 * (y * y + z * z), ny = 2 * (x * y + z * w), nz = 2 * (x * z - y * w);
-      const T d = nx * (s.bp[0] - s.rp[0]) + ny * (s.bp[1] - s.rp[1]) + nz * (s.bp[2] - s.rp[2]);
-      const T vn = nx * (s.bv[0] - s.rv[0]) + ny * (s.bv[1] - s.rv[1]) + nz * (s.bv[2] - s.rv[2]);
-      const bool closing = d * vn < 0 && M<T>::abs(d) < (T)0.6 * M<T>::abs(vn);
-      cls = ff_classify_state(sc, s) == kFfFull ? 2 : ((dot3(s.bv, s.bv) > (T)9 || closing) ? 0 : 1);
-    }
+    if (!__syncthreads_or(cls != 3)) return;  // (every thread of the CTA gets here: DEFER lanes and tail lanes included)
     unsigned m0 = __ballot_sync(full, cls == 0), m1 = __ballot_sync(full, cls == 1), m2 = __ballot_sync(full, cls == 2);
     if (lane == 0) { s_cnt[wib] = __popc(m0); s_cnt[W + wib] = __popc(m1); s_cnt[2 * W + wib] = __popc(m2); }
     __syncthreads();
@@ -491,12 +498,7 @@ __device__ __forceinline__ void step_tile(const Scene<T> &sc, const StepIO &io, 
       if (cls == 0) io.queue[s_base[0] + s_cnt[wib] + __popc(m0 & lt)] = (int)me;
       else if (cls == 1) io.queue[io.n - 1 - (int64_t)(s_base[1] + s_cnt[W + wib] + __popc(m1 & lt))] = (int)me;
       else io.queue_full[s_base[2] + s_cnt[2 * W + wib] + __popc(m2 & lt)] = (int)me;
-      s.flags = (s.flags & ~(0xff << kFlagEventShift)) | kFlagInFlight | kFlagFirst | (c.events << kFlagEventShift);
     }
-  }
-  if (valid) {
-    const bool restarted = s.episode != episode0;
-    store_state_changed(base, io.n, me, s, restarted || s.bw[1] != spin1 || s.bw[2] != spin2, restarted, have5 || restarted);
   }
 }
 
