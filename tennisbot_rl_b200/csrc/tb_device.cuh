@@ -101,6 +101,7 @@ template <typename T> __device__ __forceinline__ T norm3_fast(const T *a) { retu
 // unroll depth of the loops over the edge tables: the entries are constant-bank loads with a lane-dependent index (long
 // latency), and a lone lane of a server warp has nothing else to overlap them with
 constexpr int kEdgeUnroll = TB_EDGE_UNROLL;
+constexpr int kBallVzEntries = 32;  // Scene::ball_vz (SwingRacket's control phase is 26 substeps long)
 constexpr int kRacketEdges = TB_RACKET_OUTLINE_N;
 constexpr int kGoalEdges = TB_GOAL_SIDES;
 
@@ -136,6 +137,7 @@ template <typename T> struct Scene {
   T rest_racket, rest_court, rest_goal, mu_racket, mu_court, mu_goal;
   T erp, slop, rest_vel_threshold, solver_residual, contact_threshold, hull_margin, box_margin, gyro;
   int iters, shoot_start, shoot_frames;  // Tennisbot-v0: env steps on which the ball's shoot force acts (tennisbot_env.py:21,118)
+  T ball_vz[kBallVzEntries];             // vz of a ball after k free-fall substeps from rest (kStPristine), filled on the device
   int racket_court;                      // 1: racket vs the court's floor box is modelled (parameter racket_court_contact), on the
                                          // generic path only: a state with TB_EV_RACKET_LOW never takes a straight-line substep then
   T rest_racket_court, mu_racket_court;
@@ -855,11 +857,17 @@ __device__ __forceinline__ void draw_init(uint64_t seed, uint64_t gid, uint32_t 
 //               explicit placements (tb_reset_from) or injected states (tb_set_state).  Tennisbot-v0: pack 6 holds only the
 //               constant z shoot force, so there the bit is set by every episode start
 //   kStSpin     the ball's spin has a y or z component (it has none until a frictional contact): pack 5 must be loaded
-constexpr int kStDerived = 1 << 24, kStSpin = 1 << 25;
+//   kStPristine (SwingRacket) the ball has only fallen freely from rest since the episode began: its velocity is (0, 0, vz[k])
+//               after k substeps whatever the placement (Scene::ball_vz, tabulated by the kernels' own arithmetic) and it does
+//               not spin, so pack 4 (ball velocity | spin x) is neither loaded nor written while the bit is set; HBM holds a
+//               stale pack 4 meanwhile.  The bit lives through step_kernel's straight-line control substep only: every other
+//               path materialises the pack on load and clears the bit
+constexpr int kStDerived = 1 << 24, kStSpin = 1 << 25, kStPristine = 1 << 26;
 template <typename T, int KIND>
 __device__ __forceinline__ void start_episode(const Scene<T> &sc, St<T> &s, const T *in, uint32_t episode, bool from_rng) {
   place<T, KIND>(sc, s, in);
-  s.ret = 0; s.step = 0; s.flags = (from_rng || KIND == TB_ENV_HIT) ? kStDerived : 0; s.episode = episode;
+  s.ret = 0; s.step = 0; s.episode = episode;
+  s.flags = ((from_rng || KIND == TB_ENV_HIT) ? kStDerived : 0) | (KIND == TB_ENV_SWING ? kStPristine : 0);
 }
 template <typename T, int KIND> __device__ __forceinline__ void pack_obs(const St<T> &s, float *o) {
   if (KIND == TB_ENV_SWING) {
@@ -1273,6 +1281,20 @@ template <typename T> __device__ __forceinline__ int ff_classify_state(const Sce
 // classification bounds |omega| and every speed with room for one substep of the largest action).  Equal to
 // physics_step in exact arithmetic, to ~1e-16 per substep in floating point.  Returns the event bits of the substep
 // (TB_EV_RACKET_LOW at most).  step_kernel defers every other env to the generic path (ff_kernel's prologue).
+// the ball's part of a contact-free substep: damping as one factor, gravity (shared with the kernel that tabulates ball_vz)
+template <typename T> __device__ __forceinline__ void ball_free_velocities(const Scene<T> &sc, T *bv, T *bw) {
+  T fb = 1 - sc.ff_kl * (1 + M<T>::norm_damp(dot3(bv, bv)));
+  bv[0] *= fb; bv[1] *= fb; bv[2] = bv[2] * fb + sc.ff_dtg;
+  T fs = 1 - sc.ff_ka * (1 + M<T>::norm_damp(dot3(bw, bw)));
+  bw[0] *= fs; bw[1] *= fs; bw[2] *= fs;
+}
+// a state whose pack 4 was not loaded / is stale in HBM (kStPristine): the ball's velocity from the table, no spin
+template <typename T> __device__ __forceinline__ void materialise_ball(const Scene<T> &sc, St<T> &s) {
+  if (s.flags & kStPristine) {
+    s.bv[0] = 0; s.bv[1] = 0; s.bv[2] = sc.ball_vz[s.step < kBallVzEntries ? s.step : kBallVzEntries - 1];
+    s.bw[0] = 0;
+  }
+}
 template <typename T> __device__ __forceinline__ int ctl_fast(const Scene<T> &sc, St<T> &s, const float *a) {
   const T dt = sc.dt;
   T R[9];
@@ -1286,10 +1308,7 @@ template <typename T> __device__ __forceinline__ int ctl_fast(const Scene<T> &sc
   }
   const T F[3] = {(T)a[0] * 400, (T)a[1] * 400, (T)a[2] * 400 + (T)(4 * 9.81)};
   const T Tq[3] = {(T)a[3] * 5, (T)a[4] * 5, (T)a[5] * 5};
-  T fb = 1 - sc.ff_kl * (1 + M<T>::norm_damp(dot3(s.bv, s.bv)));
-  s.bv[0] *= fb; s.bv[1] *= fb; s.bv[2] = s.bv[2] * fb + sc.ff_dtg;
-  T fs = 1 - sc.ff_ka * (1 + M<T>::norm_damp(dot3(s.bw, s.bw)));
-  s.bw[0] *= fs; s.bw[1] *= fs; s.bw[2] *= fs;
+  ball_free_velocities(sc, s.bv, s.bw);
   T fr = 1 - sc.ff_kl * (1 + M<T>::norm_damp(dot3(s.rv, s.rv)));
   const T dtm = dt * sc.racket_inv_m;
   s.rv[0] = s.rv[0] * fr + dtm * F[0]; s.rv[1] = s.rv[1] * fr + dtm * F[1]; s.rv[2] = s.rv[2] * fr + (dtm * F[2] + sc.ff_dtg);

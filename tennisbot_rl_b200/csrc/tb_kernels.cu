@@ -82,7 +82,7 @@ template <typename T> __device__ __forceinline__ void store_state_changed(T *bas
   st_pack(base, n, 1, i, Pack<T>{s.rq[0], s.rq[1], s.rq[2], s.rq[3]});
   st_pack(base, n, 2, i, Pack<T>{s.rv[0], s.rv[1], s.rv[2], s.bp[1]});
   st_pack(base, n, 3, i, Pack<T>{s.rw[0], s.rw[1], s.rw[2], s.bp[2]});
-  st_pack(base, n, 4, i, Pack<T>{s.bv[0], s.bv[1], s.bv[2], s.bw[0]});
+  if (!(s.flags & kStPristine) || p6) st_pack(base, n, 4, i, Pack<T>{s.bv[0], s.bv[1], s.bv[2], s.bw[0]});  // (p6: episode restarted)
   if (p5 && have_aux) st_pack(base, n, 5, i, Pack<T>{s.bw[1], s.bw[2], s.aux[0], s.aux[1]});
   if (p5 && !have_aux) {  // (pack 5 was not loaded: its aux half stays as it is in HBM)
     T *q = base + ((int64_t)5 * n + i) * 4;
@@ -109,18 +109,23 @@ template <typename T> __device__ __forceinline__ void store_state(T *base, int64
 // loaded them (spin changed) or restarted the episode (all fields fresh).
 // Returns whether pack 5 was loaded (if not, its aux half is unknown and a lane whose spin changes writes the spin half only).
 template <typename T, int KIND>
-__device__ __forceinline__ bool load_state_ctl(const T *base, int64_t n, int64_t i, uint64_t seed, uint64_t gid, int shoot_end, St<T> &s) {
+__device__ __forceinline__ bool load_state_ctl(const Scene<T> &sc, const T *base, int64_t n, int64_t i, uint64_t seed, uint64_t gid, St<T> &s) {
   Pack<T> p0 = ld_pack(base, n, 0, i), p1 = ld_pack(base, n, 1, i), p2 = ld_pack(base, n, 2, i),
-          p3 = ld_pack(base, n, 3, i), p4 = ld_pack(base, n, 4, i), p7 = ld_pack(base, n, 7, i);
+          p3 = ld_pack(base, n, 3, i), p7 = ld_pack(base, n, 7, i);
   s.rp[0] = p0.x; s.rp[1] = p0.y; s.rp[2] = p0.z; s.bp[0] = p0.w;
   s.rq[0] = p1.x; s.rq[1] = p1.y; s.rq[2] = p1.z; s.rq[3] = p1.w;
   s.rv[0] = p2.x; s.rv[1] = p2.y; s.rv[2] = p2.z; s.bp[1] = p2.w;
   s.rw[0] = p3.x; s.rw[1] = p3.y; s.rw[2] = p3.z; s.bp[2] = p3.w;
-  s.bv[0] = p4.x; s.bv[1] = p4.y; s.bv[2] = p4.z; s.bw[0] = p4.w;
   s.ret = p7.x; s.step = (int)as_int(p7.y); s.flags = (int)as_int(p7.z); s.episode = (uint32_t)as_int(p7.w);
+  if (KIND == TB_ENV_SWING && (s.flags & kStPristine)) {  // ball in free fall from rest: pack 4 is a table entry
+    materialise_ball(sc, s);
+  } else {
+    Pack<T> p4 = ld_pack(base, n, 4, i);
+    s.bv[0] = p4.x; s.bv[1] = p4.y; s.bv[2] = p4.z; s.bw[0] = p4.w;
+  }
   const bool derived = (s.flags & kStDerived) != 0;
   // Tennisbot-v0 reads the shoot force (aux x, y in pack 5) during the first frames of every episode
-  const bool need5 = (s.flags & kStSpin) != 0 || (KIND == TB_ENV_HIT && s.step < shoot_end) || (KIND == TB_ENV_SWING && !derived);
+  const bool need5 = (s.flags & kStSpin) != 0 || (KIND == TB_ENV_HIT && s.step < sc.shoot_start + sc.shoot_frames) || (KIND == TB_ENV_SWING && !derived);
   s.bw[1] = 0; s.bw[2] = 0; s.aux[0] = 0; s.aux[1] = 0; s.aux[2] = 0; s.goal[0] = 0; s.goal[1] = 0; s.d0 = 0;
   if (need5) {
     Pack<T> p5 = ld_pack(base, n, 5, i);
@@ -468,7 +473,7 @@ __device__ __forceinline__ void step_tile(const Scene<T> &sc, const StepIO &io, 
     const T vn = nx * (s.bv[0] - s.rv[0]) + ny * (s.bv[1] - s.rv[1]) + nz * (s.bv[2] - s.rv[2]);
     const bool closing = d * vn < 0 && M<T>::abs(d) < (T)0.6 * M<T>::abs(vn);
     cls = ff_classify_state(sc, s) == kFfFull ? 2 : ((dot3(s.bv, s.bv) > (T)9 || closing) ? 0 : 1);
-    s.flags = (s.flags & ~(0xff << kFlagEventShift)) | kFlagInFlight | kFlagFirst | (c.events << kFlagEventShift);
+    s.flags = (s.flags & ~((0xff << kFlagEventShift) | kStPristine)) | kFlagInFlight | kFlagFirst | (c.events << kFlagEventShift);
   }
   // the state goes back first: the bookkeeping below synchronises the CTA, and on 25 steps out of 26 it has nothing to do
   if (valid) {
@@ -566,7 +571,7 @@ __global__ void __launch_bounds__(kBlock, MINB ? MINB : StepMinBlocks<T, KIND>::
   }
   bool have5 = true;
   if (valid) {
-    have5 = load_state_ctl<T, KIND>(static_cast<const T *>(io.state), io.n, me, io.seed, (uint64_t)(io.id_offset + me), sc.shoot_start + sc.shoot_frames, s);
+    have5 = load_state_ctl<T, KIND>(sc, static_cast<const T *>(io.state), io.n, me, io.seed, (uint64_t)(io.id_offset + me), s);
     if (!STAGE) load_action<KIND>(io.actions, me, a);
   }
   step_tile<T, KIND, STAGE, KIND == TB_ENV_SWING>(sc, io, qctr, tile0, me, rows, valid, s, a, ws, s_cnt, s_base, s_tile, have5);
@@ -1224,6 +1229,8 @@ __device__ __noinline__ void ff_prologue(const Scene<T> &sc, const StepIO &io, u
     if (valid) {
       float a[8];
       load_state(static_cast<const T *>(io.state), io.n, (int64_t)me, s);
+      materialise_ball(sc, s);
+      s.flags &= ~kStPristine;  // (the generic step may touch the ball: pack 4 goes back to HBM from here on)
       load_action<KIND>(io.actions, (int64_t)me, a);
       spin1 = s.bw[1]; spin2 = s.bw[2]; episode0 = s.episode;
       c.done = s.flags & kFlagDone;
@@ -1250,7 +1257,7 @@ __device__ __noinline__ void ff_prologue(const Scene<T> &sc, const StepIO &io, u
     bool to_full = false;
     if (queued) {
       to_full = ff_classify_state(sc, s) == kFfFull;
-      s.flags = (s.flags & ~(0xff << kFlagEventShift)) | kFlagInFlight | kFlagFirst | (c.events << kFlagEventShift);
+      s.flags = (s.flags & ~((0xff << kFlagEventShift) | kStPristine)) | kFlagInFlight | kFlagFirst | (c.events << kFlagEventShift);
     }
     if (valid) {
       const bool restarted = s.episode != episode0;
@@ -1361,7 +1368,11 @@ __global__ void __launch_bounds__(kBlock) rollout_kernel(const __grid_constant__
   float a[8], ob[12] = {0}, rsum = 0;
   int left = 0, dcount = 0;
   bool active = me < io.n && io.k_steps > 0;
-  if (me < io.n) load_state(base, io.n, me, s);
+  if (me < io.n) {
+    load_state(base, io.n, me, s);
+    materialise_ball(sc, s);
+    s.flags &= ~kStPristine;
+  }
   if (active) {
     left = io.k_steps;
     rollout_action<T, KIND>(io, me, s, a);
@@ -1404,6 +1415,7 @@ __global__ void __launch_bounds__(kBlock) rollout_kernel(const __grid_constant__
       if (io.obs) store_obs<KIND>(io.obs, me, ob);
       if (io.reward_sum) io.reward_sum[me] = rsum;
       if (io.done_count) io.done_count[me] = dcount;
+      if (s.step > 0) s.flags &= ~kStPristine;  // (stepped through the generic path since its last episode start)
     }
     store_state(base, io.n, me, s);
   }
@@ -1569,12 +1581,37 @@ __global__ void __launch_bounds__(kBlock) reset_kernel(const __grid_constant__ S
   }
 }
 
+// Scene::ball_vz: the vertical velocity of a ball after k contact-free substeps from rest, by the kernels' own arithmetic
+// (ball_free_velocities, as in ctl_fast), so that a state materialised from the table is the state that was stepped
+template <typename T> __global__ void ball_vz_kernel(const __grid_constant__ Scene<T> sc, T *out) {
+  T bv[3] = {0, 0, 0}, bw[3] = {0, 0, 0};
+  for (int k = 0; k < kBallVzEntries; ++k) {
+    out[k] = bv[2];
+    ball_free_velocities(sc, bv, bw);
+  }
+}
+
+// Write pack 4 of every kStPristine env from the table and clear the bit (before the table changes: tb_set_param)
+template <typename T> __global__ void materialise_kernel(const __grid_constant__ Scene<T> sc, T *base, int64_t n) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Pack<T> p7 = ld_pack(base, n, 7, i);
+  int flags = (int)as_int(p7.z);
+  if (!(flags & kStPristine)) return;
+  St<T> s;
+  s.flags = flags; s.step = (int)as_int(p7.y);
+  materialise_ball(sc, s);
+  st_pack(base, n, 4, i, Pack<T>{s.bv[0], s.bv[1], s.bv[2], s.bw[0]});
+  base[((int64_t)7 * n + i) * 4 + 2] = int_as(T(), flags & ~kStPristine);
+}
+
 // canonical double [N, 32] record <-> packed state
-template <typename T> __global__ void get_state_kernel(const T *base, int64_t n, double *out) {
+template <typename T> __global__ void get_state_kernel(const __grid_constant__ Scene<T> sc, const T *base, int64_t n, double *out) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   St<T> s;
   load_state(base, n, i, s);
+  materialise_ball(sc, s);
   double *o = out + i * TB_STATE_WORDS;
   for (int j = 0; j < 3; ++j) {
     o[TB_S_RACKET_POS + j] = s.rp[j]; o[TB_S_RACKET_VEL + j] = s.rv[j]; o[TB_S_RACKET_ANGVEL + j] = s.rw[j];
@@ -1973,9 +2010,19 @@ static int check_fault(tb_ctx *c, const char *who) {
                 "the batch state is incomplete - destroy the context", who, f);
   return 1;
 }
-static void rebuild(tb_ctx *c) {
+template <typename T> static bool fill_ball_vz(Scene<T> &sc) {
+  T *d = nullptr;
+  if (cudaMalloc(&d, kBallVzEntries * sizeof(T)) != cudaSuccess) return false;
+  ball_vz_kernel<T><<<1, 1>>>(sc, d);
+  bool ok = cudaMemcpy(sc.ball_vz, d, kBallVzEntries * sizeof(T), cudaMemcpyDeviceToHost) == cudaSuccess;
+  cudaFree(d);
+  return ok;
+}
+// (needs the context's device current: the ball_vz tables are computed there)
+static bool rebuild(tb_ctx *c) {
   build_scene<float>(c->params, c->sc32);
   build_scene<double>(c->params, c->sc64);
+  return fill_ball_vz(c->sc32) && fill_ball_vz(c->sc64);
 }
 static unsigned grid_for(int64_t n, int block) { return (unsigned)((n + block - 1) / block); }
 static StepIO make_io(tb_ctx *c) {
@@ -2188,9 +2235,9 @@ int tb_create(const tb_config *cfg, tb_ctx **out) {
   if (!c) return fail("%s", "tb_create: out of memory");
   c->cfg = *cfg;
   params_default(c->params);
-  rebuild(c);
   DeviceGuard g(cfg->device);
   if (!g.ok) { delete c; return fail("%s", "tb_create: cudaSetDevice failed"); }
+  if (!rebuild(c)) { delete c; return fail("%s", "tb_create: could not build the scene tables on the device"); }
   size_t word = cfg->precision == TB_F64 ? 8 : 4;
   size_t bytes = (size_t)cfg->num_envs * kPacks * 4 * word;
   cudaError_t e = cudaMalloc(&c->state, bytes);
@@ -2274,10 +2321,22 @@ int tb_destroy(tb_ctx *c) {
 }
 
 int tb_set_param(tb_ctx *c, const char *name, double value) {
-  if (!c || !name) return fail("%s", "tb_set_param: bad argument");
+  if (!name) return fail("%s", "tb_set_param: bad argument");
+  GUARD(c);
   double *slots = reinterpret_cast<double *>(&c->params);
   for (int i = 0; i < kNumParams; ++i)
-    if (!std::strcmp(name, k_param_names[i])) { slots[i] = value; rebuild(c); return 0; }
+    if (!std::strcmp(name, k_param_names[i])) {
+      // envs whose ball velocity lives in the free-fall table (kStPristine) get it written out under the OLD parameters
+      // first; a configuration call, so it simply waits for everything the device has in flight
+      CU(cudaDeviceSynchronize());
+      const int64_t n = c->cfg.num_envs;
+      if (c->cfg.precision == TB_F64) materialise_kernel<double><<<grid_for(n, 256), 256, 0, c->own_stream>>>(c->sc64, (double *)c->state, n);
+      else materialise_kernel<float><<<grid_for(n, 256), 256, 0, c->own_stream>>>(c->sc32, (float *)c->state, n);
+      CU(cudaStreamSynchronize(c->own_stream));
+      slots[i] = value;
+      if (!rebuild(c)) return fail("%s", "tb_set_param: could not rebuild the scene tables on the device");
+      return 0;
+    }
   return fail("tb_set_param: unknown parameter '%s'", name);
 }
 int tb_set_control_mode(tb_ctx *c, int mode) {
@@ -2385,8 +2444,8 @@ int tb_get_state(tb_ctx *c, double *d_state, void *stream) {
   GUARD(c);
   if (!d_state) return fail("%s", "tb_get_state: d_state is NULL");
   int64_t n = c->cfg.num_envs;
-  if (c->cfg.precision == TB_F64) get_state_kernel<double><<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>((const double *)c->state, n, d_state);
-  else get_state_kernel<float><<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>((const float *)c->state, n, d_state);
+  if (c->cfg.precision == TB_F64) get_state_kernel<double><<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(c->sc64, (const double *)c->state, n, d_state);
+  else get_state_kernel<float><<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(c->sc32, (const float *)c->state, n, d_state);
   c->launches++;
   CU(cudaGetLastError());
   return 0;
