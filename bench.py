@@ -43,6 +43,10 @@ ALGO_BYTES = {  # action + obs + reward + done + state read + st
     ("Tennisbot-v0", "f32"): 8 + 48 + 4 + 1 + 128 + 128,
     ("Tennisbot-v0", "f64"): 8 + 48 + 4 + 1 + 256 + 256,
 }
+MOVED_BYTES = {  # what a control step actually moves per env (profiles/r2_traffic.json): packs 0-3 + 7 each way, I/O
+    ("SwingRacket-v0", "f64"): 160 + 160 + 53, ("SwingRacket-v0", "f32"): 80 + 80 + 53,
+    ("Tennisbot-v0", "f64"): 224 + 224 + 61, ("Tennisbot-v0", "f32"): 112 + 112 + 61,
+}
 ALGO_BYTES_F32_STATE = {"SwingRacket-v0": 24 + 24 + 4 + 1 + 128 + 128, "Tennisbot-v0": 8 + 48 + 4 + 1 + 128 + 128}  # BASELINE.md's yardstick
 EPISODE_STEPS = 26
 GROUP = 128
@@ -119,7 +123,7 @@ class ClockSampler:
 def measured_traffic(env, precision, n):
     """DRAM bytes of one env step of the whole batch (dram__bytes_read.sum + dram__bytes_write.sum of a step_kernel launch
     + 1/26 of a fast-forward ff_kernel launch) from the committed ncu captures of the same workload, else None."""
-    p = ROOT / "profiles" / "r1_traffic.json"
+    p = ROOT / "profiles" / "r2_traffic.json"
     key = {"SwingRacket-v0": "dram_bytes_per_env_step_launch_pair", "Tennisbot-v0": "hit_step_kernel_dram_bytes_per_launch"}[env]
     if precision == "f64" and n == 1 << 20 and p.exists():
         try:
@@ -514,13 +518,17 @@ def run_b200(args, rank, world):
                          "kernels": {
                              "step_kernel": {"ms_per_launch": ms_step, "achieved_gbs": step_gbs, "frac": step_gbs / peak, "bound": "hbm",
                                              "share_of_step_time": ms_a / max(ms_a + ms_b, 1e-9),
-                                             "note": "algorithmic bytes of all envs over this kernel's mean launch time; in SwingRacket the "
-                                                     "envs whose control substep can touch something (up to ~30 % in the last steps of an "
-                                                     "episode) are only classified here and stepped by ff_kernel's prologue"},
+                                             "moved_bytes_per_env_step": MOVED_BYTES.get((args.env, args.precision)),
+                                             "wire_gbs": n * MOVED_BYTES.get((args.env, args.precision), algo) / (ms_step * 1e-3) / 1e9,
+                                             "wire_frac": n * MOVED_BYTES.get((args.env, args.precision), algo) / (ms_step * 1e-3) / 1e9 / peak,
+                                             "note": "achieved_gbs / frac: ALGORITHMIC bytes (SURVEY 8(d)) of all envs over this kernel's mean launch "
+                                                     "time - above the peak because the kernel moves fewer: it re-derives the episode constants "
+                                                     "from the RNG counters and tabulates the free-falling ball's velocity instead of loading them; "
+                                                     "wire_*: the bytes a control step actually moves (profiles/r2_traffic.json)"},
                              "ff_kernel": {"ms_per_launch": ms_b / max(nk, 1), "share_of_step_time": ms_b / max(ms_a + ms_b, 1e-9),
                                            "ms_per_episode": ms_b / max(nk, 1) * (EPISODE_STEPS if args.env == "SwingRacket-v0" else 1),
-                                           "bound": "fp64 pipe / latency: ~150 dependent FP64 instructions per physics substep, "
-                                                    "~110 substeps per env on its 26th step; not memory-bound (see profiles/)"}}},
+                                           "bound": "fp64 pipe / latency: ~160 FP64 instructions per physics substep, ~106 substeps per env "
+                                                    "on its 26th step; not memory-bound (profiles/r2_ff_kernel_f64_ncu.txt)"}}},
             "e2e": {"value": total_envs * args.e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "steps": args.e2e_steps, "api": "TennisBatch.step_host -> tb_step_host: pinned host buffers in and out; the kernels read the actions from and write obs/reward/done to host memory over PCIe themselves (both directions concurrent with the compute)"},
             "gpu_launches": int(launches),
