@@ -259,7 +259,7 @@ constexpr int kFlagLastShift = 16;  // contact bits of the flight's last substep
 constexpr int kFlagVisitShift = 4;  // 2 bits: visits to the full path during this flight
 // counter words of one step's set
 constexpr int kCtrWords = 512;  // words that are polled never share a 128-byte line with words that are claimed from; words 128.. : TB_FF_DIAG time series
-constexpr int kCFront = 0, kCBack = 1, kCError = 3;
+constexpr int kCFront = 0, kCBack = 1, kCSafe = 2, kCError = 3;
 constexpr int kDRounds = 48, kDFullEnvs = 49, kDPhase = 50, kDFinish = 62;  // tb_ff_diagnostics
 constexpr int kCFull0 = 4;        // entries of queue_full (appended by step_kernel)
 constexpr int kCClaim0 = 5;       // claimed entries of queue (ff_kernel's flight lanes)
@@ -460,10 +460,14 @@ __device__ __forceinline__ void step_tile(const Scene<T> &sc, const StepIO &io, 
   // envs entering the fast-forward: queue them for ff_kernel (only SwingRacket ever does).  Longest-job-first:
   // a ball the racket has hit flies for up to 775 more substeps and is queued from the FRONT, a ball still in free
   // fall lands after ~100 and is queued from the BACK, so the long flights start first and the short ones fill
-  // the tail of ff_kernel.  An env whose first fast-forward substep needs the full treatment (ball within reach of
-  // the racket, mostly: a hit in progress) goes to the full queue, which ff_kernel serves before anything else.
+  // the tail of ff_kernel.  LAST come the free-falling balls that are moving away from the racket's plane at 0.5 m/s
+  // or more: they do not meet the racket on the way down (2 in 60 000 do, against 3 % of the other free-falling ones,
+  // and a visit to the servers shortly before the landing is what the launch would end up waiting for).  An env whose
+  // first fast-forward substep needs the full treatment (ball within reach of the racket, mostly: a hit in progress)
+  // goes to the full queue, which ff_kernel serves before anything else.
+  constexpr int kNone = 4;
   bool queued = valid && !fin;
-  int cls = 3;
+  int cls = kNone;
   if (KIND == TB_ENV_SWING && queued) {
     // front of the queue as well: a ball that is closing in on the racket's plane and would cross it within ~0.6 s.
     // If the racket is there when it does, the flight that follows is a long one, and it should not start last.
@@ -472,7 +476,7 @@ __device__ __forceinline__ void step_tile(const Scene<T> &sc, const StepIO &io, 
     const T d = nx * (s.bp[0] - s.rp[0]) + ny * (s.bp[1] - s.rp[1]) + nz * (s.bp[2] - s.rp[2]);
     const T vn = nx * (s.bv[0] - s.rv[0]) + ny * (s.bv[1] - s.rv[1]) + nz * (s.bv[2] - s.rv[2]);
     const bool closing = d * vn < 0 && M<T>::abs(d) < (T)0.6 * M<T>::abs(vn);
-    cls = ff_classify_state(sc, s) == kFfFull ? 2 : ((dot3(s.bv, s.bv) > (T)9 || closing) ? 0 : 1);
+    cls = ff_classify_state(sc, s) == kFfFull ? 2 : ((dot3(s.bv, s.bv) > (T)9 || closing) ? 0 : (d * vn > 0 && M<T>::abs(vn) >= (T)0.5) ? 3 : 1);
     s.flags = (s.flags & ~((0xff << kFlagEventShift) | kStPristine)) | kFlagInFlight | kFlagFirst | (c.events << kFlagEventShift);
   }
   // the state goes back first: the bookkeeping below synchronises the CTA, and on 25 steps out of 26 it has nothing to do
@@ -482,11 +486,12 @@ __device__ __forceinline__ void step_tile(const Scene<T> &sc, const StepIO &io, 
   }
   if (KIND == TB_ENV_SWING) {
     constexpr int W = kBlock / 32;
-    if (!__syncthreads_or(cls != 3)) return;  // (every thread of the CTA gets here: DEFER lanes and tail lanes included)
-    unsigned m0 = __ballot_sync(full, cls == 0), m1 = __ballot_sync(full, cls == 1), m2 = __ballot_sync(full, cls == 2);
-    if (lane == 0) { s_cnt[wib] = __popc(m0); s_cnt[W + wib] = __popc(m1); s_cnt[2 * W + wib] = __popc(m2); }
+    if (!__syncthreads_or(cls != kNone)) return;  // (every thread of the CTA gets here: DEFER lanes and tail lanes included)
+    unsigned m0 = __ballot_sync(full, cls == 0), m1 = __ballot_sync(full, cls == 1), m2 = __ballot_sync(full, cls == 2),
+             m3 = __ballot_sync(full, cls == 3);
+    if (lane == 0) { s_cnt[wib] = __popc(m0); s_cnt[W + wib] = __popc(m1); s_cnt[2 * W + wib] = __popc(m2); s_cnt[3 * W + wib] = __popc(m3); }
     __syncthreads();
-    if (threadIdx.x < 3) {
+    if (threadIdx.x < 4) {
       int k = threadIdx.x, tot = 0;
 #pragma unroll
       for (int w = 0; w < W; ++w) {
@@ -494,15 +499,18 @@ __device__ __forceinline__ void step_tile(const Scene<T> &sc, const StepIO &io, 
         s_cnt[k * W + w] = tot;
         tot += a;
       }
-      unsigned long long *ctr = qctr + (k == 0 ? kCFront : k == 1 ? kCBack : kCFull0);
+      unsigned long long *ctr = qctr + (k == 0 ? kCFront : k == 1 ? kCBack : k == 2 ? kCFull0 : kCSafe);
       s_base[k] = tot ? atomicAdd(ctr, (unsigned long long)tot) : 0ULL;
     }
     __syncthreads();
     if (queued) {
+      // queue: front entries from [0] up, back entries from [n - 1] down; queue_full: full entries from [0] up, the
+      // last-to-start entries from [n - 1] down (an env is in one list only, so neither pair can meet)
       const unsigned lt = (1u << lane) - 1u;
       if (cls == 0) io.queue[s_base[0] + s_cnt[wib] + __popc(m0 & lt)] = (int)me;
       else if (cls == 1) io.queue[io.n - 1 - (int64_t)(s_base[1] + s_cnt[W + wib] + __popc(m1 & lt))] = (int)me;
-      else io.queue_full[s_base[2] + s_cnt[2 * W + wib] + __popc(m2 & lt)] = (int)me;
+      else if (cls == 2) io.queue_full[s_base[2] + s_cnt[2 * W + wib] + __popc(m2 & lt)] = (int)me;
+      else io.queue_full[io.n - 1 - (int64_t)(s_base[3] + s_cnt[3 * W + wib] + __popc(m3 & lt))] = (int)me;
     }
   }
 }
@@ -516,8 +524,8 @@ __device__ __forceinline__ void step_tile(const Scene<T> &sc, const StepIO &io, 
 template <typename T, int KIND, bool STAGE, int MINB = 0>
 __global__ void __launch_bounds__(kBlock, MINB ? MINB : StepMinBlocks<T, KIND>::v) step_kernel(const __grid_constant__ Scene<T> sc, const __grid_constant__ StepIO io) {
   __shared__ unsigned long long sacc[kBlock / 32][TB_NUM_STATS];
-  __shared__ int s_cnt[3 * (kBlock / 32)];
-  __shared__ unsigned long long s_base[3];
+  __shared__ int s_cnt[4 * (kBlock / 32)];
+  __shared__ unsigned long long s_base[4];
   // Each warp's 32 action rows come in and its 32 observation rows go out as one contiguous tile through shared
   // memory (warp-private, __syncwarp only): [N, act] / [N, obs] float32 rows are 24 / 8 / 48 bytes, which per-thread
   // accesses would turn into strided partial sectors - harmless in HBM behind L2, costly when the caller's buffers
@@ -789,6 +797,9 @@ __device__ __noinline__ void ff_finish_dense(const Scene<T> &sc, const StepIO &i
       s.step = (int)as_int(p7.y);
       s.episode = (uint32_t)as_int(p7.w);
       events = (flags >> kFlagEventShift) & 0xff;
+#ifdef TB_FF_DIAG_VISITS  // (analysis builds only: bit 7 of the events byte = the flight went through the servers)
+      if ((flags >> kFlagVisitShift) & 3) events |= 128;
+#endif
       reward = ff_reward(s, (flags >> kFlagLastShift) & 0xff);
       s.ret = p7.x + (T)reward;
       s.flags = flags & kFlagDone;  // drop every in-flight mark
@@ -857,9 +868,10 @@ __device__ __forceinline__ int ff_finishing_duty(const Scene<T> &sc, const StepI
   return 2;
 }
 
-// A flight warp.  n0 / qfront: step_kernel's queue (front / back layout); nctl, total0: see ff_all_landed.
+// A flight warp.  n0 / qfront / qmid: step_kernel's lists in the order they are claimed (front: [0, qfront), back: [qfront, qmid),
+// last-to-start: [qmid, n0)); nctl, total0: see ff_all_landed.
 template <typename T>
-__device__ __forceinline__ void ff_flight_warp(const Scene<T> &sc, const StepIO &io, unsigned epoch, long long n0, long long qfront,
+__device__ __forceinline__ void ff_flight_warp(const Scene<T> &sc, const StepIO &io, unsigned epoch, long long n0, long long qfront, long long qmid,
                                                long long nctl, long long total0, WarpStats &ws, int &nsub) {
   const unsigned full = 0xffffffffu;
   const int lane = ws.lane;
@@ -878,6 +890,10 @@ __device__ __forceinline__ void ff_flight_warp(const Scene<T> &sc, const StepIO 
   bool exhausted0 = n0 == 0, first = false, first_pending = false, pass1_over = false;
   long long idle_since = 0;
   unsigned nap = 0;  // idle back-off: thousands of warps polling one cache line would starve the servers' atomics on it
+#ifdef TB_FF_DIAG
+  int src = 0;
+  const unsigned long long ts0 = global_ns();
+#endif
   for (;;) {
     // ---- substeps until enough lanes want to leave / claim (no call, no rare code in this loop)
     unsigned run_m, leave_m;
@@ -914,6 +930,9 @@ __device__ __forceinline__ void ff_flight_warp(const Scene<T> &sc, const StepIO 
         if (landed && ld_ctr(ctr + kCLanded) + 100 >= (unsigned long long)total0 + ld_ctr(ctr + kCDynTotal)) ff_diag_late(ctr, L.step, L.step - step0, visits, 0);
 #endif
         ff_store(base, io.n, (int64_t)me, L, flags);
+#ifdef TB_FF_DIAG
+        if (to_full) { atomicAdd(ctr + 92 + src, 1ULL); atomicAdd(ctr + 95 + src, (unsigned long long)(L.step - 26)); }
+#endif
       }
       dq_push(io.dq_full, io.dq_cap, ctr + kCFullTail, epoch, to_full, me, lane, ctr + kCError);
       unsigned done_m = __ballot_sync(full, landed);
@@ -930,6 +949,11 @@ __device__ __forceinline__ void ff_flight_warp(const Scene<T> &sc, const StepIO 
       if (!ctr[kDPhase + 1] && ld * 2 >= tot) ctr[kDPhase + 1] = t;
       if (!ctr[kDPhase + 2] && ld * 10 >= tot * 9) ctr[kDPhase + 2] = t;
       if (!ctr[kDPhase + 3] && ld * 100 >= tot * 99) ctr[kDPhase + 3] = t;
+      int bin = (int)((t - ts0) / 100000ULL);
+      if (bin < 34 && !ctr[128 + 5 * bin]) {
+        ctr[128 + 5 * bin] = ld + 1; ctr[129 + 5 * bin] = ld_ctr(ctr + kCClaim0); ctr[130 + 5 * bin] = ld_ctr(ctr + kCFullTail);
+        ctr[131 + 5 * bin] = ld_ctr(ctr + kCLateTail); ctr[132 + 5 * bin] = ld_ctr(ctr + kCLateHead);
+      }
     }
 #endif
     // ---- lanes without an env: the next entries of step_kernel's queue (one atomic per warp); once that is empty, a
@@ -937,7 +961,12 @@ __device__ __forceinline__ void ff_flight_warp(const Scene<T> &sc, const StepIO 
     bool got = false;
     if (st == kWait) {
       int e = dq_poll(io.dq_late, ticket, epoch);
-      if (e >= 0) { me = e; got = true; }
+      if (e >= 0) {
+        me = e; got = true;
+#ifdef TB_FF_DIAG
+        src = 2;
+#endif
+      }
     }
     unsigned idle = __ballot_sync(full, st == kIdle);
     if (idle) {
@@ -972,8 +1001,11 @@ __device__ __forceinline__ void ff_flight_warp(const Scene<T> &sc, const StepIO 
         if (at + want >= n0) exhausted0 = true;
         long long idx = at + __popc(init_m & ((1u << lane) - 1u));
         if (st == kIdle && idx < n0) {
-          me = idx < qfront ? __ldcg(io.queue + idx) : __ldcg(io.queue + (io.n - 1 - (idx - qfront)));
+          me = __ldcg(idx < qfront ? io.queue + idx : idx < qmid ? io.queue + (io.n - 1 - (idx - qfront)) : io.queue_full + (io.n - 1 - (idx - qmid)));
           got = true;
+#ifdef TB_FF_DIAG
+          src = idx < qfront ? 0 : 1;  // (last-to-start entries count as back)
+#endif
         }
       }
     }
@@ -1049,9 +1081,9 @@ __device__ __noinline__ void ff_server_warp(const Scene<T> &sc, const StepIO &io
   for (;;) {
 #ifdef TB_FF_DIAG
     if (blockIdx.x == 0 && lane == 0) {
-      int bin = (int)((global_ns() - ts0) / 500000ULL);
+      int bin = (int)((global_ns() - ts0) / 100000ULL);
       if (bin < 34 && !ctr[128 + 5 * bin]) {
-        ctr[128 + 5 * bin] = ld_ctr(ctr + kCLanded) + 1; ctr[129 + 5 * bin] = ld_ctr(ctr + kCFullTail); ctr[130 + 5 * bin] = ld_ctr(ctr + kCFullHead);
+        ctr[128 + 5 * bin] = ld_ctr(ctr + kCLanded) + 1; ctr[129 + 5 * bin] = ld_ctr(ctr + kCClaim0); ctr[130 + 5 * bin] = ld_ctr(ctr + kCFullTail);
         ctr[131 + 5 * bin] = ld_ctr(ctr + kCLateTail); ctr[132 + 5 * bin] = ld_ctr(ctr + kCLateHead);
       }
     }
@@ -1284,7 +1316,8 @@ __global__ void __launch_bounds__(kBlock, MinBlocks<T>::v) ff_kernel(const __gri
   if (blockIdx.x == 0 && threadIdx.x == 0) io.epoch[0] = epoch == kEpochLast ? 0u : epoch;  // (read by the next step_kernel only)
   unsigned long long *ctr = ctr_set(io, epoch - 1u);
   // (all four written by step_kernel, same stream)
-  const long long nctl = (long long)ctr[kCCtl], qfront = (long long)ctr[kCFront], qn0 = qfront + (long long)ctr[kCBack], nfull0 = (long long)ctr[kCFull0];
+  const long long nctl = (long long)ctr[kCCtl], qfront = (long long)ctr[kCFront], qmid = qfront + (long long)ctr[kCBack],
+                  qn0 = qmid + (long long)ctr[kCSafe], nfull0 = (long long)ctr[kCFull0];
   const long long total0 = qn0 + nfull0;
   if (nctl == 0 && total0 == 0) return;
   if (io.ff_ran_host && blockIdx.x == 0 && threadIdx.x == 0) *io.ff_ran_host = 1u;
@@ -1320,7 +1353,7 @@ __global__ void __launch_bounds__(kBlock, MinBlocks<T>::v) ff_kernel(const __gri
     server = s_server != 0;
   }
   if (server) ff_server_warp<T>(sc, io, epoch, nfull0, nctl, total0, &ws, &nsub);
-  else ff_flight_warp<T>(sc, io, epoch, qn0, qfront, nctl, total0, ws, nsub);
+  else ff_flight_warp<T>(sc, io, epoch, qn0, qfront, qmid, nctl, total0, ws, nsub);
   if (diag) {
     unsigned long long t = global_ns();
 #ifdef TB_FF_DIAG
@@ -2668,6 +2701,9 @@ int tb_ff_diagnostics(tb_ctx *c, int64_t *h_out) {
     std::fprintf(stderr, "server substeps: lean %llu (mean %llu cycles, %llu with contact), handed to ff_full %llu (lean part mean %llu cycles, ff_full mean %llu cycles; "
                  "%llu with racket contact, %llu with another event); loads %llu (mean %llu cycles)\n", s[100], s[100] ? s[101] / s[100] : 0ULL, s[107], s[102],
                  s[102] ? s[103] / s[102] : 0ULL, s[102] ? s[104] / s[102] : 0ULL, s[105], s[106], s[108], s[108] ? s[109] / s[108] : 0ULL);
+  if (std::getenv("TB_FF_DIAG_DUMP"))
+    std::fprintf(stderr, "visits to the servers by where the flight lane got the env: front list %llu (mean substep %llu), back list %llu (%llu), late queue %llu (%llu)\n",
+                 s[92], s[92] ? s[95] / s[92] : 0ULL, s[93], s[93] ? s[96] / s[93] : 0ULL, s[94], s[94] ? s[97] / s[94] : 0ULL);
   if (std::getenv("TB_FF_DIAG_DUMP")) {
     unsigned long long tmax = 0;
     for (int i = 0; i < 100 && i < (int)s[299]; ++i) tmax = s[301 + 2 * i] > tmax ? s[301 + 2 * i] : tmax;
@@ -2677,8 +2713,8 @@ int tb_ff_diagnostics(tb_ctx *c, int64_t *h_out) {
   }
   if (std::getenv("TB_FF_DIAG_DUMP"))
     for (int b = 0; b < 34 && s[128 + 5 * b]; ++b)
-      std::fprintf(stderr, "t=%.1fms landed %llu fullq %llu/%llu lateq %llu/%llu\n", 0.5 * b, s[128 + 5 * b] - 1, s[130 + 5 * b], s[129 + 5 * b],
-                   s[132 + 5 * b], s[131 + 5 * b]);
+      std::fprintf(stderr, "t=%.1fms landed %llu claimed %llu full queue tail %llu late queue head / tail %llu / %llu\n", 0.1 * b, s[128 + 5 * b] - 1, s[129 + 5 * b],
+                   s[130 + 5 * b], s[132 + 5 * b], s[131 + 5 * b]);
   return 0;
 }
 
