@@ -105,6 +105,10 @@ constexpr int kBallVzEntries = 32;  // Scene::ball_vz (SwingRacket's control pha
 constexpr int kRacketEdges = TB_RACKET_OUTLINE_N;
 constexpr int kGoalEdges = TB_GOAL_SIDES;
 
+#ifndef TB_COARSE_UNROLL
+#define TB_COARSE_UNROLL 6
+#endif
+constexpr int kCoarseEdges = 18, kCoarseUnroll = TB_COARSE_UNROLL;
 template <typename T> struct Edge {
   T ax, ay, ex, ey, inv_len2, nx, ny;
 };
@@ -122,6 +126,11 @@ template <typename T, int NE> struct Prism {
   // between the quadrilateral's two edge lines and above v = out_lo.
   T out_a, out_b, out_v, out_lo;
   T out_inv_a, out_inv_b;  // reciprocal semi-axes of the ellipse that contains the rim-neighbourhood of E(out_a, out_b), rim = ffp_rim
+  // A coarse outline for what the two quick tests leave undecided: a subset of the edge lines (the long edges, and one of
+  // every few along the arcs: a convex polygon that CONTAINS the outline and overshoots it by a millimetre or two), as
+  // point + outward unit normal; unused entries repeat the first.  (ff_kernel's flight loop: a lane in the band between
+  // the quick tests keeps 31 others waiting while it walks the edge table.)
+  T c_ax[kCoarseEdges], c_ay[kCoarseEdges], c_nx[kCoarseEdges], c_ny[kCoarseEdges];
 };
 // true: (u, v) is strictly inside the outline (false says nothing)
 template <typename T, int NE> __device__ __forceinline__ bool prism_inside_fast(const Prism<T, NE> &pr, T u, T v) {
@@ -1209,6 +1218,9 @@ constexpr int kFfDone = 3;  // (returned by the step functions) the env step is 
 // only, so which path integrates a given substep never depends on the other lanes of the warp.
 // nb, nr, nw: squared speeds of ball, racket and racket spin.
 // QUICK: the outline test with its quick accept / reject first (ff_kernel's loops); else the plain loop (step_kernel).
+#ifdef TB_FF_DIAG
+__device__ unsigned long long g_diag_edge_loops, g_diag_quick_in, g_diag_quick_out, g_diag_edge_in;
+#endif
 // Around the rim: is the ball within `rim` of the hull?  pl0: its face-normal coordinate, max_side: the largest signed
 // distance to an edge line of the outline (a lower bound of the in-plane distance to it).  Beyond the plate's thickness
 // AND beyond the outline the two offsets are orthogonal, so the distance is at least their root sum of squares; taking
@@ -1241,16 +1253,25 @@ __device__ __forceinline__ int ff_classify_core(const Scene<T> &sc, const T *rp,
       // the substep loop's schedule (measured on B200: +7 % on the whole fast-forward launch).
       T q1 = pl1, q2 = pl2;
       opaque(q1); opaque(q2);
+#ifdef TB_FF_DIAG
+      if (prism_inside_fast(sc.racket, q1, q2)) atomicAdd(&g_diag_quick_in, 1ULL);
+      else if (prism_outside_fast(sc.racket, q1, q2, sc.ffp_rim)) atomicAdd(&g_diag_quick_out, 1ULL);
+#endif
       if (prism_inside_fast(sc.racket, q1, q2)) racket = true;
       else if (prism_outside_fast(sc.racket, q1, q2, sc.ffp_rim)) racket = false;
-      else {
+      else {  // the coarse outline decides (it contains the outline: the signed distance to its edge lines is a lower bound too)
+#ifdef TB_FF_DIAG
+        atomicAdd(&g_diag_edge_loops, 1ULL);
+#endif
         T max_side = -M<T>::inf();
-#pragma unroll kEdgeUnroll
-        for (int i = 0; i < kRacketEdges; ++i) {
-          const Edge<T> &e = sc.racket.e[i];
-          T side = (q1 - e.ax) * e.nx + (q2 - e.ay) * e.ny;
+#pragma unroll kCoarseUnroll
+        for (int i = 0; i < kCoarseEdges; ++i) {
+          T side = (q1 - sc.racket.c_ax[i]) * sc.racket.c_nx[i] + (q2 - sc.racket.c_ay[i]) * sc.racket.c_ny[i];
           max_side = side > max_side ? side : max_side;
         }
+#ifdef TB_FF_DIAG
+        if (!(max_side > sc.ffp_rim)) atomicAdd(&g_diag_edge_in, 1ULL);
+#endif
         // (the in-plane bound alone: ff_rim_within here keeps a ball in the corner band in this lane, where it takes the edge
         // loop above every substep with the other 31 lanes waiting - measured +0.06 ms per launch, more than the servers save)
         racket = !(max_side > sc.ffp_rim);

@@ -1774,6 +1774,34 @@ template <typename T, int NE> static void build_prism(Prism<T, NE> &pr, const do
     pr.out_v = (T)vlo; pr.out_lo = (T)-1e30;
     pr.out_inv_a = pr.out_inv_b = 0;  // (set by build_scene once the rim is known)
   }
+  {
+    // coarse outline: walk the edges and keep one whenever the direction has turned by `turn` since the last one kept, and every
+    // edge that is long (its neighbours' lines would meet far outside the outline); the smallest `turn` that fits the table
+    double len[NE], med[NE], ang[NE];
+    for (int i = 0; i < NE; ++i) {
+      const double *a = v[i], *b = v[(i + 1) % NE];
+      len[i] = med[i] = std::hypot(b[0] - a[0], b[1] - a[1]);
+      ang[i] = std::atan2(b[1] - a[1], b[0] - a[0]);
+    }
+    std::sort(med, med + NE);
+    const double long_edge = 1.5 * med[NE / 2];
+    int keep[NE], nk = 0;
+    for (double turn = 10.0; turn <= 180.0; turn += 1.0) {
+      nk = 0;
+      double last = 0;
+      for (int i = 0; i < NE; ++i) {
+        double d = nk ? std::remainder(ang[i] - last, 2 * M_PI) * (180.0 / M_PI) : 1e9;
+        // (an edge before a long one is kept too when skipping it would leave more than `turn` to the long edge's predecessor)
+        if (len[i] >= long_edge || std::fabs(d) >= turn) { keep[nk++] = i; last = ang[i]; }
+      }
+      if (nk <= kCoarseEdges) break;
+    }
+    if (nk == 0 || nk > kCoarseEdges) { nk = 0; for (int i = 0; i < NE && nk < kCoarseEdges; ++i) keep[nk++] = i; }  // (NE <= kCoarseEdges only)
+    for (int k = 0; k < kCoarseEdges; ++k) {
+      const int i = keep[k < nk ? k : 0];
+      pr.c_ax[k] = (T)v[i][0]; pr.c_ay[k] = (T)v[i][1]; pr.c_nx[k] = (T)nx[i]; pr.c_ny[k] = (T)ny[i];
+    }
+  }
   pr.tz_lo = 1; pr.tz_hi = 0;
   for (int k = 0; k < 2; ++k) { pr.t_ax[k] = pr.t_ay[k] = 0; pr.t_nx[k] = pr.t_ny[k] = 0; }
   if (quad_edges) {
@@ -2242,6 +2270,11 @@ int tb_scene_constant(const char *name, int index, double *value) {
     if (!std::strcmp(name, "racket_rim")) { *value = sd.ffp_rim; return 0; }
     if (!std::strcmp(name, "racket_inside") && index >= 0 && index < 5) { *value = in_r[index]; return 0; }
     if (!std::strcmp(name, "goal_inside") && index >= 0 && index < 5) { *value = in_g[index]; return 0; }
+    if (!std::strcmp(name, "racket_coarse_edge") && index >= 0 && index < 4 * kCoarseEdges) {  // (point u, v; outward normal u, v) per edge
+      const double *t[4] = {sd.racket.c_ax, sd.racket.c_ay, sd.racket.c_nx, sd.racket.c_ny};
+      *value = t[index & 3][index >> 2];
+      return 0;
+    }
     if (!std::strcmp(name, "racket_quad_edge") && index >= 0 && index < 8) {
       const double q[8] = {sd.racket.t_ax[0], sd.racket.t_ay[0], sd.racket.t_nx[0], sd.racket.t_ny[0], sd.racket.t_ax[1], sd.racket.t_ay[1], sd.racket.t_nx[1], sd.racket.t_ny[1]};
       *value = q[index];
@@ -2704,6 +2737,17 @@ int tb_ff_diagnostics(tb_ctx *c, int64_t *h_out) {
   if (std::getenv("TB_FF_DIAG_DUMP"))
     std::fprintf(stderr, "visits to the servers by where the flight lane got the env: front list %llu (mean substep %llu), back list %llu (%llu), late queue %llu (%llu)\n",
                  s[92], s[92] ? s[95] / s[92] : 0ULL, s[93], s[93] ? s[96] / s[93] : 0ULL, s[94], s[94] ? s[97] / s[94] : 0ULL);
+#ifdef TB_FF_DIAG
+  if (std::getenv("TB_FF_DIAG_DUMP")) {
+    unsigned long long v[4] = {0, 0, 0, 0}, z = 0;
+    cudaMemcpyFromSymbol(&v[0], g_diag_edge_loops, 8); cudaMemcpyFromSymbol(&v[1], g_diag_quick_in, 8);
+    cudaMemcpyFromSymbol(&v[2], g_diag_quick_out, 8); cudaMemcpyFromSymbol(&v[3], g_diag_edge_in, 8);
+    cudaMemcpyToSymbol(g_diag_edge_loops, &z, 8); cudaMemcpyToSymbol(g_diag_quick_in, &z, 8);
+    cudaMemcpyToSymbol(g_diag_quick_out, &z, 8); cudaMemcpyToSymbol(g_diag_edge_in, &z, 8);
+    std::fprintf(stderr, "racket classification inside the slab and the bounding box (since the last dump): quick inside %llu, quick outside %llu, edge loop %llu (within the rim: %llu)\n",
+                 v[1], v[2], v[0], v[3]);
+  }
+#endif
   if (std::getenv("TB_FF_DIAG_DUMP")) {
     unsigned long long tmax = 0;
     for (int i = 0; i < 100 && i < (int)s[299]; ++i) tmax = s[301 + 2 * i] > tmax ? s[301 + 2 * i] : tmax;

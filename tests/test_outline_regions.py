@@ -51,3 +51,22 @@ def test_quick_regions_agree_with_the_outline():
     # and the quick tests are worth having: they settle all but a thin band
     undecided = ~(inside | outside)
     assert undecided[len(band):].mean() < 0.2
+
+
+def test_coarse_outline_contains_the_outline():
+    """ff_classify's band test walks a coarse polygon (a subset of the outline's edge lines): it must contain the outline - then
+    "farther than rim from the coarse polygon" implies "farther than rim from the outline" - and stay within millimetres of it."""
+    from tennisbot_rl_b200 import _lib
+
+    V = _consts()[0]
+    g = lambda i: _lib.scene_constant("racket_coarse_edge", i)  # noqa: E731
+    C = np.array([[g(4 * k + j) for j in range(4)] for k in range(18)])
+    assert np.allclose(np.hypot(C[:, 2], C[:, 3]), 1.0)
+    side = ((V[:, None, :] - C[None, :, :2]) * C[None, :, 2:]).sum(2)
+    assert side.max() <= 1e-12                               # every outline vertex inside every coarse edge line
+    U = np.unique(C.round(12), axis=0)
+    U = U[np.argsort(np.arctan2(U[:, 3], U[:, 2]))]
+    assert len(U) >= 8
+    corners = np.array([np.linalg.solve(np.array([a[2:], b[2:]]), np.array([a[:2] @ a[2:], b[:2] @ b[2:]])) for a, b in zip(U, np.roll(U, -1, 0))])
+    over = _dist(V, corners)
+    assert over.min() > -1e-9 and over.max() < 0.004, over   # the coarse polygon's corners overshoot the outline by < 4 mm
