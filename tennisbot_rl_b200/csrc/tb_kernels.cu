@@ -2444,7 +2444,9 @@ static int step_impl(tb_ctx *c, const float *d_actions, float *d_obs, float *d_r
 }
 int tb_step(tb_ctx *c, const float *d_actions, float *d_obs, float *d_reward, uint8_t *d_done, float *d_terminal_obs,
             uint8_t *d_events, void *stream) {
-  return step_impl(c, d_actions, d_obs, d_reward, d_done, d_terminal_obs, d_events, stream, false);
+  // TB_STEP_STAGE (measurements, tools/e2e_paths_probe.py): the kernel build that tb_step_host's zero copy uses
+  static const bool stage = std::getenv("TB_STEP_STAGE") != nullptr;
+  return step_impl(c, d_actions, d_obs, d_reward, d_done, d_terminal_obs, d_events, stream, stage);
 }
 
 int tb_rollout(tb_ctx *c, int action_mode, int k_steps, float *d_obs, float *d_reward_sum, int32_t *d_done_count, void *stream) {
@@ -2656,10 +2658,12 @@ int tb_step_host(tb_ctx *c, const float *h_actions, float *h_obs, float *h_rewar
   size_t n = (size_t)c->cfg.num_envs, od = (size_t)tb_obs_dim(c->cfg.env_kind), ad = (size_t)tb_act_dim(c->cfg.env_kind);
   cudaStream_t s = c->own_stream;
   // mode: TB_HOST_MODE = zero_copy (default for pinned buffers) | pipeline | staging (pageable memory always takes it).
-  // Measured on the B200 box, 1 Mi SwingRacket envs, per step averaged over episodes: zero copy 0.95 ms, pipeline 1.19 ms,
-  // staging 1.24 ms.  The link alone allows 0.63 ms (42 GB/s up, 53 GB/s down, concurrently); the pipeline does not get there:
-  // its ~70 small copies, event records and waits per step cost more than the overlap wins, and every fast-forward step
-  // copies the outputs twice.
+  // Measured on the B200 box, 1 Mi SwingRacket envs, per step averaged over episodes: zero copy 0.92 ms, pipeline 1.19 ms,
+  // staging 1.24 ms.  The link carries 50 GB/s either way alone and 80-92 GB/s both ways at once (0.63-0.68 ms for a step's
+  // 55.6 MB through the copy engines); a zero-copy light step is 0.77 ms (72 GB/s, tools/e2e_paths_probe.py).  The pipeline's
+  // device time line (8 slices): uploads slowed to 33 GB/s by the concurrent downloads, 0.72 ms, then 0.16 ms for the last
+  // slice's results - and every fast-forward step copies the outputs twice.  Reading the actions in place and copying only the
+  // results down ("hybrid") was measured too: kernel slices 97 us instead of 63, 0.93 ms per light step.
   const char *mode = std::getenv("TB_HOST_MODE");
   const bool pinned = mapped_alias(h_actions) && mapped_alias(h_obs) && mapped_alias(h_reward) && mapped_alias(h_done) &&
                       (mapped_alias(h_terminal_obs) || !h_terminal_obs) && (mapped_alias(h_events) || !h_events);
