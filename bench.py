@@ -75,49 +75,106 @@ def parse():
 
 # ---------------------------------------------------------------------------------------------- helpers
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons while the timed region runs (B200_PROFILING.md's clocks line), one
-    long-running `nvidia-smi -lms 50` whose rows between start() and stop() are kept."""
+    """SM clock, throttle reasons and power while the timed region runs (B200_PROFILING.md's clocks line).  NVML from a
+    polling thread (a row per millisecond: the driver's 20-step window lasts under 4 ms) plus one row taken by the launching
+    thread itself once the whole window is queued and the device is still working through it (sample_now), so that a window of
+    any length holds a sample; without the NVML
+    bindings, one long-running `nvidia-smi -lms 50` whose rows between start() and stop() are kept."""
 
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,power.draw")
+    REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
 
-    def __init__(self, index):
-        self.rows, self.proc, self.thread = [], None, None
+    def __init__(self, index, uuid=None):
+        self.rows, self.proc, self.thread, self.nvml, self.handle = [], None, None, None, None
+        self.keep, self.quit, self.source = False, False, None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            try:
+                self.handle = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + str(uuid)) if uuid and not str(uuid).startswith("GPU-") else str(uuid))
+            except Exception:
+                self.handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.nvml = pynvml
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM)
+            self._nvml_row()  # (fails here, not in the timed region, if a query is unsupported)
+            self.rows.clear()
+            self.source = "nvml"
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
                                           "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
             return
-        self.keep = False
+        self.source = "nvidia-smi"
         self.thread = threading.Thread(target=self._pump, daemon=True)
         self.thread.start()
+
+    def _nvml_row(self):
+        n, h = self.nvml, self.handle
+        sm = n.nvmlDeviceGetClockInfo(h, n.NVML_CLOCK_SM)
+        try:
+            bits = n.nvmlDeviceGetCurrentClocksEventReasons(h)
+        except Exception:
+            bits = n.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+        try:
+            watts = n.nvmlDeviceGetPowerUsage(h) / 1000.0
+        except Exception:
+            watts = None
+        self.rows.append((sm, self.max_mhz, bits, watts))
+
+    def _poll(self):
+        while not self.quit:
+            if self.keep:
+                try:
+                    self._nvml_row()
+                except Exception:
+                    pass
+            time.sleep(0.001)
 
     def _pump(self):
         for line in self.proc.stdout:
             if self.keep:
                 parts = [p.strip() for p in line.strip().split(",")]
                 if len(parts) >= 7:
-                    self.rows.append(parts)
+                    bits = sum(bit for (_, bit), v in zip(self.REASONS, parts[2:6]) if v.lower().startswith("active"))
+                    if parts[0].isdigit():
+                        self.rows.append((int(parts[0]), int(parts[1]) if parts[1].isdigit() else None, bits,
+                                          float(parts[6]) if parts[6].replace(".", "", 1).isdigit() else None))
 
     def start(self):
-        time.sleep(0.15)  # let nvidia-smi reach its sampling loop
+        if self.source == "nvidia-smi":
+            time.sleep(0.15)  # let nvidia-smi reach its sampling loop
         self.keep = True
+
+    def sample_now(self):
+        """one row from the calling thread"""
+        if self.nvml is not None and self.keep:
+            try:
+                self._nvml_row()
+            except Exception:
+                pass
 
     def stop(self):
         self.keep = False
+        self.quit = True
         if self.proc is not None:
             self.proc.terminate()
-        sm = sorted(int(r[0]) for r in self.rows if r[0].isdigit())
-        reasons = set()
-        for r in self.rows:
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[2:6]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        watts = [float(r[6]) for r in self.rows if r[6].replace(".", "", 1).isdigit()]
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None,
-                "sm_max_mhz": int(self.rows[0][1]) if self.rows and self.rows[0][1].isdigit() else None,
-                "reasons": sorted(reasons), "samples": len(self.rows), "power_w_max": max(watts) if watts else None}
+        rows = list(self.rows)
+        sm = sorted(r[0] for r in rows)
+        bits = 0
+        for r in rows:
+            bits |= r[2]
+        watts = [r[3] for r in rows if r[3] is not None]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": rows[0][1] if rows else None,
+                "reasons": sorted(name for name, bit in self.REASONS if bits & bit), "samples": len(rows),
+                "power_w_max": max(watts) if watts else None, "source": self.source}
 
 
 def measured_traffic(env, precision, n):
@@ -420,7 +477,7 @@ def run_b200(args, rank, world):
     batch.read_stats(clear=True)
     l0 = batch.launch_count()
 
-    sampler = ClockSampler(local) if rank == 0 else None
+    sampler = ClockSampler(local, getattr(torch.cuda.get_device_properties(local), "uuid", None)) if rank == 0 else None
     if sampler:
         sampler.start()
     barrier()
@@ -436,6 +493,8 @@ def run_b200(args, rank, world):
             dist.all_reduce(reduced)
             n_reductions += 1
     e1.record()
+    if sampler:
+        sampler.sample_now()  # everything is queued and the device is still working through it (the window ends on a fast-forward step)
     barrier()
     ms = e0.elapsed_time(e1)
     clocks = sampler.stop() if sampler else None
