@@ -586,8 +586,8 @@ def run_b200(args, rank, world):
                                                      "wire_*: the bytes a control step actually moves (profiles/r2_traffic.json)"},
                              "ff_kernel": {"ms_per_launch": ms_b / max(nk, 1), "share_of_step_time": ms_b / max(ms_a + ms_b, 1e-9),
                                            "ms_per_episode": ms_b / max(nk, 1) * (EPISODE_STEPS if args.env == "SwingRacket-v0" else 1),
-                                           "bound": "fp64 pipe / latency: ~160 FP64 instructions per physics substep, ~106 substeps per env "
-                                                    "on its 26th step; not memory-bound (profiles/r2_ff_kernel_f64_ncu.txt)"}}},
+                                           "bound": "instruction issue / fp64 pipe: ~335 instructions (160 FP64) per physics substep, ~106 substeps per env "
+                                                    "on its 26th step; not memory-bound (profiles/r2_ff_kernel_f64_ncu.txt, DESIGN.md 4.2)"}}},
             "e2e": {"value": total_envs * args.e2e_steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "steps": args.e2e_steps, "api": "TennisBatch.step_host -> tb_step_host: pinned host buffers in and out; the kernels read the actions from and write obs/reward/done to host memory over PCIe themselves (both directions concurrent with the compute)"},
             "gpu_launches": int(launches),
