@@ -608,7 +608,7 @@ __global__ void __launch_bounds__(kBlock, MINB ? MINB : StepMinBlocks<T, KIND>::
 // loop); the same work in barrier-separated phases 4.6 - 5.0 ms (every round of "contact, then fly on" paid the latency
 // of its longest chain and longest flight); roles: see profiles/.
 #ifndef TB_FF_SERVE_MIN
-#define TB_FF_SERVE_MIN 8
+#define TB_FF_SERVE_MIN 6
 #endif
 #ifndef TB_FF_SERVE_WAIT
 #define TB_FF_SERVE_WAIT 12
