@@ -587,21 +587,25 @@ __global__ void __launch_bounds__(kBlock, MINB ? MINB : StepMinBlocks<T, KIND>::
   pdl_trigger();
 }
 
-// Fast-forward continuation (SwingRacket only): one persistent launch (a CTA per resident slot) whose warps have roles:
+// Fast-forward continuation (SwingRacket only): one persistent launch (a CTA per resident slot) whose warps have roles.
+// Nothing in it waits for a particular other CTA: all work is claimed from counters and queues, so any subset of the CTAs
+// completes the launch (another stream may hold SMs).
 //
+//   prologue      the control substeps step_kernel deferred (ball within reach of something), 32 list entries per warp.
 //   flight warps  every LANE is a small state machine: claim an env, keep its flight state in registers and take ff_fast
 //                 substeps (a straight line, the court landing included) until the flight ends or a substep needs the full
 //                 treatment; then hand the env on through HBM (landed mark, or the dynamic full queue) and claim the next
-//                 one - from step_kernel's queue (longest flights first) and, once that is empty, from the late queue.
-//                 Leaving / claiming is done for several lanes of a warp at once.  A lane in an 800-substep flight
-//                 delays nobody, and no rare code ever enters these warps' instruction stream.
-//   server warps  (one in kServerStride CTAs' last warp) poll the full queues: generic substeps (ff_full: narrow phase,
-//                 contact solve, time-out) for one env per lane until ff_fast applies again; the env then goes to the
-//                 late queue, or is marked landed.  Contact chains (a ball rolling on the racket face takes dozens
-//                 of full substeps) therefore run concurrently with the bulk of the flights, and the long flight that
-//                 follows a late hit starts at once.
-//   everybody     when all envs have landed: the finishing pass - reward, statistics, outputs, auto-reset for every
-//                 env, coalesced like step_kernel.
+//                 one - from step_kernel's lists (balls the racket has hit or is about to first, plain free fall next, the
+//                 free-falling balls that move away from the racket last) and from the late queue (flights that go on after a
+//                 visit to the servers).  Leaving / claiming is done for several lanes of a warp at once.  A lane in an
+//                 800-substep flight delays nobody, and no rare code ever enters these warps' instruction stream.
+//   server warps  (all warps of every io.server_sm_stride-th SM; one warp in kServerStride CTAs when the grid does not fill the
+//                 device) poll the full queues: ff_contact_lean / ff_full (narrow phase, contact solve, time-out) for one env
+//                 per lane until ff_fast applies again; the env then goes to the late queue, or is marked landed.  Contact
+//                 chains (a ball rolling on the racket face takes dozens of full substeps) therefore run concurrently with
+//                 the bulk of the flights, and the long flight that follows a late hit starts at once.
+//   finishing     reward, statistics, outputs, auto-reset for every env that has landed, coalesced like step_kernel: done by
+//                 whichever flight warps have nothing to integrate, tile by tile, overlapping the tail of the flights.
 //
 // History (measured on B200, 1 Mi envs, f64): everything in one loop per lane 6.8 ms (every landing / claim /
 // contact stalled 31 other lanes and streamed ~40 KB of rare code through the instruction caches of the substep
