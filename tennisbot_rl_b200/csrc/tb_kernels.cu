@@ -1129,7 +1129,10 @@ __device__ __noinline__ void ff_server_warp(const Scene<T> &sc, const StepIO &io
 #endif
       step0 = L.step;
       last = 0;
-      r = ff_classify(sc, L);  // fills the lane's squared speeds; kFfFull, rounding apart
+      // no classification here: the lane that parked the env found it within reach of something, and the substep functions
+      // cope with a state that is just outside after the trip through HBM (3 % of a server iteration)
+      L.nb = dot3(L.bv, L.bv); L.nr = dot3(L.rv, L.rv); L.nw = dot3(L.wl, L.wl);
+      r = kFfFull;
       busy = true;
 #ifdef TB_FF_DIAG
       atomicAdd(ctr + 108, 1ULL); atomicAdd(ctr + 109, (unsigned long long)(clock64() - tl0));
